@@ -1,0 +1,322 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (/root/reference/MC-GRA) on CPU.
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+What is recorded (all float32 unless noted), per attack case:
+  inputs : features X, dense true adjacency (uint8), labels, victim weights, idx_attack, feature_adj,
+           label_adj is derived from labels, flags (measure, w1..w10, lr, eps, dataset, use*), num_edges
+  outputs: total loss of every iteration (the scalar `loss.backward()` is called on,
+           MC-GRA/topology_attack.py:274), x = adj_changes after every iteration's projection
+           (topology_attack.py:281-283), final adj_changes (after :301), final modified_adj (:322),
+           sklearn ROC-AUC (main.metric_pool semantics, main.py:66-75) and average precision.
+Function-level fixtures: normalize_adj_tensor, CudaCKA.*, utils.HSIC, hsic.*, dot_product_decode,
+gcn_parameterized.get_modified_adj.
+"""
+import argparse
+import os
+import random
+import sys
+import tempfile
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "mc-gra_b200"))
+
+import ref_shim  # noqa: E402
+
+ref = ref_shim.load()
+import synth  # noqa: E402  (our synthetic-graph generator; data only)
+from sklearn.metrics import auc, average_precision_score, roc_curve  # noqa: E402
+
+R_utils = ref["utils"]
+R_ta = ref["topology_attack"]
+R_gcn = ref["models.gcn"]
+R_hsic = ref["hsic"]
+R_gp = ref["gcn_parameterized"]
+
+
+def build_victim(X, W, c):
+    f = X.shape[1]
+    victim = R_gcn.GCN(nfeat=f, nclass=c, nhid=16, nlayer=2, dropout=0.5, weight_decay=5e-4, device="cpu")
+    with torch.no_grad():
+        victim.gc[0].weight.copy_(torch.from_numpy(W["W1"]))
+        victim.gc[0].bias.copy_(torch.from_numpy(W["b1"]))
+        victim.gc[1].weight.copy_(torch.from_numpy(W["W2"]))
+        victim.gc[1].bias.copy_(torch.from_numpy(W["b2"]))
+        victim.linear1.weight.copy_(torch.from_numpy(W["Wl"]))
+        victim.linear1.bias.copy_(torch.from_numpy(W["bl"]))
+    emb = R_gcn.embedding_GCN(nfeat=f, nhid=16, nlayer=2, device="cpu")
+    emb.gc = deepcopy(victim.gc)          # MC-GRA/main.py:185-190
+    victim.eval()
+    emb.eval()
+    return victim, emb
+
+
+def feature_adj_of(X, dataset):
+    """main.dot_product_decode (MC-GRA/main.py:44-55) -- module-level code there is not importable
+    (main.py runs argparse at import), so its 8 lines are re-evaluated with the same torch ops."""
+    Z = torch.from_numpy(X)
+    if dataset in ("cora", "citeseer", "AIDS"):
+        Z = torch.matmul(Z, Z.t())
+        return torch.sigmoid(torch.relu(Z - torch.eye(Z.shape[0])))
+    Z = torch.nn.functional.normalize(Z, p=2, dim=1)
+    Z = torch.matmul(Z, Z.t())
+    return torch.relu(Z - torch.eye(Z.shape[0]))
+
+
+def run_attack_case(name, n, f, c, measure, weights, lr_exp, epochs, dataset="cora", eps=0.0,
+                    use=(True, True, True), density=1e7, weight_sup=1.0, seed=15, gain=3.0, nlabel=1.0,
+                    mean_deg=4.5, graph=None, W=None, x0_scale=0.0):
+    g = graph or synth.make_graph(n, f, c, seed=seed, mean_deg=mean_deg)
+    n = g["labels"].shape[0]
+    X = g["features"]
+    f = X.shape[1]
+    A = synth.dense_adj(n, g["edges"])
+    labels = g["labels"]
+    c = int(labels.max()) + 1
+    W = W or synth.gcn_weights(f, 16, c, seed=seed, gain=gain)
+    victim, emb = build_victim(X, W, c)
+
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    idx_attack = np.array(random.sample(range(n), int(n * nlabel)))
+    num_edges = int(0.5 * density * A.sum() / n ** 2 * len(idx_attack) ** 2)   # main.py:247-248
+
+    adj_t = torch.from_numpy(A)
+    X_t = torch.from_numpy(X)
+    feature_adj = feature_adj_of(X, dataset)
+    with torch.no_grad():
+        emb.set_layers(2)
+        H_A2 = emb(X_t, adj_t)
+        Y_A = victim(X_t, adj_t)
+
+    class Args:
+        pass
+    args = Args()
+    args.max_eval = 100
+    args.lr = lr_exp
+    args.eps = eps
+    args.measure = measure
+    args.dataset = dataset
+    args.useH_A, args.useY_A, args.useY = use
+    for k in range(1, 11):
+        setattr(args, f"w{k}", weights.get(k, 0.0))
+    wp = tuple(weights.get(k, 0.0) for k in range(1, 11))
+
+    model = R_ta.PGDAttack(model=victim, embedding=emb, H_A=H_A2, Y_A=Y_A, nnodes=n, loss_type="CE", device="cpu")
+
+    P = n * (n - 1) // 2
+    x0 = np.zeros(P, np.float32)
+    if x0_scale > 0:     # non-zero start (API allows presetting adj_changes.data) so interior arithmetic is exercised
+        r0 = np.random.RandomState(seed + 77)
+        x0 = (r0.random_sample(P) * x0_scale * (r0.random_sample(P) < 0.5)).astype(np.float32)
+        model.adj_changes.data = torch.from_numpy(x0.copy())
+    losses, xs = [], []
+    orig_backward = torch.Tensor.backward
+
+    def rec_backward(self, *a, **k):
+        losses.append(float(self.detach().double()))
+        return orig_backward(self, *a, **k)
+
+    orig_proj = model.projection
+
+    def rec_proj(num_edges_):
+        orig_proj(num_edges_)
+        xs.append(model.adj_changes.detach().clone().numpy())
+
+    model.projection = rec_proj
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "saved_data"))
+        np.save(os.path.join(td, "saved_data", dataset + ".npy"),
+                (labels[:, None] == labels[None, :]).astype(np.float32))      # main.py:440-450
+        os.chdir(td)
+        torch.Tensor.backward = rec_backward
+        try:
+            model.attack(args, None, 10 ** lr_exp, 0, weight_sup, wp, feature_adj, 0, 0, 0,
+                         None, None, np.arange(min(8, n)), adj_t, X, np.zeros((n, n), np.float32), labels,
+                         idx_attack, num_edges, 0, epochs=epochs)
+        finally:
+            torch.Tensor.backward = orig_backward
+            os.chdir(cwd)
+    final = model.modified_adj.detach().numpy()
+    real = A.reshape(-1)
+    pred = final.reshape(-1)
+    fpr, tpr, _ = roc_curve(real, pred)
+    out = dict(
+        X=X, adj=A.astype(np.uint8), labels=labels, idx_attack=idx_attack.astype(np.int64),
+        feature_adj=feature_adj.numpy(), H_A2=H_A2.numpy(), Y_A=Y_A.numpy(),
+        num_edges=np.int64(num_edges), epochs=np.int64(epochs), lr_exp=np.float64(lr_exp), eps=np.float64(eps),
+        weight_sup=np.float64(weight_sup), weights=np.array(wp, dtype=np.float64),
+        measure=np.array(measure), dataset=np.array(dataset), use=np.array(use, dtype=np.bool_),
+        x0=x0, loss=np.array(losses, dtype=np.float64), x_iters=np.stack(xs).astype(np.float32),
+        x_final=model.adj_changes.detach().numpy().astype(np.float32),
+        modified_adj=final.astype(np.float32),
+        auc=np.float64(auc(fpr, tpr)), ap=np.float64(average_precision_score(real, pred)),
+        **{k: v for k, v in W.items()},
+    )
+    np.savez_compressed(os.path.join(HERE, f"attack_{name}.npz"), **out)
+    print(f"[golden] attack_{name}: n={n} measure={measure} loss[0..2]={losses[:3]} auc={out['auc']:.5f} "
+          f"ap={out['ap']:.5f} budget={num_edges} sum_x={xs[-1].sum():.3f}")
+
+
+def function_goldens():
+    rng = np.random.RandomState(7)
+    out = {}
+    n = 53
+    M = rng.random_sample((n, n)).astype(np.float32)
+    M = np.tril(M, -1)
+    M = M + M.T
+    M[:, 5] = 0
+    M[5, :] = 0
+    out["norm_in"] = M
+    out["norm_out"] = R_utils.normalize_adj_tensor(torch.from_numpy(M)).numpy()
+    # autograd of a scalar through normalize (used to pin the rho formula)
+    Mt = torch.from_numpy(M).clone().requires_grad_(True)
+    Gw = torch.from_numpy(rng.standard_normal((n, n)).astype(np.float32))
+    (R_utils.normalize_adj_tensor(Mt) * Gw).sum().backward()
+    out["norm_G"] = Gw.numpy()
+    out["norm_grad"] = Mt.grad.numpy()
+
+    X = rng.standard_normal((n, 16)).astype(np.float32)
+    Y = rng.standard_normal((n, 7)).astype(np.float32) * 0.5 + X[:, :7] * 0.3
+    out["hs_X"], out["hs_Y"] = X, Y
+    cka = R_utils.CudaCKA("cpu")
+    Xt, Yt = torch.from_numpy(X), torch.from_numpy(Y)
+    out["linear_HSIC"] = cka.linear_HSIC(Xt, Yt).numpy()
+    out["linear_CKA"] = cka.linear_CKA(Xt, Yt).numpy()
+    out["kernel_HSIC_s2"] = cka.kernel_HSIC(Xt, Yt, 2.0).numpy()
+    out["kernel_HSIC_med"] = cka.kernel_HSIC(Xt, Yt, None).numpy()
+    out["kernel_CKA_s2"] = cka.kernel_CKA(Xt, Yt, 2.0).numpy()
+    out["kernel_CKA_med"] = cka.kernel_CKA(Xt, Yt, None).numpy()
+    out["rbf_s2"] = cka.rbf(Xt, 2.0).numpy()
+    out["centering"] = cka.centering(torch.from_numpy(M)).numpy()
+    out["utils_HSIC_1_1"] = R_utils.HSIC(Xt, Yt, 1, 1).numpy()
+    out["utils_HSIC_5_3"] = R_utils.HSIC(Xt, Yt, 5, 3).numpy()
+    out["hsic_distmat"] = R_hsic.distmat(Xt).numpy()
+    out["hsic_sigma_est"] = np.float64(R_hsic.sigma_estimation(Xt, Yt[:, :7].repeat(1, 3)[:, :16]))
+    out["hsic_kernelmat_s1"] = R_hsic.kernelmat(Xt, 1.0).numpy()
+    out["hsic_kernelmat_auto"] = R_hsic.kernelmat(Xt, None).numpy()
+    out["hsic_regular_s1"] = R_hsic.hsic_regular(Xt, Yt, 1.0).numpy()
+    out["hsic_regular_auto"] = R_hsic.hsic_regular(Xt, Yt, None).numpy()
+    out["hsic_normalized_s1"] = R_hsic.hsic_normalized(Xt, Yt, 1.0).numpy()
+    out["hsic_normalized_auto"] = R_hsic.hsic_normalized(Xt, Yt, None).numpy()
+    out["hsic_distcorr"] = R_hsic.distcorr(Xt, 1.5).numpy()
+    out["hsic_compute_kernel"] = R_hsic.compute_kernel(Xt, Xt[:20] * 0.5).numpy()
+    out["hsic_mmd_s1"] = R_hsic.mmd(Xt, Xt * 0.7 + 0.1, 1.0).numpy()
+    out["hsic_mmd_auto"] = R_hsic.mmd(Xt, Xt * 0.7 + 0.1, None).numpy()
+    out["hsic_mmd_pxpy_s1"] = R_hsic.mmd_pxpy_pxy(Xt, Yt, 1.0, use_cuda=False).numpy()
+    out["hsic_mmd_pxpy_auto"] = R_hsic.mmd_pxpy_pxy(Xt, Yt, None, use_cuda=False).numpy()
+
+    # PGDAttack helpers on a tiny instance
+    g = synth.make_graph(41, 12, 3, seed=3)
+    W = synth.gcn_weights(12, 16, 3, seed=3, gain=3.0)
+    victim, emb = build_victim(g["features"], W, 3)
+    atk = R_ta.PGDAttack(model=victim, embedding=emb, nnodes=41, device="cpu")
+    x = rng.random_sample(41 * 40 // 2).astype(np.float32)
+    atk.adj_changes.data = torch.from_numpy(x)
+    out["pa_x"] = x
+    out["pa_expand"] = atk.get_modified_adj(torch.zeros(41, 41)).detach().numpy()
+    Z = rng.standard_normal((41, 16)).astype(np.float32)
+    Z[3] = 0
+    out["pa_Z"] = Z
+    out["pa_decode"] = atk.dot_product_decode(torch.from_numpy(Z)).numpy()
+    for ds, use in (("cora", (1, 1, 1)), ("citeseer", (1, 1, 1)), ("brazil", (1, 1, 1)), ("polblogs", (1, 1, 1)),
+                    ("polblogs", (1, 0, 1)), ("usair", (0, 0, 1)), ("usair", (1, 1, 0)), ("usair", (1, 0, 1)),
+                    ("usair", (1, 1, 1)), ("AIDS", (0, 0, 0))):
+        class A:
+            pass
+        atk.args = A()
+        atk.args.dataset = ds
+        atk.args.useH_A, atk.args.useY_A, atk.args.useY = [bool(u) for u in use]
+        out[f"pa_decode2_{ds}_{use[0]}{use[1]}{use[2]}"] = atk.dot_product_decode2(torch.from_numpy(Z)).numpy()
+    # bisection / projection with an active budget
+    atk.adj_changes.data = torch.from_numpy(x * 1.7 - 0.2)
+    atk.projection(37)
+    out["pa_proj_in"] = x * 1.7 - 0.2
+    out["pa_proj_out_37"] = atk.adj_changes.detach().numpy().copy()
+    atk.adj_changes.data = torch.from_numpy(x * 1.7 - 0.2)
+    atk.projection(100000)
+    out["pa_proj_out_big"] = atk.adj_changes.detach().numpy().copy()
+    out["pa_entropy_in"] = M
+    out["pa_entropy"] = R_ta.Info_entropy(torch.from_numpy(M)).numpy()
+    out["pa_kl"] = atk.calc_kl(torch.from_numpy(M), torch.from_numpy(M.T * 0.5 + 0.1)).numpy()
+    out["pa_dp"] = atk.dot_product(Xt, Yt[:, :7]).numpy() if False else atk.dot_product(Xt, Xt * 0.3 + 1).numpy()
+    # GCN forward
+    Xg = torch.from_numpy(g["features"])
+    Ag = torch.from_numpy(synth.dense_adj(41, g["edges"]))
+    out["gcn_X"], out["gcn_A"] = g["features"], synth.dense_adj(41, g["edges"])
+    for k, v in W.items():
+        out["gcn_" + k] = v
+    out["gcn_out_raw"] = victim(Xg, Ag).detach().numpy()
+    out["gcn_out_norm"] = victim(Xg, R_utils.normalize_adj_tensor(Ag)).detach().numpy()
+    emb.set_layers(1)
+    out["emb1_raw"] = emb(Xg, Ag).detach().numpy()
+    emb.set_layers(2)
+    out["emb2_raw"] = emb(Xg, Ag).detach().numpy()
+    # gcn_parameterized.get_modified_adj forward (MC-GRA/gcn_parameterized.py:406-416)
+    gp = R_gp.PGDAttack.__new__(R_gp.PGDAttack)
+    torch.nn.Module.__init__(gp)
+    gp.device = "cpu"
+    gp.features = Xg
+    gp.gc = deepcopy(victim.gc)
+    out["gp_modified_adj"] = gp.get_modified_adj(torch.zeros(41, 41)).detach().numpy()
+    # AUC / AP with ties
+    lab = (rng.random_sample(4000) < 0.1).astype(np.float32)
+    sc = np.round(rng.random_sample(4000) * 50 + lab * 8).astype(np.float32) / 50
+    fpr, tpr, _ = roc_curve(lab, sc)
+    out["auc_labels"], out["auc_scores"] = lab, sc
+    out["auc_value"] = np.float64(auc(fpr, tpr))
+    out["ap_value"] = np.float64(average_precision_score(lab, sc))
+    np.savez_compressed(os.path.join(HERE, "functions.npz"), **out)
+    print("[golden] functions.npz written:", len(out), "arrays")
+
+
+PROFILE_A = {1: 0.01, 6: 10, 7: 10, 9: 10, 10: 1000}                    # MC-GRA/README.md:29 (Cora, MSELoss)
+PROFILE_B = {1: 0.01, 2: 0.01, 6: 10000, 7: 100, 9: 0.001, 10: 1000}    # MC-GRA/README.md:90 (Polblogs, HSIC)
+PROFILE_C = {1: 100, 2: 1e-4, 6: 1e-3, 9: 1000, 10: 1e-3}               # MC-GRA/README.md:59 (Citeseer, KL)
+ALLW = {1: 0.5, 2: 0.3, 6: 2.0, 7: 3.0, 9: 1.5, 10: 50.0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    if not a.only or a.only == "functions":
+        function_goldens()
+    cases = [
+        dict(name="mse_A_n37", n=37, f=24, c=4, measure="MSELoss", weights=PROFILE_A, lr_exp=-2, epochs=6),
+        dict(name="mse_A_n150", n=150, f=24, c=4, measure="MSELoss", weights=PROFILE_A, lr_exp=-2, epochs=8, x0_scale=0.4),
+        dict(name="mse_all_n150", n=150, f=24, c=4, measure="MSELoss", weights=ALLW, lr_exp=-1.5, epochs=6, x0_scale=0.3),
+        dict(name="mse_budget_n150", n=150, f=24, c=4, measure="MSELoss", weights=ALLW, lr_exp=-1, epochs=6,
+             density=1.0, mean_deg=12.0, x0_scale=0.5),
+        dict(name="mse_nosup_n90", n=90, f=20, c=3, measure="MSELoss", weights={1: 1000, 2: 0.001, 6: 0.1, 7: 0.1, 9: 100, 10: 100},
+             lr_exp=-2, epochs=5, weight_sup=0.0, use=(True, True, False), gain=1.0),
+        dict(name="kl_C_n150", n=150, f=24, c=4, measure="KL", weights=PROFILE_C, lr_exp=-1.5, epochs=6, dataset="citeseer"),
+        dict(name="kl_all_n90", n=90, f=20, c=3, measure="KL", weights=ALLW, lr_exp=-1.5, epochs=5, dataset="citeseer", x0_scale=0.3),
+        dict(name="hsic_B_n150", n=150, f=24, c=4, measure="HSIC", weights=PROFILE_B, lr_exp=-2.5, epochs=6, dataset="polblogs", x0_scale=0.3),
+        dict(name="hsic_all_n90", n=90, f=20, c=3, measure="HSIC", weights={1: 1e-4, 2: 1e-4, 6: 2.0, 7: 3.0, 9: 1e-3, 10: 5.0},
+             lr_exp=-2, epochs=5, x0_scale=0.5),
+        dict(name="cka_n90", n=90, f=20, c=3, measure="CKA", weights={1: 0.01, 2: 0.01, 6: 100, 7: 1.0, 9: 1.0, 10: 1.0},
+             lr_exp=-2, epochs=5, dataset="polblogs", use=(False, True, True)),
+        dict(name="dp_n90", n=90, f=20, c=3, measure="DP", weights={1: 1e-3, 2: 1e-3, 6: 10, 7: 1.0, 9: 0.1, 10: 1.0},
+             lr_exp=-2, epochs=5, dataset="brazil", x0_scale=0.3),
+        dict(name="mse_sub_n90", n=90, f=20, c=3, measure="MSELoss", weights=PROFILE_A, lr_exp=-2, epochs=5, nlabel=0.6,
+             dataset="usair", use=(False, False, True)),
+    ]
+    for cs in cases:
+        if a.only and a.only not in cs["name"]:
+            continue
+        run_attack_case(**cs)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,118 @@
+"""Pin the CPU oracle (oracle/pgd_oracle.py) against fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pgd_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN, "attack_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def fn():
+    return np.load(os.path.join(GOLDEN, "functions.npz"))
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(a, b, rtol=2e-5, atol=1e-6):
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=atol)
+
+
+def test_normalize_value_and_grad(fn):
+    M = T(fn["norm_in"])
+    close(O.normalize(M), fn["norm_out"], rtol=1e-6, atol=1e-7)
+    Mt = M.clone().requires_grad_(True)
+    (O.normalize(Mt) * T(fn["norm_G"])).sum().backward()
+    close(Mt.grad, fn["norm_grad"], rtol=1e-5, atol=1e-6)
+
+
+def test_cka_family(fn):
+    X, Y = T(fn["hs_X"]), T(fn["hs_Y"])
+    close(O.linear_hsic(X, Y), fn["linear_HSIC"])
+    close(O.linear_cka(X, Y), fn["linear_CKA"])
+    close(O.kernel_hsic(X, Y, 2.0), fn["kernel_HSIC_s2"])
+    close(O.kernel_hsic(X, Y, None), fn["kernel_HSIC_med"])
+    close(O.kernel_cka(X, Y, 2.0), fn["kernel_CKA_s2"])
+    close(O.kernel_cka(X, Y, None), fn["kernel_CKA_med"])
+    close(O.rbf(X, 2.0), fn["rbf_s2"])
+    close(O.centering(T(fn["norm_in"])), fn["centering"], atol=1e-6)
+
+
+def test_gaussian_hsic_family(fn):
+    X, Y = T(fn["hs_X"]), T(fn["hs_Y"])
+    close(O.gaussian_hsic(X, Y, 1, 1), fn["utils_HSIC_1_1"])
+    close(O.gaussian_hsic(X, Y, 5, 3), fn["utils_HSIC_5_3"])
+    close(O.hs_distmat(X), fn["hsic_distmat"], atol=1e-5)
+    close(O.hs_kernelmat(X, 1.0), fn["hsic_kernelmat_s1"], atol=1e-6)
+    close(O.hs_kernelmat(X, None), fn["hsic_kernelmat_auto"], atol=1e-6)
+    close(O.hs_hsic_regular(X, Y, 1.0), fn["hsic_regular_s1"])
+    close(O.hs_hsic_regular(X, Y, None), fn["hsic_regular_auto"])
+    close(O.hs_hsic_normalized(X, Y, 1.0), fn["hsic_normalized_s1"])
+    close(O.hs_hsic_normalized(X, Y, None), fn["hsic_normalized_auto"])
+    close(O.hs_distcorr(X, 1.5), fn["hsic_distcorr"])
+    close(O.hs_compute_kernel(X, X[:20] * 0.5), fn["hsic_compute_kernel"])
+    close(O.hs_mmd(X, X * 0.7 + 0.1, 1.0), fn["hsic_mmd_s1"], atol=1e-6)
+    close(O.hs_mmd(X, X * 0.7 + 0.1, None), fn["hsic_mmd_auto"], atol=1e-6)
+    close(O.hs_mmd_pxpy_pxy(X, Y, 1.0), fn["hsic_mmd_pxpy_s1"], atol=1e-7)
+    close(O.hs_mmd_pxpy_pxy(X, Y, None), fn["hsic_mmd_pxpy_auto"], atol=1e-7)
+
+
+def test_attack_helpers(fn):
+    x = T(fn["pa_x"])
+    close(O.expand(x, 41), fn["pa_expand"], rtol=0, atol=0)
+    close(O.decode_tril(T(fn["pa_Z"])), fn["pa_decode"], rtol=1e-6, atol=1e-7)
+    for key in fn.files:
+        if key.startswith("pa_decode2_"):
+            _, _, ds, use = key.split("_")
+            got = O.decode2(T(fn["pa_Z"]), ds, use[0] == "1", use[1] == "1", use[2] == "1")
+            close(got, fn[key], rtol=1e-6, atol=1e-6)
+    close(O.projection(T(fn["pa_proj_in"]), 37), fn["pa_proj_out_37"], rtol=0, atol=0)
+    close(O.projection(T(fn["pa_proj_in"]), 100000), fn["pa_proj_out_big"], rtol=0, atol=0)
+    close(O.info_entropy(T(fn["pa_entropy_in"])), fn["pa_entropy"], rtol=1e-6)
+    M = T(fn["pa_entropy_in"])
+    close(O.calc_kl(M, M.t() * 0.5 + 0.1), fn["pa_kl"], rtol=1e-5)
+    X = T(fn["hs_X"])
+    close(O.dot_product(X, X * 0.3 + 1), fn["pa_dp"], rtol=1e-6)
+
+
+def test_gcn_forward(fn):
+    Wt = {k: T(fn["gcn_" + k]) for k in ("W1", "b1", "W2", "b2", "Wl", "bl")}
+    X, A = T(fn["gcn_X"]), T(fn["gcn_A"])
+    close(O.victim(X, A, Wt), fn["gcn_out_raw"], rtol=1e-5, atol=1e-6)
+    close(O.victim(X, O.normalize(A), Wt), fn["gcn_out_norm"], rtol=1e-5, atol=1e-6)
+    close(O.embed(X, A, Wt, 1), fn["emb1_raw"], rtol=1e-5, atol=1e-6)
+    close(O.embed(X, A, Wt, 2), fn["emb2_raw"], rtol=1e-5, atol=1e-6)
+    # gcn_parameterized.get_modified_adj == gram of row-normalised relu-GCN(X, I)
+    Z = torch.nn.functional.normalize(O.embed(X, torch.eye(X.shape[0]), Wt, 2), p=2, dim=1)
+    close(Z @ Z.t(), fn["gp_modified_adj"], rtol=1e-5, atol=1e-6)
+
+
+def test_auc_ap_sklearn_semantics(fn):
+    assert abs(O.roc_auc(fn["auc_labels"], fn["auc_scores"]) - float(fn["auc_value"])) < 1e-12
+    assert abs(O.average_precision(fn["auc_labels"], fn["auc_scores"]) - float(fn["ap_value"])) < 1e-12
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_attack_loop_matches_reference(case):
+    d = np.load(os.path.join(GOLDEN, f"attack_{case}.npz"))
+    prob, cfg = O.problem_from_npz(d)
+    res = O.attack(prob, cfg, int(d["epochs"]), x0=T(d["x0"]))
+    ref_loss = d["loss"]
+    got = np.array(res["loss"])
+    # north_star tolerance: per-iteration loss within 1e-4 relative
+    np.testing.assert_allclose(got, ref_loss, rtol=1e-4)
+    xs = np.stack([x.numpy() for x in res["x_iters"]])
+    assert np.max(np.abs(xs - d["x_iters"])) < 2e-4
+    np.testing.assert_allclose(res["x_final"].numpy(), d["x_final"], rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(res["modified_adj"].numpy(), d["modified_adj"], rtol=1e-3, atol=1e-3)
+    real = d["adj"].reshape(-1).astype(np.float32)
+    assert abs(O.roc_auc(real, res["modified_adj"].numpy().reshape(-1)) - float(d["auc"])) < 1e-3
+    assert abs(O.average_precision(real, res["modified_adj"].numpy().reshape(-1)) - float(d["ap"])) < 1e-3
