@@ -1,0 +1,210 @@
+/*
+ * mcgra.h -- C ABI of libmcgra_b200.so: hand-written sm_100a CUDA kernels for the MC-GRA PGD attack
+ * inner loop (reference: /root/reference/MC-GRA/topology_attack.py:161-324 and the helpers it calls).
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); each entry point below replaces the ATen
+ * call sequence of the reference lines it cites.  The Python host (mc-gra_b200/) binds these with ctypes.
+ *
+ * Conventions
+ *   - extern "C"; every function returns int: 0 ok, >0 a cudaError_t, <0 an argument error.
+ *   - never allocates, never synchronises, never throws: the caller owns every buffer, all work is
+ *     enqueued on the cudaStream_t passed as `void* stream`.
+ *   - fp32 data, int64 sizes, device pointers unless a parameter says "host".
+ *   - PACKED vector  : reference layout, strict lower triangle row-major, k = i(i-1)/2 + j, i > j
+ *                      (topology_attack.py:372-374).
+ *   - TILED triangle : working layout of the loop.  T = ceil(n/128) tile rows; tile (I,J), J <= I, is a
+ *                      contiguous row-major 128x128 fp32 block at element offset
+ *                      (I(I+1)/2 + J - tr0(tr0+1)/2) * 16384 of a buffer that holds tile rows [tr0,tr1)
+ *                      (one rank's shard).  Entry (a,b) of the tile is element (i,j) = (128I+a, 128J+b);
+ *                      it is "valid" iff j < i < n, every other entry is kept at 0.
+ *   - PARAMETER VIEW : the optimised parameter is stored lazily as the un-projected Adam output x'
+ *                      together with a device scalar mu; the parameter value is clamp(x' - mu, 0, 1)
+ *                      (topology_attack.py:338-347).  raw != 0 means "the buffer is a user-provided raw
+ *                      parameter": value = x', forward uses clamp(x',0,1) with the clamp's gradient mask
+ *                      (topology_attack.py:474-478).
+ */
+#ifndef MCGRA_H
+#define MCGRA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCGRA_TILE 128
+#define MCGRA_HID 16            /* GCN hidden width, hard-coded in the reference (main.py:175) */
+#define MCGRA_MAXC 32           /* max classes handled by the node kernels */
+
+/* measures for the n x n terms c1/c2 and the n x d terms c9/c10 (topology_attack.py:190-208) */
+enum { MCGRA_M_NONE = 0, MCGRA_M_MSE = 1, MCGRA_M_KL = 2, MCGRA_M_HSIC = 3, MCGRA_M_CKA = 4, MCGRA_M_DP = 5 };
+
+/* slots of the per-iteration double-precision accumulator block `acc` (32 doubles).
+ * Slots 0-15 are accumulated by the tile kernels over one rank's shard (all-reduced across ranks);
+ * slots 16-31 by the node kernels, which every rank runs redundantly (NOT reduced).                 */
+enum {
+  MCGRA_ACC_C1 = 1,       /* c1 term, off-diagonal part, fully scaled (w1 * 1000 * 100 * measure)  */
+  MCGRA_ACC_C2 = 2,
+  MCGRA_ACC_C6 = 3,
+  MCGRA_ACC_C7 = 4,
+  MCGRA_ACC_SUMCLAMP = 8, /* sum clamp(x',0,1) after the Adam step (budget test, :339)            */
+  MCGRA_ACC_SUMSQ = 9,    /* sum of squares of the projected parameter (for 0.001*||x||, :172)    */
+  MCGRA_ACC_NLL = 16,     /* sum_i w_i * -log p(y_i)   (w_i already divided by |idx|)             */
+  MCGRA_ACC_C9 = 17,
+  MCGRA_ACC_C10 = 18,
+  MCGRA_ACC_C1D = 19,     /* diagonal (A_hat_ii = r_i^2) parts of the element-wise terms           */
+  MCGRA_ACC_C2D = 20,
+  MCGRA_ACC_C6D = 21,
+  MCGRA_ACC_C7D = 22,
+  MCGRA_ACC_N = 32
+};
+
+int mcgra_version(void);
+int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */
+
+/* ---- layout (replaces torch.tril_indices + index_put + m+m.t(), topology_attack.py:365-379) ---- */
+int mcgra_tril_to_tiles(const float* packed, int64_t n, int tr0, int tr1, float* tiles, void* stream);
+int mcgra_tiles_to_tril(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
+                        float* packed, void* stream);
+/* lower triangle of a dense row-major matrix (leading dimension ld) -> tiles; symmetrize!=0 stores
+ * (F_ij+F_ji)/2; diag (may be NULL) receives F_ii for the rows of [tr0,tr1).                        */
+int mcgra_dense_to_tiles(const float* dense, int64_t ld, int64_t n, int tr0, int tr1, int symmetrize,
+                         float* tiles, float* diag, void* stream);
+/* symmetric dense expansion with zero diagonal (get_modified_adj, :365-379); writes rows AND mirrored
+ * columns of the owned tile rows into dense[n x ld]; caller zero-fills dense first.                 */
+int mcgra_tiles_to_dense(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
+                         float* dense, int64_t ld, void* stream);
+
+/* ---- degree: d[i] += sum_j M_ij over the shard (utils.py:224-225); caller pre-fills d with 1 ---- */
+int mcgra_degree(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, float* d,
+                 void* stream);
+
+/* ---- propagation Y += M * B (GraphConvolution.forward's spmm, models/gcn.py:42, and its transpose
+ *      in backward); M symmetric zero-diagonal from the tiles; B,Y row-major [n x K], K in {16,32}.
+ *      Caller zero-fills Y.  Optional fused element-wise terms of the layer-1 pass (c1 MSE/KL against
+ *      feature_adj, c6 entropy; topology_attack.py:212-232,44-47): values into acc[], the row sums
+ *      eps_row[i] += sum_j (e'_ij+e'_ji) M_ij r_j needed by the degree gradient.     */
+typedef struct {
+  const float* r;         /* [n] D^-1/2                                                              */
+  const float* Ftiles;    /* tiled feature_adj (same shard) or NULL                                  */
+  const float* lseA;      /* [n] log sum_j exp(A_hat_ij)  (KL only)                                   */
+  const float* lseF;      /* [n] log sum_j exp(F_ij)      (KL only)                                   */
+  int measure;            /* MCGRA_M_NONE / MCGRA_M_MSE / MCGRA_M_KL for c1                           */
+  float k1;               /* c1 scale: w1*1e5/n^2 (MSE) or w1*1e5/n (KL); sign included               */
+  float k6;               /* c6 scale: -w6*1000/n^2, 0 = off                                          */
+  double* acc;            /* accumulator block (slots C1, C6)                                         */
+  float* eps_row;         /* [n]                                                                      */
+} mcgra_elem_args;
+int mcgra_propagate(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
+                    const float* B, int K, float* Y, const mcgra_elem_args* elem, void* stream);
+/* row log-sum-exp of A_hat over the shard: sumexp[i] += sum_{j != i} exp(r_i M_ij r_j) (KL measure) */
+int mcgra_row_sumexp(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
+                     const float* r, float* sumexp, void* stream);
+
+/* ---- node-level stages (n x 16 work of GCN.forward / embedding_GCN.forward, models/gcn.py:71-76,
+ *      164-174, their hand-derived backward, nll (:326-336) and the n x d measure terms c9/c10) ---- */
+typedef struct {
+  int64_t n;
+  int nclass;
+  const float *W2, *b1, *b2, *Wl, *bl;   /* victim weights: W2[16x16], Wl[c x 16] (nn.Linear layout)  */
+  const float* S1;                       /* X W1 [n x 16] (constant)                                   */
+  const int64_t* labels;                 /* [n]                                                        */
+  const float* wmult;                    /* [n] multiplicity of node i in idx_attack / |idx_attack|    */
+  const float* HA;                       /* H_A target [n x 16]                                        */
+  const float* YA;                       /* Y_A target [n x c] (log-probabilities, :264-271)           */
+  float* d;                              /* [n] degree (1 + row sum)                                   */
+  float* r;                              /* [n]                                                        */
+  float *B1, *Y1, *B2, *Y2, *B3, *Y3;    /* [n x 32] operands / results of the three 32-wide passes    */
+  float *B4, *Y4;                        /* [n x 16] operand / result of the degree-gradient pass      */
+  float *S2, *T2, *H2, *dZ2, *dZ1, *dQ1, *dQ2, *demd, *zhat, *dzhat;   /* [n x 16]                   */
+  float* inv_norm;                       /* [n] 1/max(||em||,1e-12)                                    */
+  uint32_t* masks;                       /* [n] relu masks: bits 0-15 H1>0, 16-31 E1>0                 */
+  uint32_t* masks2;                      /* [n] bits 0-15 Z2>0, 16-31 em>0                             */
+  float* eps_row;                        /* [n] element-wise degree-gradient row sums                  */
+  float* rho;                            /* [n] degree gradient                                        */
+  float* Wt;                             /* [128 x npad] transposed fold factors [U|V]                 */
+  const float* Fdiag;                    /* [n] diagonal of feature_adj (or NULL)                      */
+  double* acc;                           /* accumulator block                                          */
+  int measure;                           /* measure for c1 (diag part) and c9/c10                      */
+  float weight_sup;
+  float k1, k2, k6, k7;                  /* scaled weights of the n x n element-wise terms             */
+  float w9, w10;                         /* raw weights of c9 / c10 (sign for HSIC included)           */
+  int64_t npad;
+  /* state reset done by mcgra_node_rho for the fold that follows it */
+  float* d_next;                         /* [n] filled with d_fill (1 on rank 0, 0 elsewhere)          */
+  float d_fill;
+  double* acc_next;                      /* [MCGRA_ACC_N] zeroed                                       */
+  float* minmax;                         /* [2] set to {+inf, -inf}                                    */
+  const float* lseA;                     /* KL: [n] log sum_j exp(A_hat_ij) incl. diagonal (or NULL)   */
+  const float* lseF;                     /* KL: [n] log sum_j exp(F_ij)                                */
+} mcgra_node_args;
+int mcgra_node_pre(const mcgra_node_args* a, void* stream);    /* r = d^-1/2 ; B1 = [r*S1 | S1]       */
+int mcgra_node_mid(const mcgra_node_args* a, void* stream);    /* after pass 1: H1,E1,S2,T2,B2        */
+int mcgra_node_head(const mcgra_node_args* a, void* stream);   /* after pass 2: heads, losses, dZ2... */
+int mcgra_node_bwd2(const mcgra_node_args* a, void* stream);   /* dQ2, B3                              */
+int mcgra_node_bwd1(const mcgra_node_args* a, void* stream);   /* after pass 3: dZ1,dQ1,B4             */
+int mcgra_node_rho(const mcgra_node_args* a, void* stream);    /* after pass 4: rho, fold factors Wt   */
+
+/* ---- pair pass over the decode gram M1 = relu(zhat zhat^T) (dot_product_decode :414-419,
+ *      get_modified_adj_after :381-395): c7 entropy (:233-236) and c2 MSE (:221-229) values, their
+ *      gradient w.r.t. zhat (dzhat, caller zero-fills) and c2's eps_row contribution.              */
+int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
+                const float* zhat, const float* r, float k7, float k2, float* dzhat, float* eps_row,
+                double* acc, void* stream);
+
+/* ---- gradient fold + Adam + box clamp (loss.backward()+optimizer.step()+clamp, :274-283) ---- */
+typedef struct {
+  int64_t n;
+  int64_t npad;
+  const float* Wt;        /* [128 x npad] fold factors                                               */
+  const float* r;         /* [n]                                                                      */
+  const float* rho;       /* [n]                                                                      */
+  const float* Ftiles;    /* tiled feature_adj or NULL                                                */
+  const float* lseA;      /* KL */
+  const float* lseF;      /* KL */
+  const float* zhat;      /* [n x 16] (c2 only) or NULL                                               */
+  int measure;            /* c1 measure                                                               */
+  float k1, k6, k2;       /* element-wise scales as above                                             */
+  float norm_coef;        /* weight_sup * 0.001                                                       */
+  float lr, beta1, beta2, adam_eps;
+  int step;               /* 1-based Adam step                                                        */
+  const double* acc_prev; /* accumulator block of the state the gradient was taken at (SUMSQ)         */
+  double* acc_next;       /* receives SUMCLAMP, SUMSQ, XMIN, XMAX of the new x'                       */
+  float* d_next;          /* [n] += row/col sums of clamp(x',0,1) (caller pre-fills with 1)           */
+} mcgra_fold_args;
+/* minmax: device float[2] = {min x', max x'} (bisection bracket, :340-341); reset by mcgra_node_rho          */
+int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const float* mu, int raw,
+                    const mcgra_fold_args* a, float* minmax, void* stream);
+
+/* ---- budget projection by bisection on device (projection/bisection, :338-347, 397-412) ----
+ * state[8] floats on device: a, b, mu, done, active, ... ; one call = 3 halvings evaluated in one
+ * pass over x' (7 candidate midpoints, the same fp32 midpoints the scalar loop would visit).       */
+int mcgra_bisect_init(const double* acc, const float* minmax, double budget, float* state, float* mu,
+                      void* stream);
+int mcgra_bisect_pass(const float* tiles, int64_t n, int tr0, int tr1, float epsilon, const float* state,
+                      double* cand_sums /* device [7], zero on entry */, void* stream);
+int mcgra_bisect_update(double budget, float epsilon, float* state, double* cand_sums, float* mu,
+                        void* stream);
+/* after the last pass: recompute SUMSQ and the degree of the projected parameter (only if active);
+ * reset != 0 first discards the fold's mu = 0 statistics (d_next = 1, SUMSQ = 0).                   */
+int mcgra_bisect_finish(const float* tiles, int64_t n, int tr0, int tr1, const float* state,
+                        const float* mu, double* acc_next, float* d_next, int reset, void* stream);
+
+/* ---- finalisation (topology_attack.py:300-322) ---- */
+/* x_final tiles = relu(zf_i . zf_j) for j<i (dot_product_decode of the last embedding)              */
+int mcgra_decode_to_tiles(const float* zhat, int64_t n, int tr0, int tr1, float* tiles, void* stream);
+/* one gram term of the ensemble: out[i,j] (+)= f(Z_i . Z_j) with the dataset's decode2 variant
+ * (dot_product_decode2, :421-467): variant 0 sigmoid(relu(g - I)), 1 relu(g - I),
+ * 2 relu(g/rownorm_i - I) (rownorm = ||row i of ZZ^T||, given).                                     */
+int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const float* rownorm,
+                          float* out, int64_t ld, int64_t row0, int64_t row1, void* stream);
+/* out[i,j] += (labels[i]==labels[j])                                                                */
+int mcgra_label_accumulate(const int64_t* labels, int64_t n, float* out, int64_t ld, int64_t row0,
+                           int64_t row1, void* stream);
+
+/* out += in (dense, `count` floats); F.normalize(Z, p, dim=1) with eps 1e-12                          */
+int mcgra_dense_add(float* out, const float* in, int64_t count, void* stream);
+int mcgra_row_normalize(const float* Z, int64_t n, int d, float p, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

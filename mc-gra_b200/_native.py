@@ -1,0 +1,139 @@
+"""ctypes binding of libmcgra_b200.so (the C ABI declared in include/mcgra.h).
+
+There is no fallback: if the shared library is missing or a call fails this module raises.  The library
+is built in-tree by `build_native.py` (nvcc, sm_100a); `__graft_entry__.build()` calls it.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmcgra_b200.so")
+
+TILE = 128
+HID = 16
+MAXC = 32
+ACC_N = 32
+M_NONE, M_MSE, M_KL, M_HSIC, M_CKA, M_DP = 0, 1, 2, 3, 4, 5
+ACC = dict(C1=1, C2=2, C6=3, C7=4, SUMCLAMP=8, SUMSQ=9, NLL=16, C9=17, C10=18, C1D=19, C2D=20, C6D=21, C7D=22)
+
+c_fp = C.c_void_p     # device float* (passed as integer address)
+i64 = C.c_int64
+
+
+class ElemArgs(C.Structure):
+    _fields_ = [("r", c_fp), ("Ftiles", c_fp), ("lseA", c_fp), ("lseF", c_fp), ("measure", C.c_int),
+                ("k1", C.c_float), ("k6", C.c_float), ("acc", c_fp), ("eps_row", c_fp)]
+
+
+class NodeArgs(C.Structure):
+    _fields_ = [("n", i64), ("nclass", C.c_int),
+                ("W2", c_fp), ("b1", c_fp), ("b2", c_fp), ("Wl", c_fp), ("bl", c_fp),
+                ("S1", c_fp), ("labels", c_fp), ("wmult", c_fp), ("HA", c_fp), ("YA", c_fp),
+                ("d", c_fp), ("r", c_fp),
+                ("B1", c_fp), ("Y1", c_fp), ("B2", c_fp), ("Y2", c_fp), ("B3", c_fp), ("Y3", c_fp),
+                ("B4", c_fp), ("Y4", c_fp),
+                ("S2", c_fp), ("T2", c_fp), ("H2", c_fp), ("dZ2", c_fp), ("dZ1", c_fp), ("dQ1", c_fp),
+                ("dQ2", c_fp), ("demd", c_fp), ("zhat", c_fp), ("dzhat", c_fp),
+                ("inv_norm", c_fp), ("masks", c_fp), ("masks2", c_fp), ("eps_row", c_fp), ("rho", c_fp),
+                ("Wt", c_fp), ("Fdiag", c_fp), ("acc", c_fp),
+                ("measure", C.c_int), ("weight_sup", C.c_float),
+                ("k1", C.c_float), ("k2", C.c_float), ("k6", C.c_float), ("k7", C.c_float),
+                ("w9", C.c_float), ("w10", C.c_float),
+                ("npad", i64),
+                ("d_next", c_fp), ("d_fill", C.c_float), ("acc_next", c_fp), ("minmax", c_fp),
+                ("lseA", c_fp), ("lseF", c_fp)]
+
+
+class FoldArgs(C.Structure):
+    _fields_ = [("n", i64), ("npad", i64), ("Wt", c_fp), ("r", c_fp), ("rho", c_fp), ("Ftiles", c_fp),
+                ("lseA", c_fp), ("lseF", c_fp), ("zhat", c_fp), ("measure", C.c_int),
+                ("k1", C.c_float), ("k6", C.c_float), ("k2", C.c_float), ("norm_coef", C.c_float),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp)]
+
+
+_SIGS = {
+    "mcgra_version": (C.c_int, []),
+    "mcgra_tiles_in_rows": (i64, [C.c_int, C.c_int]),
+    "mcgra_tril_to_tiles": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, c_fp]),
+    "mcgra_tiles_to_tril": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp]),
+    "mcgra_dense_to_tiles": (C.c_int, [c_fp, i64, i64, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp]),
+    "mcgra_tiles_to_dense": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, i64, c_fp]),
+    "mcgra_degree": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp]),
+    "mcgra_propagate": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, C.c_int, c_fp,
+                                  C.POINTER(ElemArgs), c_fp]),
+    "mcgra_row_sumexp": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp, c_fp]),
+    "mcgra_node_pre": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
+    "mcgra_node_mid": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
+    "mcgra_node_head": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
+    "mcgra_node_bwd2": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
+    "mcgra_node_bwd1": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
+    "mcgra_node_rho": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
+    "mcgra_pairs": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp, C.c_float, C.c_float,
+                              c_fp, c_fp, c_fp, c_fp]),
+    "mcgra_fold_adam": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp, C.c_int, C.POINTER(FoldArgs), c_fp,
+                                  c_fp]),
+    "mcgra_bisect_init": (C.c_int, [c_fp, c_fp, C.c_double, c_fp, c_fp, c_fp]),
+    "mcgra_bisect_pass": (C.c_int, [c_fp, i64, C.c_int, C.c_int, C.c_float, c_fp, c_fp, c_fp]),
+    "mcgra_bisect_update": (C.c_int, [C.c_double, C.c_float, c_fp, c_fp, c_fp, c_fp]),
+    "mcgra_bisect_finish": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_int, c_fp]),
+    "mcgra_decode_to_tiles": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, c_fp]),
+    "mcgra_gram_accumulate": (C.c_int, [c_fp, C.c_int, i64, C.c_int, c_fp, c_fp, i64, i64, i64, c_fp]),
+    "mcgra_label_accumulate": (C.c_int, [c_fp, i64, c_fp, i64, i64, i64, c_fp]),
+    "mcgra_dense_add": (C.c_int, [c_fp, c_fp, i64, c_fp]),
+    "mcgra_row_normalize": (C.c_int, [c_fp, i64, C.c_int, C.c_float, c_fp, c_fp]),
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it is missing -- there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  mcgra_b200 has no CPU / PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS)
+
+
+def check(code, what):
+    if code != 0:
+        raise NativeError(f"{what} failed with code {code}" + (" (cudaError_t)" if code > 0 else " (bad argument)"))
+
+
+def ptr(t):
+    """Device address of a torch tensor (must be contiguous) or None -> NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "native kernels need contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+LAUNCHES = {"count": 0}
+
+
+def call(name, *args):
+    """Call a C-ABI entry point, check its return code, count the launch (bench.py's gpu_launches)."""
+    LAUNCHES["count"] += 1
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,393 @@
+// Gradient fold back to the triangle + Adam + box clamp, and the budget projection by bisection.
+//
+// Reference work replaced: loss.backward() (the n x n gradients of every propagation and element-wise term,
+// autograd through utils.normalize_adj_tensor, the index_put / m+m.t() scatter back to the P-vector),
+// torch.optim.Adam.step() and the clamp (MC-GRA/topology_attack.py:274-283); PGDAttack.projection / bisection
+// (topology_attack.py:338-347, 397-412).
+//
+// The n x n gradient is never stored.  For entry (i,j), i > j, the gradient of the parameter is
+//   g = mask * [ U_i.V_j + V_i.U_j  +  r_i r_j (e'_ij + e'_ji)  +  rho_i + rho_j ]  +  0.001 w_sup x / ||x||
+// with U = [r dZ1 | r dZ2 | dQ1 | dQ2], V = [r S1 | r S2 | S1 | T2] (rank-64 factors built by the node kernels),
+// e' the element-wise loss derivatives at A_hat_ij and rho the degree gradient.
+// One CTA per 128x128 tile: rank product as an fp32 register-tiled GEMM (K = 128), then a streaming epilogue
+// that reads x', m, v (and feature_adj) once and writes x', m, v once:  24 (+4) bytes per entry.
+#include "common.cuh"
+
+namespace {
+
+struct FoldSmem {
+  float wi[64][TILE];
+  float wj[64][TILE];
+  float zI[TILE][HID + 1];
+  float zJ[TILE][HID + 1];
+  float rI[TILE], rJ[TILE], rhoI[TILE], rhoJ[TILE];
+  float lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE];
+  float rowacc[TILE], colacc[TILE];
+  double red[32];
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+__global__ void __launch_bounds__(256, 2)
+k_fold_adam(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int64_t t0, const float* mu,
+            int raw, mcgra_fold_args fa, float* __restrict__ minmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FoldSmem& sm = *reinterpret_cast<FoldSmem*>(smem_raw);
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+  const int64_t n = fa.n, np = fa.npad;
+
+  if (tid < TILE) {
+    const int64_t gi = i0 + tid, gj = j0 + tid;
+    sm.rI[tid] = gi < n ? fa.r[gi] : 0.f;
+    sm.rJ[tid] = gj < n ? fa.r[gj] : 0.f;
+    sm.rhoI[tid] = gi < n ? fa.rho[gi] : 0.f;
+    sm.rhoJ[tid] = gj < n ? fa.rho[gj] : 0.f;
+    if (fa.measure == MCGRA_M_KL) {
+      sm.lseAI[tid] = gi < n ? fa.lseA[gi] : 0.f;
+      sm.lseAJ[tid] = gj < n ? fa.lseA[gj] : 0.f;
+      sm.lseFI[tid] = gi < n ? fa.lseF[gi] : 0.f;
+      sm.lseFJ[tid] = gj < n ? fa.lseF[gj] : 0.f;
+    }
+    sm.colacc[tid] = 0.f;
+    sm.rowacc[tid] = 0.f;
+  }
+  if (fa.k2 != 0.f) {
+    for (int e = tid; e < TILE * HID; e += 256) {
+      const int a = e >> 4, k = e & 15;
+      sm.zI[a][k] = (i0 + a < n) ? fa.zhat[(i0 + a) * HID + k] : 0.f;
+      sm.zJ[a][k] = (j0 + a < n) ? fa.zhat[(j0 + a) * HID + k] : 0.f;
+    }
+  }
+
+  // ---- rank-128 product: acc[a][b] = U_i.V_j + V_i.U_j ----------------------------------------------------
+  float acc[8][8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
+
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+    const int rowI = half == 0 ? 0 : 64;     // U rows for I in half 0, V rows in half 1
+    const int rowJ = half == 0 ? 64 : 0;
+    for (int e = tid; e < 64 * 32; e += 256) {
+      const int k = e >> 5, c4 = e & 31;
+      reinterpret_cast<float4*>(&sm.wi[k][0])[c4] = ld4(fa.Wt + (int64_t)(rowI + k) * np + i0 + c4 * 4);
+      reinterpret_cast<float4*>(&sm.wj[k][0])[c4] = ld4(fa.Wt + (int64_t)(rowJ + k) * np + j0 + c4 * 4);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < 64; ++k) {
+      const float4 a0 = ld4(&sm.wi[k][ty * 4]);
+      const float4 a1 = ld4(&sm.wi[k][64 + ty * 4]);
+      const float4 b0 = ld4(&sm.wj[k][tx * 4]);
+      const float4 b1 = ld4(&sm.wj[k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+    }
+  }
+
+  // ---- streaming epilogue: element-wise terms, Adam, clamp statistics ------------------------------------
+  const double sumsq_prev = fa.acc_prev[MCGRA_ACC_SUMSQ];
+  const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
+  const double bc1 = 1.0 - pow((double)fa.beta1, (double)fa.step);
+  const double bc2 = 1.0 - pow((double)fa.beta2, (double)fa.step);
+  const float step_size = (float)((double)fa.lr / bc1);
+  const float sqrt_bc2 = (float)sqrt(bc2);
+  const float omb1 = 1.f - fa.beta1, omb2 = 1.f - fa.beta2;
+
+  float* xt = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
+  float* mt = mbuf + (int64_t)blockIdx.x * TILE_ELEMS;
+  float* vt = vbuf + (int64_t)blockIdx.x * TILE_ELEMS;
+  const float* ft = fa.Ftiles ? fa.Ftiles + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+
+  float s_clamp = 0.f, s_sq = 0.f, xmin = INFINITY, xmax = -INFINITY;
+  float colp[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) colp[q] = 0.f;
+
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int a = (p < 4) ? (ty * 4 + p) : (64 + ty * 4 + (p - 4));
+    const int64_t gi = i0 + a;
+    const float ri = sm.rI[a], rhoi = sm.rhoI[a];
+    float rowp = 0.f;
+#pragma unroll
+    for (int cg = 0; cg < 2; ++cg) {
+      const int b0 = cg * 64 + tx * 4;
+      const int off = a * TILE + b0;
+      const float4 x4 = ld4(xt + off);
+      const float4 m4 = ld4(mt + off);
+      const float4 v4 = ld4(vt + off);
+      float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ft) f4 = ld4(ft + off);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float ms[4] = {m4.x, m4.y, m4.z, m4.w};
+      const float vs[4] = {v4.x, v4.y, v4.z, v4.w};
+      const float fs[4] = {f4.x, f4.y, f4.z, f4.w};
+      float xo[4], mo[4], vo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int b = b0 + k;
+        const int64_t gj = j0 + b;
+        const bool valid = (gj < gi) && (gi < n);
+        const float p_ = pv.param(xs[k]);
+        const float M = pv.adj(xs[k]);
+        const float rj = sm.rJ[b];
+        const float ah = ri * M * rj;
+        float esym = 0.f;
+        if (fa.measure == MCGRA_M_MSE) {
+          esym += 4.f * fa.k1 * (ah - fs[k]);
+        } else if (fa.measure == MCGRA_M_KL) {
+          const float xij = __expf(fs[k] - sm.lseFI[a]);
+          const float xji = __expf(fs[k] - sm.lseFJ[b]);
+          esym += fa.k1 * ((__expf(ah - sm.lseAI[a]) - xij) + (__expf(ah - sm.lseAJ[b]) - xji));
+        }
+        if (fa.k6 != 0.f) esym += 2.f * fa.k6 * ent_grad(ah);
+        if (fa.k2 != 0.f) {
+          float s = 0.f;
+#pragma unroll
+          for (int q = 0; q < HID; ++q) s = fmaf(sm.zI[a][q], sm.zJ[b][q], s);
+          esym += 4.f * fa.k2 * (ah - fmaxf(s, 0.f));
+        }
+        float g = ri * rj * esym + rhoi + sm.rhoJ[b] + acc[p][cg * 4 + k];
+        g = pv.mask(xs[k]) * g + fa.norm_coef * p_ * inv_norm;
+        const float mn = fa.beta1 * ms[k] + omb1 * g;
+        const float vn = fa.beta2 * vs[k] + omb2 * g * g;
+        const float denom = sqrtf(vn) / sqrt_bc2 + fa.adam_eps;
+        const float xn = p_ - step_size * (mn / denom);
+        xo[k] = valid ? xn : 0.f;
+        mo[k] = valid ? mn : 0.f;
+        vo[k] = valid ? vn : 0.f;
+        if (valid) {
+          const float c = fminf(fmaxf(xn, 0.f), 1.f);
+          s_clamp += c;
+          s_sq = fmaf(c, c, s_sq);
+          xmin = fminf(xmin, xn);
+          xmax = fmaxf(xmax, xn);
+          rowp += c;
+          colp[cg * 4 + k] += c;
+        }
+      }
+      *reinterpret_cast<float4*>(xt + off) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+      *reinterpret_cast<float4*>(mt + off) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+      *reinterpret_cast<float4*>(vt + off) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+    }
+    // row a is owned by the 16 threads of this ty: reduce over tx (half-warp)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rowp += __shfl_xor_sync(0xffffffffu, rowp, o);
+    if (tx == 0) sm.rowacc[a] = rowp;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int b = (q < 4) ? (tx * 4 + q) : (64 + tx * 4 + (q - 4));
+    if (colp[q] != 0.f) atomicAdd(&sm.colacc[b], colp[q]);
+  }
+  __syncthreads();
+  if (tid < TILE) {
+    const int64_t gi = i0 + tid, gj = j0 + tid;
+    if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(fa.d_next + gi, sm.rowacc[tid]);
+    if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(fa.d_next + gj, sm.colacc[tid]);
+  }
+  block_atomic_add_d((double)s_clamp, fa.acc_next + MCGRA_ACC_SUMCLAMP, sm.red);
+  block_atomic_add_d((double)s_sq, fa.acc_next + MCGRA_ACC_SUMSQ, sm.red);
+  xmin = warp_min(xmin);
+  xmax = warp_max(xmax);
+  if ((tid & 31) == 0) {
+    if (xmin != INFINITY) atomic_min_f(minmax, xmin);
+    if (xmax != -INFINITY) atomic_max_f(minmax + 1, xmax);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Bisection on device.  state: [0]=a [1]=b [2]=mu(last midpoint) [3]=done [4]=active
+// One pass evaluates the 7 midpoints of a depth-3 bisection tree rooted at (a,b); the update walks the tree
+// with the reference's decision rule (func(miu)*func(a) < 0 -> b = miu else a = miu, func(a) > 0 invariant).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bisect_candidates(float a, float b, float* c) {
+  // heap order: c[0] root; children of node k are 2k+1 (left: (a, c_k)), 2k+2 (right: (c_k, b))
+  float lo[7], hi[7];
+  lo[0] = a; hi[0] = b;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    c[k] = (lo[k] + hi[k]) / 2;          // fp32, same expression as the reference (:403)
+    if (2 * k + 2 < 7) {
+      lo[2 * k + 1] = lo[k]; hi[2 * k + 1] = c[k];
+      lo[2 * k + 2] = c[k];  hi[2 * k + 2] = hi[k];
+    }
+  }
+}
+
+__global__ void k_bisect_init(const double* acc, const float* minmax, double budget, float* state, float* mu) {
+  const bool active = acc[MCGRA_ACC_SUMCLAMP] > budget;       // :339
+  state[0] = minmax[0] - 1.f;                                  // left  = (x-1).min()  (:340)
+  state[1] = minmax[1];                                        // right = x.max()      (:341)
+  state[2] = state[0];                                         // miu = a              (:401)
+  state[3] = active ? 0.f : 1.f;
+  state[4] = active ? 1.f : 0.f;
+  *mu = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+k_bisect_pass(const float* __restrict__ tiles, int64_t n, int64_t t0, float epsilon, const float* __restrict__ state,
+              double* __restrict__ cand_sums) {
+  __shared__ double red[32];
+  if (state[3] != 0.f) return;                                 // done / inactive: nothing to read
+  if (!((state[1] - state[0]) >= epsilon)) return;
+  float c[7];
+  bisect_candidates(state[0], state[1], c);
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+  const float4* src = reinterpret_cast<const float4*>(tiles + (int64_t)blockIdx.x * TILE_ELEMS);
+  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int e = threadIdx.x; e < TILE_ELEMS / 4; e += 256) {
+    const int row = e >> 5, c4 = e & 31;
+    const int64_t gi = i0 + row, gj = j0 + c4 * 4;
+    const float4 x4 = src[e];
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if ((gj + k < gi) && (gi < n)) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) s[q] += fminf(fmaxf(xv[k] - c[q], 0.f), 1.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) block_atomic_add_d((double)s[q], cand_sums + q, red);
+}
+
+__global__ void k_bisect_update(double budget, float epsilon, float* state, double* cand_sums, float* mu) {
+  if (state[3] == 0.f) {
+    float a = state[0], b = state[1], miu = state[2];
+    float c[7];
+    bisect_candidates(a, b, c);
+    int k = 0;
+    bool done = false;
+    for (int lvl = 0; lvl < 3; ++lvl) {
+      if (!((b - a) >= epsilon)) { done = true; break; }      // while ((b - a) >= epsilon)  (:402)
+      miu = c[k];
+      const double f = cand_sums[k] - budget;                  // func(miu)            (:399)
+      if (f == 0.0) { done = true; break; }                    // (:405)
+      if (f < 0.0) { b = miu; k = 2 * k + 1; }                 // func(miu)*func(a) < 0 with func(a) > 0  (:408)
+      else { a = miu; k = 2 * k + 2; }
+    }
+    if (!done && !((b - a) >= epsilon)) done = true;
+    state[0] = a; state[1] = b; state[2] = miu;
+    if (done) { state[3] = 1.f; *mu = miu; }
+  }
+  for (int q = 0; q < 7; ++q) cand_sums[q] = 0.0;
+}
+
+// after the bisection: statistics of the projected parameter clamp(x' - mu, 0, 1)
+__global__ void __launch_bounds__(128)
+k_bisect_finish(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* __restrict__ state,
+                const float* __restrict__ mu, double* __restrict__ acc_next, float* __restrict__ d_next) {
+  __shared__ float colacc[TILE];
+  __shared__ double red[32];
+  if (state[4] == 0.f) return;                                 // projection inactive: fold's statistics stand
+  const float m = *mu;
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+  const float4* src = reinterpret_cast<const float4*>(tiles + (int64_t)blockIdx.x * TILE_ELEMS);
+  colacc[tid] = 0.f;
+  __syncthreads();
+  float col[4] = {0.f, 0.f, 0.f, 0.f};
+  float ssq = 0.f;
+  for (int it = 0; it < 32; ++it) {
+    const int row = it * 4 + warp;
+    const float4 x4 = src[row * 32 + lane];
+    const int64_t gi = i0 + row, gj = j0 + lane * 4;
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+    float rs = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if ((gj + k < gi) && (gi < n)) {
+        const float c = fminf(fmaxf(xv[k] - m, 0.f), 1.f);
+        rs += c;
+        col[k] += c;
+        ssq = fmaf(c, c, ssq);
+      }
+    }
+    rs = warp_sum(rs);
+    if (lane == 0 && gi < n && rs != 0.f) atomicAdd(d_next + gi, rs);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) atomicAdd(&colacc[lane * 4 + k], col[k]);
+  __syncthreads();
+  if (j0 + tid < n && colacc[tid] != 0.f) atomicAdd(d_next + j0 + tid, colacc[tid]);
+  block_atomic_add_d((double)ssq, acc_next + MCGRA_ACC_SUMSQ, red);
+}
+
+// when the projection turned out active the fold's d_next / SUMSQ (taken at mu = 0) must be discarded first
+__global__ void k_bisect_reset(int64_t n, const float* state, double* acc_next, float* d_next) {
+  if (state[4] == 0.f) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d_next[i] = 1.f;
+  if (i == 0) acc_next[MCGRA_ACC_SUMSQ] = 0.0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const float* mu, int raw,
+                    const mcgra_fold_args* a, float* minmax, void* stream) {
+  const int64_t nt = tri(tr1) - tri(tr0);
+  if (nt <= 0) return 0;
+  const size_t smem = sizeof(FoldSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_fold_adam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_fold_adam<<<(unsigned)nt, 256, smem, (cudaStream_t)stream>>>(tiles, m, v, tri(tr0), mu, raw, *a, minmax);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_bisect_init(const double* acc, const float* minmax, double budget, float* state, float* mu, void* stream) {
+  k_bisect_init<<<1, 1, 0, (cudaStream_t)stream>>>(acc, minmax, budget, state, mu);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_bisect_pass(const float* tiles, int64_t n, int tr0, int tr1, float epsilon, const float* state,
+                      double* cand_sums, void* stream) {
+  const int64_t nt = tri(tr1) - tri(tr0);
+  if (nt <= 0) return 0;
+  k_bisect_pass<<<(unsigned)nt, 256, 0, (cudaStream_t)stream>>>(tiles, n, tri(tr0), epsilon, state, cand_sums);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_bisect_update(double budget, float epsilon, float* state, double* cand_sums, float* mu, void* stream) {
+  k_bisect_update<<<1, 1, 0, (cudaStream_t)stream>>>(budget, epsilon, state, cand_sums, mu);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_bisect_finish(const float* tiles, int64_t n, int tr0, int tr1, const float* state, const float* mu,
+                        double* acc_next, float* d_next, int reset, void* stream) {
+  const int64_t nt = tri(tr1) - tri(tr0);
+  if (reset) {
+    k_bisect_reset<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, state, acc_next, d_next);
+    MCGRA_LAUNCH_CHECK();
+  }
+  if (nt <= 0) return 0;
+  k_bisect_finish<<<(unsigned)nt, 128, 0, (cudaStream_t)stream>>>(tiles, n, tri(tr0), state, mu, acc_next, d_next);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// Pair passes over n x 16 factors: the decode gram M1 = relu(zhat zhat^T) and everything that hangs off it.
+//
+// Reference work replaced: PGDAttack.dot_product_decode (MC-GRA/topology_attack.py:414-419),
+// get_modified_adj_after (:381-395), Info_entropy(modified_adj1) = c7 (:233-236), MSELoss(adj_norm,
+// modified_adj1) = c2 (:221-229) with their autograd, dot_product_decode2 (:421-467) and the final ensemble
+// sum (:300-322).  The n x n gram is never stored: every tile of it is re-generated from the 16-wide factors.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CS_LD = TILE + 4;
+
+struct PairSmem {
+  float cs[TILE][CS_LD];          // coefficient tile dL/ds_ij (zero where invalid / relu inactive)
+  float zI[TILE][HID + 1];
+  float zJ[TILE][HID + 1];
+  float rI[TILE], rJ[TILE];
+  float rowacc[TILE], colacc[TILE];
+  double red[32];
+};
+
+__global__ void __launch_bounds__(256, 2)
+k_pairs(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu, int raw,
+        const float* __restrict__ zhat, const float* __restrict__ r, float k7, float k2,
+        float* __restrict__ dzhat, float* __restrict__ eps_row, double* __restrict__ acc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PairSmem& sm = *reinterpret_cast<PairSmem*>(smem_raw);
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+
+  for (int e = tid; e < TILE * HID; e += 256) {
+    const int a = e >> 4, k = e & 15;
+    sm.zI[a][k] = (i0 + a < n) ? zhat[(i0 + a) * HID + k] : 0.f;
+    sm.zJ[a][k] = (j0 + a < n) ? zhat[(j0 + a) * HID + k] : 0.f;
+  }
+  if (tid < TILE) {
+    sm.rI[tid] = (i0 + tid < n) ? r[i0 + tid] : 0.f;
+    sm.rJ[tid] = (j0 + tid < n) ? r[j0 + tid] : 0.f;
+    sm.rowacc[tid] = 0.f;
+    sm.colacc[tid] = 0.f;
+  }
+  __syncthreads();
+
+  // ---- s_ij = zhat_i . zhat_j on an 8x8 register tile ----
+  float s[8][8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[p][q] = 0.f;
+#pragma unroll
+  for (int k = 0; k < HID; ++k) {
+    float av[8], bv[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      av[p] = sm.zI[(p < 4) ? (ty * 4 + p) : (64 + ty * 4 + p - 4)][k];
+      bv[p] = sm.zJ[(p < 4) ? (tx * 4 + p) : (64 + tx * 4 + p - 4)][k];
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[p][q] = fmaf(av[p], bv[q], s[p][q]);
+  }
+
+  // ---- element-wise stage: values, coefficient tile, c2's eps_row ----
+  const float* xt = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
+  float v7 = 0.f, v2 = 0.f;
+  float colp[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) colp[q] = 0.f;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int a = (p < 4) ? (ty * 4 + p) : (64 + ty * 4 + p - 4);
+    const int64_t gi = i0 + a;
+    const float ri = sm.rI[a];
+    float rowp = 0.f;
+#pragma unroll
+    for (int cg = 0; cg < 2; ++cg) {
+      const int b0 = cg * 64 + tx * 4;
+      float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k2 != 0.f) x4 = *reinterpret_cast<const float4*>(xt + a * TILE + b0);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      float co[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int b = b0 + k;
+        const int64_t gj = j0 + b;
+        const bool valid = (gj < gi) && (gi < n);
+        const float sv = s[p][cg * 4 + k];
+        const float pm = fmaxf(sv, 0.f);
+        float dp = 0.f;
+        if (valid) {
+          if (k7 != 0.f) {
+            v7 += 2.f * ent_val(pm);
+            dp += 2.f * k7 * ent_grad(pm);
+          }
+          if (k2 != 0.f) {
+            const float M = pv.adj(xs[k]);
+            const float rj = sm.rJ[b];
+            const float df = ri * M * rj - pm;
+            v2 += 2.f * df * df;
+            dp -= 4.f * k2 * df;
+            const float t = 4.f * k2 * df * M;      // (e'_ij + e'_ji) * M_ij
+            rowp += t * rj;
+            colp[cg * 4 + k] += t * ri;
+          }
+        }
+        co[k] = (valid && sv > 0.f) ? dp : 0.f;     // relu'(0) = 0
+      }
+      *reinterpret_cast<float4*>(&sm.cs[a][b0]) = make_float4(co[0], co[1], co[2], co[3]);
+    }
+    if (k2 != 0.f) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rowp += __shfl_xor_sync(0xffffffffu, rowp, o);
+      if (tx == 0) sm.rowacc[a] = rowp;
+    }
+  }
+  if (k2 != 0.f) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int b = (q < 4) ? (tx * 4 + q) : (64 + tx * 4 + q - 4);
+      if (colp[q] != 0.f) atomicAdd(&sm.colacc[b], colp[q]);
+    }
+  }
+  __syncthreads();
+
+  // ---- dzhat_I += C zhat_J (threads 0-127, one row each); dzhat_J += C^T zhat_I (threads 128-255) ----
+  {
+    const int u = tid & 127;
+    float o[HID];
+#pragma unroll
+    for (int k = 0; k < HID; ++k) o[k] = 0.f;
+    if (tid < 128) {
+#pragma unroll 1
+      for (int b = 0; b < TILE; b += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(&sm.cs[u][b]);
+        const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int k = 0; k < HID; ++k) o[k] = fmaf(cv[q], sm.zJ[b + q][k], o[k]);
+      }
+    } else {
+#pragma unroll 1
+      for (int a = 0; a < TILE; ++a) {
+        const float cv = sm.cs[a][u];
+#pragma unroll
+        for (int k = 0; k < HID; ++k) o[k] = fmaf(cv, sm.zI[a][k], o[k]);
+      }
+    }
+    const int64_t g = (tid < 128 ? i0 : j0) + u;
+    if (g < n) {
+      float4* dst = reinterpret_cast<float4*>(dzhat + g * HID);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 val = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+        if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) atomicAdd(dst + q, val);
+      }
+    }
+  }
+  if (k2 != 0.f && tid < TILE) {
+    const int64_t gi = i0 + tid, gj = j0 + tid;
+    if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(eps_row + gi, sm.rowacc[tid]);
+    if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(eps_row + gj, sm.colacc[tid]);
+  }
+  if (k7 != 0.f) block_atomic_add_d((double)v7 * (double)k7, acc + MCGRA_ACC_C7, sm.red);
+  if (k2 != 0.f) block_atomic_add_d((double)v2 * (double)k2, acc + MCGRA_ACC_C2, sm.red);
+}
+
+// x_final tiles = relu(z_i . z_j), j < i < n  (dot_product_decode of the last embedding, :300-301)
+__global__ void __launch_bounds__(256)
+k_decode_to_tiles(const float* __restrict__ z, int64_t n, int64_t t0, float* __restrict__ tiles) {
+  __shared__ float zI[TILE][HID + 1], zJ[TILE][HID + 1];
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const int tid = threadIdx.x;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+  for (int e = tid; e < TILE * HID; e += 256) {
+    const int a = e >> 4, k = e & 15;
+    zI[a][k] = (i0 + a < n) ? z[(i0 + a) * HID + k] : 0.f;
+    zJ[a][k] = (j0 + a < n) ? z[(j0 + a) * HID + k] : 0.f;
+  }
+  __syncthreads();
+  float* dst = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
+  for (int e = tid; e < TILE_ELEMS; e += 256) {
+    const int a = e >> 7, b = e & 127;
+    const int64_t gi = i0 + a, gj = j0 + b;
+    float v = 0.f;
+    if (gj < gi && gi < n) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < HID; ++k) s = fmaf(zI[a][k], zJ[b][k], s);
+      v = fmaxf(s, 0.f);
+    }
+    dst[e] = v;
+  }
+}
+
+// out[i, j] += f(Z_i . Z_j)   for i in [row0,row1), all j; 32x32 output block per CTA, d <= 32
+__global__ void __launch_bounds__(256)
+k_gram_accumulate(const float* __restrict__ Z, int d, int64_t n, int variant, const float* __restrict__ rownorm,
+                  float* __restrict__ out, int64_t ld, int64_t row0) {
+  __shared__ float zi[32][33], zj[32][33];
+  const int64_t bi = row0 + (int64_t)blockIdx.y * 32, bj = (int64_t)blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 32 * d; e += 256) {
+    const int a = e / d, k = e % d;
+    zi[a][k] = (bi + a < n) ? Z[(bi + a) * d + k] : 0.f;
+    zj[a][k] = (bj + a < n) ? Z[(bj + a) * d + k] : 0.f;
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int64_t gi = bi + rr, gj = bj + tx;
+    if (gi >= n || gj >= n) continue;
+    float s = 0.f;
+    for (int k = 0; k < d; ++k) s = fmaf(zi[rr][k], zj[tx][k], s);
+    if (variant == 2) s = s / fmaxf(rownorm[gi], 1e-12f);
+    float v = fmaxf(s - (gi == gj ? 1.f : 0.f), 0.f);
+    if (variant == 0) v = 1.f / (1.f + expf(-v));
+    out[gi * ld + gj] += v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_label_accumulate(const int64_t* __restrict__ labels, int64_t n, float* __restrict__ out, int64_t ld, int64_t row0,
+                   int64_t row1) {
+  const int64_t gj = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t gi = row0 + blockIdx.y;
+  if (gi >= row1 || gj >= n) return;
+  if (labels[gi] == labels[gj]) out[gi * ld + gj] += 1.f;
+}
+
+__global__ void k_dense_add(float* __restrict__ out, const float* __restrict__ in, int64_t count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) out[e] += in[e];
+}
+
+// row p-norm normalisation (F.normalize(Z, p, dim=1), eps 1e-12); one thread per row
+__global__ void k_row_normalize(const float* __restrict__ Z, int64_t n, int d, float p, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int k = 0; k < d; ++k) {
+    const float v = fabsf(Z[i * d + k]);
+    acc += (p == 2.f) ? v * v : powf(v, p);
+  }
+  const float nrm = (p == 2.f) ? sqrtf(acc) : powf(acc, 1.f / p);
+  const float inv = 1.f / fmaxf(nrm, 1e-12f);
+  for (int k = 0; k < d; ++k) out[i * d + k] = Z[i * d + k] * inv;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* zhat,
+                const float* r, float k7, float k2, float* dzhat, float* eps_row, double* acc, void* stream) {
+  const int64_t nt = tri(tr1) - tri(tr0);
+  if (nt <= 0) return 0;
+  const size_t smem = sizeof(PairSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_pairs<<<(unsigned)nt, 256, smem, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, zhat, r, k7, k2, dzhat,
+                                                              eps_row, acc);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_decode_to_tiles(const float* zhat, int64_t n, int tr0, int tr1, float* tiles, void* stream) {
+  const int64_t nt = tri(tr1) - tri(tr0);
+  if (nt <= 0) return 0;
+  k_decode_to_tiles<<<(unsigned)nt, 256, 0, (cudaStream_t)stream>>>(zhat, n, tri(tr0), tiles);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const float* rownorm, float* out, int64_t ld,
+                          int64_t row0, int64_t row1, void* stream) {
+  if (d > 32 || d < 1) return -1;
+  if (row1 <= row0) return 0;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((row1 - row0 + 31) / 32));
+  if (grid.y > 65535) return -3;
+  k_gram_accumulate<<<grid, 256, 0, (cudaStream_t)stream>>>(Z, d, n, variant, rownorm, out, ld, row0);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_label_accumulate(const int64_t* labels, int64_t n, float* out, int64_t ld, int64_t row0, int64_t row1,
+                           void* stream) {
+  if (row1 <= row0) return 0;
+  for (int64_t r = row0; r < row1; r += 65535) {
+    const int64_t r1 = (r + 65535 < row1) ? r + 65535 : row1;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)(r1 - r));
+    k_label_accumulate<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, n, out, ld, r, r1);
+    MCGRA_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int mcgra_dense_add(float* out, const float* in, int64_t count, void* stream) {
+  if (count <= 0) return 0;
+  k_dense_add<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(out, in, count);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_row_normalize(const float* Z, int64_t n, int d, float p, float* out, void* stream) {
+  if (n <= 0) return 0;
+  k_row_normalize<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(Z, n, d, p, out);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

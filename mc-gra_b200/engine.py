@@ -1,0 +1,331 @@
+"""PGDEngine: host-side sequencing of the native stages of one PGD iteration.
+
+One PGD iteration of the reference (MC-GRA/topology_attack.py:161-283) becomes a
+fixed sequence of C-ABI calls on the current CUDA stream, with no host synchronisation:
+
+    node_pre -> [row_sumexp] -> propagate#1(+element-wise c1/c6) -> node_mid -> propagate#2 -> node_head
+    -> pairs(c7,c2) -> node_bwd2 -> propagate#3 -> node_bwd1 -> propagate#4 -> node_rho -> fold_adam
+    -> [bisection passes]
+
+The adjacency estimate lives only as the tiled lower triangle (x', Adam m, v); n x n matrices are never
+materialised.  With world_size > 1 every rank owns a contiguous range of tile rows (equal tile counts) and the
+n x K partial results are summed with torch.distributed.all_reduce (NCCL over NVLink) between stages.
+PyTorch is used for device memory, streams and the collective only.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _native as N
+from ._native import ACC, call, ptr
+
+HID = N.HID
+TILE = N.TILE
+MEASURES = {"MSELoss": N.M_MSE, "KL": N.M_KL, "HSIC": N.M_HSIC, "CKA": N.M_CKA, "DP": N.M_DP}
+ALIGN = {"c1": 100, "c2": 1000, "c6": 10, "c7": 10, "c9": 1, "c10": 1}      # MC-GRA/utils.py:1100-1111
+
+
+def tri(i):
+    return i * (i + 1) // 2
+
+
+def shard_tile_rows(T, world):
+    """Contiguous tile-row ranges with (nearly) equal tile counts: boundaries ~ T*sqrt(g/G)."""
+    total = tri(T)
+    bounds = [0]
+    for g in range(1, world):
+        target = total * g / world
+        I = int(round((math.sqrt(8 * target + 1) - 1) / 2))
+        I = max(bounds[-1], min(T, I))
+        bounds.append(I)
+    bounds.append(T)
+    return [(bounds[g], bounds[g + 1]) for g in range(world)]
+
+
+class PGDEngine:
+    def __init__(self, n, S1, W2, b1, b2, Wl, bl, labels, idx_attack, HA, YA, feature_adj, measure, weights,
+                 lr, weight_sup=1.0, num_edges=None, x0=None, device="cuda", rank=0, world=1, group=None,
+                 max_epochs=1024):
+        if not torch.cuda.is_available():
+            raise N.NativeError("mcgra_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        N.lib()
+        dev = torch.device(device)
+        self.dev, self.n, self.rank, self.world, self.group = dev, int(n), rank, world, group
+        n = self.n
+        self.T = (n + TILE - 1) // TILE
+        self.npad = self.T * TILE
+        self.tr0, self.tr1 = shard_tile_rows(self.T, world)[rank]
+        self.ntiles = tri(self.tr1) - tri(self.tr0)
+        self.P = n * (n - 1) // 2
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        def dv(t, dtype=torch.float32):
+            return t.detach().to(device=dev, dtype=dtype).contiguous()
+
+        self.S1 = dv(S1)
+        self.W2, self.b1, self.b2, self.Wl, self.bl = dv(W2), dv(b1), dv(b2), dv(Wl), dv(bl)
+        assert self.W2.shape == (HID, HID) and self.S1.shape == (n, HID), "hidden width must be 16 (main.py:175)"
+        self.nclass = int(self.Wl.shape[0])
+        if self.nclass > N.MAXC:
+            raise N.NativeError(f"nclass {self.nclass} > {N.MAXC}")
+        self.labels = dv(labels, torch.int64)
+        idx = torch.as_tensor(idx_attack, dtype=torch.int64, device=dev)
+        self.wmult = (torch.bincount(idx, minlength=n).to(torch.float32) / float(idx.numel())).contiguous()
+        self.HA, self.YA = dv(HA), dv(YA)
+        assert self.HA.shape == (n, HID) and self.YA.shape == (n, self.nclass)
+
+        # ---- flags -> scaled constants (topology_attack.py:151, 211-272) ----
+        self.measure_name = measure
+        if measure not in MEASURES:
+            raise NotImplementedError(f"measure {measure!r}: KDE is a SURVEY 8(f) 'next' row")
+        self.measure = MEASURES[measure]
+        w1, w2, _, _, _, w6, w7, _w8, w9, w10 = [float(w) for w in weights]
+        self.w = (w1, w2, w6, w7, w9, w10)
+        self.weight_sup = float(weight_sup)
+        self.lr = float(lr)
+        nn2 = float(n) * float(n)
+        sgn = -1.0 if measure == "HSIC" else 1.0
+        self.c1_active = False
+        self.Ft = self.Fdiag = self.lseF = None
+        self.k1 = self.k2 = 0.0
+        self.meas_nn = N.M_NONE       # measure code used by the element-wise n x n kernels
+        if self.measure in (N.M_HSIC, N.M_CKA, N.M_DP) and (w1 != 0 or w2 != 0):
+            raise NotImplementedError(
+                f"measure {measure} on the n x n terms c1/c2 needs the dense tcgen05 contraction (DESIGN.md, "
+                "row K6) which is not built yet; n x d terms c9/c10 are supported")
+        if w1 != 0 and feature_adj is not None:
+            fa = feature_adj.to(dev)
+            # topology_attack.py:212: the term is skipped when feature_adj is constant
+            if bool(fa.max() != fa.min()):
+                self.c1_active = True
+                fa = fa.to(torch.float32).contiguous()
+                self.Ft = torch.zeros(max(self.ntiles, 1) * TILE * TILE, **f32)
+                self.Fdiag = torch.zeros(n, **f32)
+                call("mcgra_dense_to_tiles", ptr(fa), n, n, self.tr0, self.tr1, 1, ptr(self.Ft), ptr(self.Fdiag),
+                     N.stream_ptr())
+                if world > 1:
+                    self._allreduce(self.Fdiag)
+                self.meas_nn = self.measure
+                if self.measure == N.M_MSE:
+                    self.k1 = w1 * 1000 * ALIGN["c1"] / nn2
+                elif self.measure == N.M_KL:
+                    self.k1 = w1 * 1000 * ALIGN["c1"] / float(n)
+                    self.lseF = torch.logsumexp(fa, dim=1).contiguous()
+                del fa
+        if w2 != 0:
+            if self.measure != N.M_MSE:
+                raise NotImplementedError("c2 (w2) is built for --measure=MSELoss only so far (DESIGN.md)")
+            self.k2 = w2 * 100 * ALIGN["c2"] / nn2
+        self.k6 = -w6 * 100 * ALIGN["c6"] / nn2
+        self.k7 = -w7 * ALIGN["c7"] / nn2
+        self.w9 = sgn * w9 * ALIGN["c9"]
+        self.w10 = sgn * w10 * ALIGN["c10"]
+        if self.measure in (N.M_HSIC, N.M_CKA, N.M_DP) and (w9 != 0 or w10 != 0):
+            raise NotImplementedError(f"measure {measure} on c9/c10: n x d HSIC/CKA/DP stage not built yet")
+        self.budget = float(num_edges) if num_edges is not None else float("inf")
+        self.proj_possible = self.budget < float(self.P)
+
+        # ---- state: tiled triangle of x', m, v ----
+        nel = max(self.ntiles, 1) * TILE * TILE
+        self.xt = torch.zeros(nel, **f32)
+        self.mt = torch.zeros(nel, **f32)
+        self.vt = torch.zeros(nel, **f32)
+        self.mu = torch.zeros(1, **f32)
+        self.raw = 0
+        self.step = 0
+        self.max_epochs = max_epochs
+        self.acc_hist = torch.zeros(max_epochs + 2, N.ACC_N, dtype=torch.float64, device=dev)
+        self.minmax = torch.zeros(2, **f32)
+        self.bstate = torch.zeros(8, **f32)
+        self.cand = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.d = torch.zeros(n, **f32)
+        self.d_next = torch.zeros(n, **f32)
+
+        # ---- node buffers ----
+        z = lambda *s: torch.zeros(*s, **f32)
+        self.r = z(n)
+        self.B1, self.Y1, self.B2, self.Y2, self.B3, self.Y3 = (z(n, 32) for _ in range(6))
+        self.B4, self.Y4 = z(n, HID), z(n, HID)
+        (self.S2, self.T2, self.H2, self.dZ2, self.dZ1, self.dQ1, self.dQ2, self.demd, self.zhat,
+         self.dzhat) = (z(n, HID) for _ in range(10))
+        self.inv_norm, self.eps_row, self.rho = z(n), z(n), z(n)
+        self.masks = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.masks2 = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.Wt = z(128, self.npad)
+        self.sumexp = z(n) if self.meas_nn == N.M_KL else None
+        self.lseA = z(n) if self.meas_nn == N.M_KL else None
+
+        self.set_parameter(x0)
+
+    # ------------------------------------------------------------------------------------------------
+    def _allreduce(self, t, op=None):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.group)
+
+    def set_parameter(self, x_packed):
+        """Load a packed parameter vector (reference layout) -- zeros when None (topology_attack.py:77-78)."""
+        st = N.stream_ptr()
+        self.mt.zero_()
+        self.vt.zero_()
+        self.mu.zero_()
+        self.step = 0
+        self.acc_hist.zero_()
+        if x_packed is None:
+            self.xt.zero_()
+            self.raw = 0
+            sumsq = 0.0
+        else:
+            xp = x_packed.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+            assert xp.numel() == self.P
+            call("mcgra_tril_to_tiles", ptr(xp), self.n, self.tr0, self.tr1, ptr(self.xt), st)
+            self.raw = 1
+            sumsq = float((xp.double() ** 2).sum())
+        self.acc_hist[0, ACC["SUMSQ"]] = sumsq
+        self.d.fill_(1.0 if self.rank == 0 else 0.0)
+        call("mcgra_degree", ptr(self.xt), self.n, self.tr0, self.tr1, ptr(self.mu), self.raw, ptr(self.d), st)
+        self._allreduce(self.d)
+
+    def _node_args(self, t):
+        a = N.NodeArgs()
+        a.n, a.nclass = self.n, self.nclass
+        a.W2, a.b1, a.b2, a.Wl, a.bl = ptr(self.W2), ptr(self.b1), ptr(self.b2), ptr(self.Wl), ptr(self.bl)
+        a.S1, a.labels, a.wmult, a.HA, a.YA = ptr(self.S1), ptr(self.labels), ptr(self.wmult), ptr(self.HA), ptr(self.YA)
+        a.d, a.r = ptr(self.d), ptr(self.r)
+        a.B1, a.Y1, a.B2, a.Y2, a.B3, a.Y3 = (ptr(x) for x in (self.B1, self.Y1, self.B2, self.Y2, self.B3, self.Y3))
+        a.B4, a.Y4 = ptr(self.B4), ptr(self.Y4)
+        a.S2, a.T2, a.H2, a.dZ2, a.dZ1, a.dQ1 = (ptr(x) for x in (self.S2, self.T2, self.H2, self.dZ2, self.dZ1, self.dQ1))
+        a.dQ2, a.demd, a.zhat, a.dzhat = ptr(self.dQ2), ptr(self.demd), ptr(self.zhat), ptr(self.dzhat)
+        a.inv_norm, a.masks, a.masks2 = ptr(self.inv_norm), ptr(self.masks), ptr(self.masks2)
+        a.eps_row, a.rho, a.Wt = ptr(self.eps_row), ptr(self.rho), ptr(self.Wt)
+        a.Fdiag = ptr(self.Fdiag)
+        a.acc = self.acc_hist[t].data_ptr()
+        a.measure = self.measure
+        a.weight_sup = self.weight_sup
+        a.k1 = self.k1 if self.c1_active else 0.0
+        a.k2, a.k6, a.k7 = self.k2, self.k6, self.k7
+        a.w9, a.w10 = self.w9, self.w10
+        a.npad = self.npad
+        a.d_next, a.d_fill = ptr(self.d_next), (1.0 if self.rank == 0 else 0.0)
+        a.acc_next = self.acc_hist[t + 1].data_ptr()
+        a.minmax = ptr(self.minmax)
+        a.lseA, a.lseF = ptr(self.lseA), ptr(self.lseF)
+        return a
+
+    def forward_stages(self, t):
+        """Forward half of an iteration (through node_head); returns the node-args struct."""
+        st = N.stream_ptr()
+        n, tr0, tr1, mu, raw = self.n, self.tr0, self.tr1, ptr(self.mu), self.raw
+        a = self._node_args(t)
+        ap = C.byref(a)
+        call("mcgra_node_pre", ap, st)
+        if self.meas_nn == N.M_KL:
+            self.sumexp.zero_()
+            call("mcgra_row_sumexp", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.r), ptr(self.sumexp), st)
+            self._allreduce(self.sumexp)
+            torch.log(self.sumexp + torch.exp(self.r * self.r), out=self.lseA)   # + diagonal entry r_i^2
+        ea = None
+        if self.c1_active or self.k6 != 0.0:
+            e = N.ElemArgs()
+            e.r, e.Ftiles, e.lseA, e.lseF = ptr(self.r), ptr(self.Ft), ptr(self.lseA), ptr(self.lseF)
+            e.measure = self.meas_nn if self.c1_active else N.M_NONE
+            e.k1, e.k6 = (self.k1 if self.c1_active else 0.0), self.k6
+            e.acc, e.eps_row = self.acc_hist[t].data_ptr(), ptr(self.eps_row)
+            ea = C.byref(e)
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B1), 32, ptr(self.Y1), ea, st)
+        self._allreduce(self.Y1)
+        call("mcgra_node_mid", ap, st)
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B2), 32, ptr(self.Y2), None, st)
+        self._allreduce(self.Y2)
+        call("mcgra_node_head", ap, st)
+        return a
+
+    def iterate(self):
+        """One full PGD iteration (forward, backward, Adam, projection); no host synchronisation."""
+        t = self.step
+        if t >= self.max_epochs:
+            raise RuntimeError("acc history exhausted; construct the engine with a larger max_epochs")
+        st = N.stream_ptr()
+        n, tr0, tr1, mu, raw = self.n, self.tr0, self.tr1, ptr(self.mu), self.raw
+        a = self.forward_stages(t)
+        ap = C.byref(a)
+        if self.k7 != 0.0 or self.k2 != 0.0:
+            call("mcgra_pairs", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.zhat), ptr(self.r),
+                 self.k7, self.k2, ptr(self.dzhat), ptr(self.eps_row), self.acc_hist[t].data_ptr(), st)
+            self._allreduce(self.dzhat)
+        call("mcgra_node_bwd2", ap, st)
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, st)
+        self._allreduce(self.Y3)
+        call("mcgra_node_bwd1", ap, st)
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B4), 16, ptr(self.Y4), None, st)
+        if self.world > 1:
+            self._allreduce(self.Y4)
+            self._allreduce(self.eps_row)
+        call("mcgra_node_rho", ap, st)
+
+        f = N.FoldArgs()
+        f.n, f.npad, f.Wt, f.r, f.rho = n, self.npad, ptr(self.Wt), ptr(self.r), ptr(self.rho)
+        f.Ftiles = ptr(self.Ft) if self.c1_active else None
+        f.lseA, f.lseF = ptr(self.lseA), ptr(self.lseF)
+        f.zhat = ptr(self.zhat)
+        f.measure = self.meas_nn if self.c1_active else N.M_NONE
+        f.k1, f.k6, f.k2 = (self.k1 if self.c1_active else 0.0), self.k6, self.k2
+        f.norm_coef = self.weight_sup * 0.001
+        f.lr, f.beta1, f.beta2, f.adam_eps = self.lr, 0.9, 0.999, 1e-8
+        f.step = t + 1
+        f.acc_prev = self.acc_hist[t].data_ptr()
+        f.acc_next = self.acc_hist[t + 1].data_ptr()
+        f.d_next = ptr(self.d_next)
+        call("mcgra_fold_adam", ptr(self.xt), ptr(self.mt), ptr(self.vt), tr0, tr1, mu, raw, C.byref(f),
+             ptr(self.minmax), st)
+        self.raw = 0                     # the buffer now holds the un-projected Adam output x', mu = 0
+        self.mu.zero_()
+        if self.world > 1:
+            import torch.distributed as dist
+            self._allreduce(self.acc_hist[t + 1, :16])
+            self._allreduce(self.minmax[0:1], dist.ReduceOp.MIN)
+            self._allreduce(self.minmax[1:2], dist.ReduceOp.MAX)
+        if self.proj_possible:
+            self._project(t)
+        self._allreduce(self.d_next)
+        self.d, self.d_next = self.d_next, self.d
+        self.step = t + 1
+
+    def _project(self, t):
+        """projection + bisection (topology_attack.py:338-347, 397-412) without a host round trip."""
+        st = N.stream_ptr()
+        n, tr0, tr1 = self.n, self.tr0, self.tr1
+        acc_next = self.acc_hist[t + 1].data_ptr()
+        self.cand.zero_()
+        call("mcgra_bisect_init", acc_next, ptr(self.minmax), self.budget, ptr(self.bstate), ptr(self.mu), st)
+        for _ in range(8):               # 8 passes x 3 halvings covers brackets up to 167 wide at eps = 1e-5
+            call("mcgra_bisect_pass", ptr(self.xt), n, tr0, tr1, 1e-5, ptr(self.bstate), ptr(self.cand), st)
+            self._allreduce(self.cand)
+            call("mcgra_bisect_update", self.budget, 1e-5, ptr(self.bstate), ptr(self.cand), ptr(self.mu), st)
+        call("mcgra_bisect_finish", ptr(self.xt), n, tr0, tr1, ptr(self.bstate), ptr(self.mu), acc_next,
+             ptr(self.d_next), 1, st)
+        # (with world > 1 the reset writes d_next = 1 on every rank; keep rank 0's only)
+        if self.world > 1 and self.rank != 0:
+            self.d_next.sub_(self.bstate[4])
+
+    # ------------------------------------------------------------------------------------------------
+    def losses(self):
+        """Per-iteration totals from the accumulator history (one device->host copy).  Returns dict of
+        numpy arrays: loss (what loss.backward() is called on, :274), origin (:172-173), and each term."""
+        h = self.acc_hist[: self.step].cpu().numpy()
+        g = lambda k: h[:, ACC[k]]
+        origin = g("NLL") + 0.001 * (g("SUMSQ") ** 0.5)
+        c1, c2 = g("C1") + g("C1D"), g("C2") + g("C2D")
+        c6, c7 = g("C6") + g("C6D"), g("C7") + g("C7D")
+        sgn = -1.0 if self.measure_name == "HSIC" else 1.0
+        loss = self.weight_sup * origin + sgn * (c1 + c2) + c6 + c7 + g("C9") + g("C10")
+        return dict(loss=loss, origin=origin, c1=c1, c2=c2, c6=c6, c7=c7, c9=g("C9"), c10=g("C10"))
+
+    def packed_parameter(self):
+        """The optimised parameter in the reference's packed layout (all ranks' shards summed)."""
+        out = torch.zeros(self.P, dtype=torch.float32, device=self.dev)
+        call("mcgra_tiles_to_tril", ptr(self.xt), self.n, self.tr0, self.tr1, ptr(self.mu), self.raw, ptr(out),
+             N.stream_ptr())
+        self._allreduce(out)
+        return out

@@ -1,0 +1,30 @@
+"""GPU parity tests: the native path (through the C ABI) against golden fixtures of the unmodified reference and
+against the CPU oracle.  Tolerances are BASELINE.json's: per-iteration loss 1e-4 relative, AUC/AP 1e-3."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pgd_oracle as O
+from helpers import run_native_case
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SUPPORTED = ["mse_A_n37", "mse_A_n150", "mse_all_n150", "mse_budget_n150", "mse_nosup_n90", "mse_sub_n90",
+             "kl_C_n150", "kl_all_n90"]
+
+
+@pytest.mark.parametrize("case", SUPPORTED)
+def test_attack_matches_reference_golden(case):
+    d = np.load(os.path.join(GOLDEN, f"attack_{case}.npz"))
+    got = run_native_case(d)
+    np.testing.assert_allclose(got["loss"], d["loss"], rtol=1e-4)
+    xs = np.stack(got["x_iters"])
+    assert np.max(np.abs(xs - d["x_iters"])) < 2e-4
+    np.testing.assert_allclose(got["x_final"], d["x_final"], rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(got["modified_adj"], d["modified_adj"], rtol=1e-3, atol=1e-3)
+    real = d["adj"].reshape(-1).astype(np.float32)
+    assert abs(O.roc_auc(real, got["modified_adj"].reshape(-1)) - float(d["auc"])) < 1e-3
+    assert abs(O.average_precision(real, got["modified_adj"].reshape(-1)) - float(d["ap"])) < 1e-3
