@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- PGD attack iterations/second of the native path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # one JSON line on stdout
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...                      # the reference's CPU algorithm (oracle port)
+
+Workload (config.workload): synthetic planted-partition graph of BASELINE.json's shape, README-Cora flag
+profile ("Profile A": --w1=0.01 --w6=10 --w7=10 --w9=10 --w10=1000 --lr=-2 --measure=MSELoss, all three priors,
+MC-GRA/README.md:29).  One step = one full PGD iteration (forward, prior losses, backward, Adam, projection test),
+SURVEY.md 3.2 steps 1-17.  `value` is timed with CUDA events with all inputs resident in HBM; `e2e` goes through
+the public API (PGDAttack.attack + AUC) starting from pinned HOST tensors and ending with the AUC scalar on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "large": dict(n=65536, f=512, c=8, name="synthetic n=65536 f=512 c=8 (BASELINE configs[4])"),
+    "pubmed": dict(n=19717, f=500, c=3, name="synthetic PubMed-shape n=19717 f=500 c=3 (BASELINE configs[3])"),
+    "cora": dict(n=2708, f=1433, c=7, name="synthetic Cora-shape n=2708 f=1433 c=7 (BASELINE configs[0] shape)"),
+    "tiny": dict(n=1024, f=64, c=4, name="synthetic n=1024 (debug)"),
+}
+PROFILE_A = (0.01, 0, 0, 0, 0, 10, 10, 0, 10, 1000)
+SAMPLE_N = 3072           # CPU baseline sample size (reference algorithm is O(n^3) per iteration)
+
+
+class Args:
+    pass
+
+
+def make_args(measure="MSELoss"):
+    a = Args()
+    a.max_eval, a.lr, a.eps, a.measure, a.dataset = 100, -2.0, 0.0, measure, "cora"
+    a.useH_A = a.useY_A = a.useY = True
+    for k, w in enumerate(PROFILE_A, 1):
+        setattr(a, f"w{k}", w)
+    return a
+
+
+def clocks_sampler(stop, out, index):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            out.append(r.stdout.strip())
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarise_clocks(samples):
+    sm, mx, reasons = [], 0, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for s in samples:
+        p = [x.strip() for x in s.split(",")]
+        if len(p) < 7:
+            continue
+        try:
+            sm.append(float(p[0]))
+            mx = max(mx, float(p[1]))
+        except ValueError:
+            continue
+        for nme, v in zip(names, p[3:7]):
+            if v.lower().startswith("active"):
+                reasons.add(nme)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def build_problem(wl, device, seed=15):
+    """Synthetic inputs on the HOST (pinned) + victim weights.  SURVEY.md 8(d)."""
+    import torch
+    from mcgra_b200 import synth
+    g = synth.make_graph(wl["n"], wl["f"], wl["c"], seed=seed)
+    W = synth.gcn_weights(wl["f"], 16, wl["c"], seed=seed, gain=3.0)
+    n = wl["n"]
+    X = torch.from_numpy(g["features"])
+    edges = torch.from_numpy(g["edges"])
+    # feature_adj = sigmoid(relu(X X^T - I)) (main.dot_product_decode for cora, main.py:44-55); computed on the
+    # device once (setup, untimed) and handed to the API as a host tensor like the reference driver does
+    Xd = X.to(device)
+    fa = Xd @ Xd.t()
+    fa.diagonal().sub_(1.0)
+    fa = torch.sigmoid_(torch.relu_(fa))
+    fa_host = torch.empty(n, n, dtype=torch.float32, pin_memory=True)
+    fa_host.copy_(fa)
+    del fa, Xd
+    torch.cuda.empty_cache()
+    rng = np.random.RandomState(seed)
+    idx_attack = rng.permutation(n)
+    return dict(n=n, X=X.pin_memory(), edges=edges, labels=torch.from_numpy(g["labels"]), W=W,
+                feature_adj=fa_host, idx_attack=idx_attack, nedges=int(edges.shape[0]))
+
+
+def sparse_adj(prob, device):
+    import torch
+    e = prob["edges"].to(device)
+    idx = torch.cat([e.t(), e.t().flip(0)], 1)
+    return torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1], device=device), (prob["n"], prob["n"])).coalesce()
+
+
+def make_attack(prob, device):
+    import torch
+    from copy import deepcopy
+    from mcgra_b200.models.gcn import GCN, embedding_GCN
+    from mcgra_b200.topology_attack import PGDAttack
+    W = prob["W"]
+    f, c, n = W["W1"].shape[0], W["Wl"].shape[0], prob["n"]
+    victim = GCN(nfeat=f, nclass=c, nhid=16, nlayer=2, device=device)
+    with torch.no_grad():
+        victim.gc[0].weight.copy_(torch.from_numpy(W["W1"])); victim.gc[0].bias.copy_(torch.from_numpy(W["b1"]))
+        victim.gc[1].weight.copy_(torch.from_numpy(W["W2"])); victim.gc[1].bias.copy_(torch.from_numpy(W["b2"]))
+        victim.linear1.weight.copy_(torch.from_numpy(W["Wl"])); victim.linear1.bias.copy_(torch.from_numpy(W["bl"]))
+    victim = victim.to(device)
+    for layer in victim.gc:
+        layer.to(device)
+    emb = embedding_GCN(nfeat=f, nhid=16, nlayer=2, device=device)
+    emb.gc = deepcopy(victim.gc)
+    victim.eval(); emb.eval()
+    adj = sparse_adj(prob, device)
+    with torch.no_grad():
+        Xd = prob["X"].to(device)
+        H_A = emb(Xd, adj)
+        Y_A = victim(Xd, adj)
+    atk = PGDAttack(model=victim, embedding=emb, H_A=H_A, Y_A=Y_A, nnodes=n, loss_type="CE", device=device)
+    return atk, adj
+
+
+def run_native(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from mcgra_b200 import _native as N
+    from mcgra_b200 import metrics
+    N.lib()
+    wl = WORKLOADS[a.workload]
+    n = wl["n"]
+    P = n * (n - 1) // 2
+    prob = build_problem(wl, device)
+    args = make_args()
+    K, Wm = a.steps, a.warmup
+
+    # ------------------------------------------------------------------ device-resident steps (`value`)
+    atk, adj = make_attack(prob, device)
+    num_edges = int(0.5 * 1e7 * (2 * prob["nedges"]) / n ** 2 * n ** 2)          # main.py:247-248, --density 1e7
+    # epochs=0: builds the engine (constants, tiled feature_adj) without iterating; then we drive iterate() here
+    atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_A, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
+               prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=0,
+               _engine_epochs=K + Wm + 8, _skip_finalize=True)
+    eng = atk.engine
+    for _ in range(Wm):
+        eng.iterate()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
+    th.start()
+    N.TIMERS['on'] = {}
+    l0 = N.LAUNCHES["count"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(K):
+        eng.iterate()
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = N.LAUNCHES["count"] - l0
+    stop.set()
+    th.join()
+    ms = ev0.elapsed_time(ev1)
+    kt = {k: float(np.mean([s.elapsed_time(e) for s, e in v])) for k, v in N.TIMERS['on'].items()}
+    N.TIMERS['on'] = None
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    losses = eng.losses()["loss"]
+    del eng, atk
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ end to end through the public API
+    e2e = None
+    if not a.no_e2e:
+        atk, adj = make_attack(prob, device)
+        labels_pos = prob["edges"]
+        # one warm call at 1 epoch so allocator / lazy init are not in the timed region
+        atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_A, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
+                   prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=1)
+        metrics.auc_ap_from_edges(atk.modified_adj, labels_pos)
+        atk.adj_changes.data.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_A, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
+                   prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=K)
+        loss_hist = atk.engine.losses()["loss"]            # D2H of the per-iteration loss history
+        auc, ap = metrics.auc_ap_from_edges(atk.modified_adj, labels_pos)     # D2H of two scalars
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = (prob["feature_adj"].numel() + prob["X"].numel()) * 4 + prob["labels"].numel() * 8 + n * 8
+        e2e = {"value": K / dt, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d / K),
+               "d2h_bytes_per_step": int((len(loss_hist) * 32 * 8 + 16) / K),
+               "includes": "PGDAttack.attack(epochs=K) from pinned host tensors (features, feature_adj n x n, labels, "
+                           "idx) + final ensemble + GPU AUC/AP, amortised over K",
+               "auc": auc, "ap": ap}
+
+    if rank != 0:
+        return
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    prop_ms = kt.get("propagate32")
+    prop_bytes = 4.0 * P / world + 3 * n * 32 * 4          # one read of the shard + B, Y (read-modify-write)
+    roof = None
+    if prop_ms:
+        ach = prop_bytes / (prop_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_propagate<32> (Y += M*B over the tiled triangle)", "achieved": ach,
+                "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "launch_ms": prop_ms, "algorithmic_bytes_per_launch": prop_bytes,
+                "per_kernel_ms": kt}
+    clocks = summarise_clocks(samples)
+    out = {"metric": "PGD attack iterations/s (fwd+bwd+prior losses+Adam+projection)", "value": K / (ms * 1e-3),
+           "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl["name"], "n": n, "flags": "Profile A: README Cora MSELoss w1=.01 w6=10 w7=10 w9=10 "
+                      "w10=1000 lr=1e-2, density 1e7", "l2": "inputs larger than L2 (tiled x/m/v/F >> 126 MB)"
+                      if 4 * P > 4e8 else "flush: none (working set fits L2 at this size)",
+                      "sharding": f"tile-row shards x{world}" if world > 1 else "single GPU"},
+           "roofline": roof, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+           "iter_bytes_algorithmic": 52.0 * P, "hbm_frac_whole_iter": 52.0 * P / world / (ms / K * 1e-3) / 1e9 / hbm,
+           "loss_first_last": [float(losses[0]), float(losses[-1])]}
+    if world == 1 and not a.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(a, threads=os.cpu_count())
+    print(json.dumps(out))
+
+
+def cpu_problem(n, f, c, seed=15):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pgd_oracle as O
+    from mcgra_b200 import synth
+    g = synth.make_graph(n, f, c, seed=seed)
+    W = {k: torch.from_numpy(v) for k, v in synth.gcn_weights(f, 16, c, seed=seed, gain=3.0).items()}
+    X = torch.from_numpy(g["features"])
+    A = torch.from_numpy(synth.dense_adj(n, g["edges"]))
+    prob = dict(n=n, X=X, adj=A, labels=torch.from_numpy(g["labels"]), W=W,
+                idx_attack=torch.from_numpy(np.random.RandomState(seed).permutation(n)),
+                feature_adj=O.feature_adj_of(X, "cora"))
+    prob["H_A"] = O.embed(X, A, W, 2)
+    prob["Y_A"] = O.victim(X, A, W)
+    cfg = dict(measure="MSELoss", weights=list(PROFILE_A), lr=1e-2, eps=0.0, weight_sup=1.0, dataset="cora",
+               use=(True, True, True), num_edges=10 ** 12)
+    return O, prob, cfg
+
+
+def cpu_baseline(a, threads, iters=2):
+    """The reference's algorithm (oracle port, dense n x n torch CPU autograd incl. its per-iteration bookkeeping)
+    on the host cores, on a bounded sample of the workload."""
+    import torch
+    torch.set_num_threads(max(1, threads))
+    wl = WORKLOADS[a.workload]
+    n = min(SAMPLE_N, wl["n"])
+    O, prob, cfg = cpu_problem(n, wl["f"], wl["c"])
+    O.attack(prob, cfg, 1, bookkeeping=True)       # warm
+    t0 = time.perf_counter()
+    O.attack(prob, cfg, iters, bookkeeping=True)
+    dt = time.perf_counter() - t0
+    v = iters / dt
+    scale = (wl["n"] / n) ** 3
+    return {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port",
+            "sample": f"oracle port of the reference loop at n={n} (f={wl['f']}, c={wl['c']}), {iters} iterations incl. "
+                      f"the reference's in-loop bookkeeping; the reference algorithm is O(n^3)/iteration and needs "
+                      f">0.9 TB at n={wl['n']} (not runnable) -- n^3 extrapolation to n={wl['n']}: {v / scale:.3e} it/s"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    wl = WORKLOADS[a.workload]
+    threads = os.cpu_count()
+    import torch
+    torch.set_num_threads(threads)
+    n = min(SAMPLE_N, wl["n"])
+    O, prob, cfg = cpu_problem(n, wl["f"], wl["c"])
+    for _ in range(min(a.warmup, 1)):
+        O.attack(prob, cfg, 1, bookkeeping=True)
+    K = max(1, min(a.steps, 3))
+    t0 = time.perf_counter()
+    O.attack(prob, cfg, K, bookkeeping=True)
+    dt = time.perf_counter() - t0
+    v = K / dt
+    sample = (f"oracle port of the reference loop at n={n} (bounded sample; the reference needs >0.9 TB and "
+              f"O(n^3) work per iteration at n={wl['n']}), {K} timed iterations")
+    out = {"impl": "reference", "metric": "PGD attack iterations/s (fwd+bwd+prior losses+Adam+projection)", "value": v,
+           "unit": "iterations/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": min(a.warmup, 1),
+           "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl["name"], "sample_n": n},
+           "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="large", choices=list(WORKLOADS))
+    ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -204,6 +204,18 @@ int mcgra_label_accumulate(const int64_t* labels, int64_t n, float* out, int64_t
 int mcgra_dense_add(float* out, const float* in, int64_t count, void* stream);
 int mcgra_row_normalize(const float* Z, int64_t n, int d, float p, float* out, void* stream);
 
+/* ---- AUC / AP (main.metric_pool, main.py:66-75; gcn_parameterized.py:55-65) ----
+ * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU,
+ * every negative is ranked against them; exact integer counts => sklearn's trapezoid AUC with ties, and
+ * sklearn's average precision.  npos_max bounds the number of positives (workspace size).
+ * out: device double[4] = {auc, ap, npos, nneg}.                                                     */
+int64_t mcgra_auc_workspace_bytes(int64_t N, int64_t npos_max);
+int mcgra_auc_ap(const float* scores, const uint8_t* labels, int64_t N, int64_t npos_max, void* ws,
+                 double* out, void* stream);
+/* stable descending arg-sort (LSD radix sort, key = score, payload = index): the recovered-edge ranking */
+int64_t mcgra_sort_workspace_bytes(int64_t N);
+int mcgra_argsort_desc(const float* scores, int64_t N, int64_t* order, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

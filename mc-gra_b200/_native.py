@@ -82,6 +82,10 @@ _SIGS = {
     "mcgra_label_accumulate": (C.c_int, [c_fp, i64, c_fp, i64, i64, i64, c_fp]),
     "mcgra_dense_add": (C.c_int, [c_fp, c_fp, i64, c_fp]),
     "mcgra_row_normalize": (C.c_int, [c_fp, i64, C.c_int, C.c_float, c_fp, c_fp]),
+    "mcgra_auc_workspace_bytes": (i64, [i64, i64]),
+    "mcgra_auc_ap": (C.c_int, [c_fp, c_fp, i64, i64, c_fp, c_fp, c_fp]),
+    "mcgra_sort_workspace_bytes": (i64, [i64]),
+    "mcgra_argsort_desc": (C.c_int, [c_fp, i64, c_fp, c_fp, c_fp]),
 }
 
 _lib = None
@@ -133,7 +137,19 @@ def stream_ptr():
 LAUNCHES = {"count": 0}
 
 
-def call(name, *args):
+TIMERS = {"on": None}     # when a dict: name -> list of (start, end) CUDA events around each call
+
+
+def call(name, *args, tag=None):
     """Call a C-ABI entry point, check its return code, count the launch (bench.py's gpu_launches)."""
     LAUNCHES["count"] += 1
+    tm = TIMERS["on"]
+    if tm is not None:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        check(getattr(lib(), name)(*args), name)
+        e.record()
+        tm.setdefault(tag or name, []).append((s, e))
+        return
     check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,330 @@
+// ROC-AUC / average precision over N (score, label) pairs and a stable descending arg-sort, on the GPU.
+//
+// Reference work replaced: main.metric_pool (MC-GRA/main.py:66-75: .cpu() of two n^2 vectors + sklearn roc_curve
+// + auc) and the AP of gcn_parameterized.metric (MC-GRA/gcn_parameterized.py:55-65).  sklearn semantics (stable
+// descending sort, thresholds at distinct scores, trapezoid => ties contribute 1/2; AP = sum_k (R_k - R_{k-1}) P_k).
+//
+// Method: positives are few (true edges), negatives are ~n^2.  The positives' keys are radix-sorted (LSD, 8-bit
+// digits, stable); every negative is then ranked against them by binary search:
+//     2*AUC*P*N = sum_neg ( 2 * #pos_above + #pos_tied )            (exact integers, uint64)
+// and a histogram of the negatives' upper-bound positions gives fp(>= v) for every distinct positive score v,
+// from which AP follows in float64.  The same radix sort with an index payload gives the full ranking.
+#include "common.cuh"
+
+namespace {
+
+// order-preserving map float -> uint32 (ascending)
+__device__ __forceinline__ uint32_t fkey(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+constexpr int CHUNK = 4096;   // elements per single-warp block
+
+__global__ void k_hist(const uint32_t* __restrict__ keys, int64_t N, int shift, uint32_t* __restrict__ hist /*[256][nb]*/,
+                       int64_t nb) {
+  __shared__ uint32_t h[256];
+  for (int e = threadIdx.x; e < 256; e += blockDim.x) h[e] = 0;
+  __syncthreads();
+  const int64_t b0 = (int64_t)blockIdx.x * CHUNK;
+  for (int e = threadIdx.x; e < CHUNK; e += blockDim.x) {
+    const int64_t g = b0 + e;
+    if (g < N) atomicAdd(&h[(keys[g] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 256; e += blockDim.x) hist[(int64_t)e * nb + blockIdx.x] = h[e];
+}
+
+// exclusive scan of hist (bin-major, block-minor) into 64-bit offsets; single block, sequential over chunks
+__global__ void k_scan(const uint32_t* __restrict__ hist, int64_t total, int64_t* __restrict__ offs) {
+  __shared__ int64_t carry;
+  __shared__ int64_t wsum[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t base = 0; base < total; base += blockDim.x) {
+    const int64_t g = base + threadIdx.x;
+    int64_t v = g < total ? (int64_t)hist[g] : 0;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      int64_t s = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+      int64_t si = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, si, o);
+        if (lane >= o) si += t;
+      }
+      wsum[lane] = si - s;   // exclusive warp offsets
+    }
+    __syncthreads();
+    const int64_t excl = carry + wsum[w] + inc - v;
+    if (g < total) offs[g] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+// stable scatter: one warp per chunk, elements visited in order, match_any gives the in-warp rank
+template <typename PAY>
+__global__ void __launch_bounds__(32)
+k_scatter(const uint32_t* __restrict__ kin, const PAY* __restrict__ pin, int64_t N, int shift,
+          const int64_t* __restrict__ offs, int64_t nb, uint32_t* __restrict__ kout, PAY* __restrict__ pout) {
+  __shared__ int64_t pos[256];
+  const int lane = threadIdx.x;
+  for (int e = lane; e < 256; e += 32) pos[e] = offs[(int64_t)e * nb + blockIdx.x];
+  __syncwarp();
+  const int64_t b0 = (int64_t)blockIdx.x * CHUNK;
+  for (int it = 0; it < CHUNK / 32; ++it) {
+    const int64_t g = b0 + it * 32 + lane;
+    const bool ok = g < N;
+    const uint32_t k = ok ? kin[g] : 0xffffffffu;
+    const uint32_t dg = ok ? ((k >> shift) & 255u) : 256u + lane;   // inactive lanes never match anything
+    const unsigned peers = __match_any_sync(0xffffffffu, dg);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int64_t base = 0;
+    if (ok) base = pos[dg];
+    __syncwarp();
+    if (ok) {
+      kout[base + rank] = k;
+      if (pin != nullptr) pout[base + rank] = pin[g];
+      if (rank == __popc(peers) - 1) pos[dg] = base + rank + 1;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void k_compact_pos(const float* __restrict__ scores, const uint8_t* __restrict__ labels, int64_t N,
+                              uint32_t* __restrict__ poskeys, int64_t cap, unsigned long long* __restrict__ counter) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < N; g += stride) {
+    if (labels[g]) {
+      const unsigned long long s = atomicAdd(counter, 1ull);
+      if ((int64_t)s < cap) poskeys[s] = fkey(scores[g]);
+    }
+  }
+}
+
+__device__ __forceinline__ int64_t lower_bound(const uint32_t* a, int64_t n, uint32_t k) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < k) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int64_t upper_bound(const uint32_t* a, int64_t n, uint32_t k) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] <= k) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// every negative against the sorted positives
+__global__ void __launch_bounds__(256)
+k_rank_negatives(const float* __restrict__ scores, const uint8_t* __restrict__ labels, int64_t N,
+                 const uint32_t* __restrict__ pos, const unsigned long long* __restrict__ counter,
+                 unsigned long long* __restrict__ hist /*[npos+1]*/, unsigned long long* __restrict__ sums /*[2]*/) {
+  const int64_t npos = (int64_t)*counter;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long twice = 0, nneg = 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t nround = (N + stride - 1) / stride;
+  for (int64_t rd = 0; rd < nround; ++rd) {
+    const int64_t g = rd * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool neg = (g < N) && !labels[g];
+    int64_t ub = -1 - lane;     // unique sentinel so inactive lanes do not aggregate
+    if (neg) {
+      const uint32_t k = fkey(scores[g]);
+      const int64_t lb = lower_bound(pos, npos, k);
+      ub = upper_bound(pos, npos, k);
+      twice += 2ull * (unsigned long long)(npos - ub) + (unsigned long long)(ub - lb);
+      nneg += 1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, ub);
+    if (neg && lane == (__ffs(peers) - 1)) atomicAdd(hist + ub, (unsigned long long)__popc(peers));
+  }
+  // block reduce
+  __shared__ unsigned long long r0[8], r1[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    twice += __shfl_xor_sync(0xffffffffu, twice, o);
+    nneg += __shfl_xor_sync(0xffffffffu, nneg, o);
+  }
+  if (lane == 0) { r0[threadIdx.x >> 5] = twice; r1[threadIdx.x >> 5] = nneg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += r0[w]; b += r1[w]; }
+    if (a) atomicAdd(sums, a);
+    if (b) atomicAdd(sums + 1, b);
+  }
+}
+
+// suffix sums of hist -> fp(>= pos[t]) = sum_{j > t} hist[j]; AP over distinct positive values.  Single block.
+__global__ void __launch_bounds__(1024)
+k_ap_finish(const uint32_t* __restrict__ pos, const unsigned long long* __restrict__ counter,
+            unsigned long long* __restrict__ hist, const unsigned long long* __restrict__ sums,
+            double* __restrict__ out) {
+  const int64_t npos = (int64_t)*counter;
+  __shared__ unsigned long long carry;
+  __shared__ unsigned long long wsum[32];
+  __shared__ double red[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // in-place inclusive suffix scan over j = npos .. 0 : after it hist[j] = sum_{q >= j} hist[q]
+  for (int64_t base = npos; base >= 0; base -= blockDim.x) {
+    const int64_t j = base - threadIdx.x;
+    unsigned long long v = j >= 0 ? hist[j] : 0ull;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      unsigned long long s = wsum[lane], si = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, si, o);
+        if (lane >= o) si += t;
+      }
+      wsum[lane] = si - s;
+    }
+    __syncthreads();
+    const unsigned long long tot = carry + wsum[w] + inc;
+    if (j >= 0) hist[j] = tot;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = tot;
+    __syncthreads();
+  }
+  // AP = (1/npos) sum over first occurrences t of a distinct value: cnt * tp / (tp + fp),
+  //   tp = npos - t (positives >= v), fp = hist[t+1] (negatives with upper_bound > t), cnt = run length
+  double ap = 0.0;
+  for (int64_t t = threadIdx.x; t < npos; t += blockDim.x) {
+    if (t == 0 || pos[t] != pos[t - 1]) {
+      int64_t e = t + 1;
+      while (e < npos && pos[e] == pos[t]) ++e;
+      const double tp = (double)(npos - t), fp = (double)hist[t + 1];
+      ap += (double)(e - t) * tp / (tp + fp);
+    }
+  }
+  ap = warp_sum_d(ap);
+  if (lane == 0) red[w] = ap;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += red[q];
+    const double P = (double)npos, Nn = (double)sums[1];
+    out[0] = (P > 0 && Nn > 0) ? (double)sums[0] / (2.0 * P * Nn) : 0.0;   // AUC
+    out[1] = P > 0 ? s / P : 0.0;                                          // AP
+    out[2] = P;
+    out[3] = Nn;
+  }
+}
+
+__global__ void k_make_keys_desc(const float* __restrict__ scores, int64_t N, uint32_t* __restrict__ keys,
+                                 int64_t* __restrict__ idx) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < N; g += stride) {
+    keys[g] = ~fkey(scores[g]);     // ascending sort of ~key == descending score; LSD stability keeps index order
+    idx[g] = g;
+  }
+}
+
+inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+
+// LSD radix sort of `keys` (and payload) in place using `tmp` buffers; 4 passes of 8 bits
+template <typename PAY>
+int radix_sort(uint32_t* keys, PAY* pay, uint32_t* keys_tmp, PAY* pay_tmp, int64_t N, uint32_t* hist, int64_t* offs,
+               cudaStream_t st) {
+  if (N <= 0) return 0;
+  const int64_t nb = (N + CHUNK - 1) / CHUNK;
+  uint32_t* kin = keys; uint32_t* kout = keys_tmp;
+  PAY* pin = pay; PAY* pout = pay_tmp;
+  for (int pass = 0; pass < 4; ++pass) {
+    k_hist<<<(unsigned)nb, 256, 0, st>>>(kin, N, pass * 8, hist, nb);
+    k_scan<<<1, 1024, 0, st>>>(hist, nb * 256, offs);
+    k_scatter<PAY><<<(unsigned)nb, 32, 0, st>>>(kin, pin, N, pass * 8, offs, nb, kout, pout);
+    uint32_t* tk = kin; kin = kout; kout = tk;
+    PAY* tp = pin; pin = pout; pout = tp;
+  }
+  MCGRA_LAUNCH_CHECK();
+  return 0;   // after 4 passes the result is back in `keys` / `pay`
+}
+
+}  // namespace
+
+extern "C" {
+
+// workspace layout (bytes): [counter+sums 256][poskeys cap*4][poskeys_tmp cap*4][hist_sort][offs_sort][hist cap+1 u64]
+int64_t mcgra_auc_workspace_bytes(int64_t N, int64_t npos_max) {
+  (void)N;
+  const int64_t nb = (npos_max + CHUNK - 1) / CHUNK + 1;
+  return 256 + 2 * align256(npos_max * 4) + align256(nb * 256 * 4) + align256(nb * 256 * 8) +
+         align256((npos_max + 2) * 8);
+}
+
+int mcgra_auc_ap(const float* scores, const uint8_t* labels, int64_t N, int64_t npos_max, void* ws, double* out,
+                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N <= 0 || npos_max <= 0) return -1;
+  char* p = (char*)ws;
+  unsigned long long* counter = (unsigned long long*)p;       // [0] npos, [1..2] sums
+  unsigned long long* sums = counter + 1;
+  p += 256;
+  uint32_t* pos = (uint32_t*)p; p += align256(npos_max * 4);
+  uint32_t* pos_tmp = (uint32_t*)p; p += align256(npos_max * 4);
+  const int64_t nb = (npos_max + CHUNK - 1) / CHUNK + 1;
+  uint32_t* hs = (uint32_t*)p; p += align256(nb * 256 * 4);
+  int64_t* offs = (int64_t*)p; p += align256(nb * 256 * 8);
+  unsigned long long* hist = (unsigned long long*)p;
+  cudaError_t e = cudaMemsetAsync(ws, 0, 256, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(hist, 0, (npos_max + 2) * 8, st);
+  if (e != cudaSuccess) return (int)e;
+  // keys of unused slots sort to the top and are ignored (counter gives the true count); fill with 0xff
+  e = cudaMemsetAsync(pos, 0xff, npos_max * 4, st);
+  if (e != cudaSuccess) return (int)e;
+  k_compact_pos<<<148 * 8, 256, 0, st>>>(scores, labels, N, pos, npos_max, counter);
+  int rc = radix_sort<uint32_t>(pos, nullptr, pos_tmp, nullptr, npos_max, hs, offs, st);
+  if (rc) return rc;
+  k_rank_negatives<<<148 * 8, 256, 0, st>>>(scores, labels, N, pos, counter, hist, sums);
+  k_ap_finish<<<1, 1024, 0, st>>>(pos, counter, hist, sums, out);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+// workspace: [keys N*4][keys_tmp N*4][idx_tmp N*8][hist][offs]
+int64_t mcgra_sort_workspace_bytes(int64_t N) {
+  const int64_t nb = (N + CHUNK - 1) / CHUNK + 1;
+  return 2 * align256(N * 4) + align256(N * 8) + align256(nb * 256 * 4) + align256(nb * 256 * 8);
+}
+
+int mcgra_argsort_desc(const float* scores, int64_t N, int64_t* order, void* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N <= 0) return 0;
+  char* p = (char*)ws;
+  uint32_t* keys = (uint32_t*)p; p += align256(N * 4);
+  uint32_t* keys_tmp = (uint32_t*)p; p += align256(N * 4);
+  int64_t* idx_tmp = (int64_t*)p; p += align256(N * 8);
+  const int64_t nb = (N + CHUNK - 1) / CHUNK + 1;
+  uint32_t* hs = (uint32_t*)p; p += align256(nb * 256 * 4);
+  int64_t* offs = (int64_t*)p;
+  k_make_keys_desc<<<148 * 8, 256, 0, st>>>(scores, N, keys, order);
+  return radix_sort<int64_t>(keys, order, keys_tmp, idx_tmp, N, hs, offs, st);
+}
+
+}  // extern "C"

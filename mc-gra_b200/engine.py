@@ -233,10 +233,10 @@ class PGDEngine:
             e.k1, e.k6 = (self.k1 if self.c1_active else 0.0), self.k6
             e.acc, e.eps_row = self.acc_hist[t].data_ptr(), ptr(self.eps_row)
             ea = C.byref(e)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B1), 32, ptr(self.Y1), ea, st)
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B1), 32, ptr(self.Y1), ea, st, tag="propagate32_elem")
         self._allreduce(self.Y1)
         call("mcgra_node_mid", ap, st)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B2), 32, ptr(self.Y2), None, st)
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B2), 32, ptr(self.Y2), None, st, tag="propagate32")
         self._allreduce(self.Y2)
         call("mcgra_node_head", ap, st)
         return a
@@ -255,10 +255,10 @@ class PGDEngine:
                  self.k7, self.k2, ptr(self.dzhat), ptr(self.eps_row), self.acc_hist[t].data_ptr(), st)
             self._allreduce(self.dzhat)
         call("mcgra_node_bwd2", ap, st)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, st)
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, st, tag="propagate32")
         self._allreduce(self.Y3)
         call("mcgra_node_bwd1", ap, st)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B4), 16, ptr(self.Y4), None, st)
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B4), 16, ptr(self.Y4), None, st, tag="propagate16")
         if self.world > 1:
             self._allreduce(self.Y4)
             self._allreduce(self.eps_row)

@@ -1,0 +1,63 @@
+"""AUC / AP / ranking on the GPU (reference: main.metric_pool, MC-GRA/main.py:66-75; AP of
+gcn_parameterized.metric, gcn_parameterized.py:55-65) through mcgra_auc_ap / mcgra_argsort_desc."""
+import numpy as np
+import torch
+
+from . import _native as N
+from ._native import call, ptr
+
+
+def roc_auc_ap(scores, labels, npos_max=None):
+    """scores: float32 device tensor (any shape); labels: same numel, non-zero = positive.
+    Returns (auc, ap) as Python floats (sklearn roc_curve+auc / average_precision_score semantics)."""
+    s = scores.detach().reshape(-1).to(torch.float32).contiguous()
+    lab = labels.reshape(-1)
+    if lab.dtype != torch.uint8:
+        lab = (lab != 0).to(torch.uint8)
+    lab = lab.contiguous()
+    assert s.is_cuda and lab.is_cuda and s.numel() == lab.numel()
+    total = s.numel()
+    if npos_max is None:
+        npos_max = int(lab.sum().item())
+    npos_max = max(int(npos_max), 1)
+    ws = torch.empty(N.lib().mcgra_auc_workspace_bytes(total, npos_max), dtype=torch.uint8, device=s.device)
+    out = torch.zeros(4, dtype=torch.float64, device=s.device)
+    call("mcgra_auc_ap", ptr(s), ptr(lab), total, npos_max, ptr(ws), ptr(out), N.stream_ptr())
+    o = out.cpu().numpy()
+    if int(o[2]) > npos_max:
+        raise N.NativeError(f"positives {int(o[2])} exceed npos_max {npos_max}")
+    return float(o[0]), float(o[1])
+
+
+def auc_ap_from_edges(scores_dense, edges):
+    """All n^2 ordered pairs incl. the diagonal (metric_pool semantics); positives = both orientations of `edges`."""
+    n = scores_dense.shape[0]
+    dev = scores_dense.device
+    e = torch.as_tensor(edges, device=dev).long()
+    lab = torch.zeros(n, n, dtype=torch.uint8, device=dev)
+    lab[e[:, 0], e[:, 1]] = 1
+    lab[e[:, 1], e[:, 0]] = 1
+    return roc_auc_ap(scores_dense, lab, npos_max=2 * int(e.shape[0]))
+
+
+def metric_pool(ori_adj, inference_adj, idx, index_delete=None, print_cfg=False):
+    """Same signature / value as main.metric_pool: ROC-AUC over adj[idx][:,idx] (index_delete has no effect on
+    the AUC in the reference either, main.py:70-72)."""
+    dev = inference_adj.device
+    idx_t = torch.as_tensor(np.asarray(idx), device=dev).long()
+    real = ori_adj.to(dev)[idx_t][:, idx_t]
+    pred = inference_adj[idx_t][:, idx_t]
+    auc, _ = roc_auc_ap(pred, real)
+    if print_cfg:
+        print(f"current auc={auc}")
+    return auc
+
+
+def argsort_desc(scores):
+    """Stable descending arg-sort of a float32 device tensor (recovered-edge ranking)."""
+    s = scores.detach().reshape(-1).to(torch.float32).contiguous()
+    total = s.numel()
+    ws = torch.empty(N.lib().mcgra_sort_workspace_bytes(total), dtype=torch.uint8, device=s.device)
+    order = torch.empty(total, dtype=torch.int64, device=s.device)
+    call("mcgra_argsort_desc", ptr(s), total, ptr(order), ptr(ws), N.stream_ptr())
+    return order

@@ -152,13 +152,16 @@ class PGDAttack(BaseAttack):
         x0 = x0 if bool((x0 != 0).any()) else None
         self.engine = PGDEngine(n, S1, W2, b1, b2, Wl, bl, labels_t, idx_attack, HA_loop, YA_loop, fa,
                                 args.measure, weights, lr_ori, weight_sup=weight_supervised, num_edges=num_edges,
-                                x0=x0, device=dev, rank=rank, world=world, max_epochs=max(int(epochs), 1))
+                                x0=x0, device=dev, rank=rank, world=world,
+                                max_epochs=max(int(epochs), int(kwargs.get('_engine_epochs', 1)), 1))
         eng = self.engine
         self._trace = []
         for _ in range(int(epochs)):
             eng.iterate()
             if kwargs.get("_trace"):             # test hook: parameter after every iteration's projection
                 self._trace.append(eng.packed_parameter())
+        if kwargs.get("_skip_finalize"):         # bench hook: engine is driven by the caller
+            return 0, 0, 0, 0
         if int(epochs) == 0:
             eng.forward_stages(0)
         self._finalize(eng, args, fa, labels_t, W2, b1, b2, Wl, bl)
