@@ -15,7 +15,7 @@ namespace {
 
 // order-preserving map float -> uint32 (ascending)
 __device__ __forceinline__ uint32_t fkey(float f) {
-  uint32_t u = __float_as_uint(f);
+  uint32_t u = __float_as_uint(f + 0.0f);          // -0.0 -> +0.0: they compare equal, so they must share a key
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 

@@ -1,0 +1,10 @@
+#!/bin/bash
+# ncu evidence for profiles/: launch list (shares) + one --set full capture of the hot kernels.  Run under gpurun.
+set -x
+mkdir -p gpurun_out
+W=${1:-pubmed}
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$W.csv \
+    python bench.py --workload $W --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_bench_$W.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_fold_adam|k_propagate|k_pairs' -s 11 -c 6 \
+    -o gpurun_out/prof_$W -f python bench.py --workload $W --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_full_$W.log 2>&1
+ls -la gpurun_out
