@@ -54,6 +54,7 @@ class FoldArgs(C.Structure):
 
 _SIGS = {
     "mcgra_version": (C.c_int, []),
+    "mcgra_set_engine": (C.c_int, [C.c_int, C.c_int]),
     "mcgra_tiles_in_rows": (i64, [C.c_int, C.c_int]),
     "mcgra_tril_to_tiles": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, c_fp]),
     "mcgra_tiles_to_tril": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp]),

@@ -209,6 +209,255 @@ k_fold_adam(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// v2 engine: the rank-128 factor product on warp-level tensor-core MMA (mma.sync m16n8k8 tf32, 3xTF32 split,
+// fp32 accumulate), result tile parked in shared memory, then a fully coalesced streaming epilogue (one warp =
+// one 512 B tile row per step, 4 rows in flight per warp).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int W_LD = TILE + 8;     // k-major operand rows: banks 8t+g distinct for fragment loads
+constexpr int G_LD = TILE + 4;
+
+struct FoldMmaSmem {
+  union {
+    struct { float wi[64][W_LD]; float wj[64][W_LD]; } op;     // operands of one K half
+    float gt[TILE][G_LD];                                       // rank-part gradient tile (aliases operands)
+  } u;
+  float zI[TILE][HID + 1];
+  float zJt[HID][TILE + 4];
+  float rI[TILE], rJ[TILE], rhoI[TILE], rhoJ[TILE];
+  float lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE];
+  float colacc[TILE];
+  double red[32];
+};
+
+__device__ __forceinline__ void split_tf32f(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32f(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int64_t t0, const float* mu,
+           int raw, mcgra_fold_args fa, float* __restrict__ minmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FoldMmaSmem& sm = *reinterpret_cast<FoldMmaSmem*>(smem_raw);
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+  const int64_t n = fa.n, np = fa.npad;
+
+  if (tid < TILE) {
+    const int64_t gi = i0 + tid, gj = j0 + tid;
+    sm.rI[tid] = gi < n ? fa.r[gi] : 0.f;
+    sm.rJ[tid] = gj < n ? fa.r[gj] : 0.f;
+    sm.rhoI[tid] = gi < n ? fa.rho[gi] : 0.f;
+    sm.rhoJ[tid] = gj < n ? fa.rho[gj] : 0.f;
+    if (fa.measure == MCGRA_M_KL) {
+      sm.lseAI[tid] = gi < n ? fa.lseA[gi] : 0.f;
+      sm.lseAJ[tid] = gj < n ? fa.lseA[gj] : 0.f;
+      sm.lseFI[tid] = gi < n ? fa.lseF[gi] : 0.f;
+      sm.lseFJ[tid] = gj < n ? fa.lseF[gj] : 0.f;
+    }
+    sm.colacc[tid] = 0.f;
+  }
+  if (fa.k2 != 0.f) {
+    for (int e = tid; e < TILE * HID; e += 256) {
+      const int a = e >> 4, k = e & 15;
+      sm.zI[a][k] = (i0 + a < n) ? fa.zhat[(i0 + a) * HID + k] : 0.f;
+      sm.zJt[k][a] = (j0 + a < n) ? fa.zhat[(j0 + a) * HID + k] : 0.f;
+    }
+  }
+
+  // ---- rank-128 product: warp (wm, wn) owns rows [32 wm, +32) x cols [64 wn, +64) ----
+  const int wm = warp >> 1, wn = warp & 1;
+  float acc[2][8][4];
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[mb][nb][q] = 0.f;
+
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+    const int rowI = half == 0 ? 0 : 64;     // U rows for I in half 0, V rows in half 1
+    const int rowJ = half == 0 ? 64 : 0;
+    for (int e = tid; e < 64 * 32; e += 256) {
+      const int k = e >> 5, c4 = e & 31;
+      *reinterpret_cast<float4*>(&sm.u.op.wi[k][c4 * 4]) = ld4(fa.Wt + (int64_t)(rowI + k) * np + i0 + c4 * 4);
+      *reinterpret_cast<float4*>(&sm.u.op.wj[k][c4 * 4]) = ld4(fa.Wt + (int64_t)(rowJ + k) * np + j0 + c4 * 4);
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ks = 0; ks < 8; ++ks) {
+      const int k0 = ks * 8;
+      uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const int m0 = wm * 32 + mb * 16;
+        split_tf32f(sm.u.op.wi[k0 + t][m0 + g], ahi[mb][0], alo[mb][0]);
+        split_tf32f(sm.u.op.wi[k0 + t][m0 + g + 8], ahi[mb][1], alo[mb][1]);
+        split_tf32f(sm.u.op.wi[k0 + t + 4][m0 + g], ahi[mb][2], alo[mb][2]);
+        split_tf32f(sm.u.op.wi[k0 + t + 4][m0 + g + 8], ahi[mb][3], alo[mb][3]);
+      }
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const int n0 = wn * 64 + nb * 8;
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32f(sm.u.op.wj[k0 + t][n0 + g], bh0, bl0);
+        split_tf32f(sm.u.op.wj[k0 + t + 4][n0 + g], bh1, bl1);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          mma_tf32f(acc[mb][nb], alo[mb], bh0, bh1);
+          mma_tf32f(acc[mb][nb], ahi[mb], bl0, bl1);
+          mma_tf32f(acc[mb][nb], ahi[mb], bh0, bh1);
+        }
+      }
+    }
+  }
+  __syncthreads();                           // operands dead: park the product tile over them
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb) {
+    const int ra = wm * 32 + mb * 16 + g;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int cb = wn * 64 + nb * 8 + 2 * t;
+      *reinterpret_cast<float2*>(&sm.u.gt[ra][cb]) = make_float2(acc[mb][nb][0], acc[mb][nb][1]);
+      *reinterpret_cast<float2*>(&sm.u.gt[ra + 8][cb]) = make_float2(acc[mb][nb][2], acc[mb][nb][3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- streaming epilogue ----
+  const double sumsq_prev = fa.acc_prev[MCGRA_ACC_SUMSQ];
+  const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
+  const double bc1 = 1.0 - pow((double)fa.beta1, (double)fa.step);
+  const double bc2 = 1.0 - pow((double)fa.beta2, (double)fa.step);
+  const float step_size = (float)((double)fa.lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float omb1 = 1.f - fa.beta1, omb2 = 1.f - fa.beta2;
+  float* xt = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
+  float* mt = mbuf + (int64_t)blockIdx.x * TILE_ELEMS;
+  float* vt = vbuf + (int64_t)blockIdx.x * TILE_ELEMS;
+  const float* ft = fa.Ftiles ? fa.Ftiles + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+  const bool interior = (J < I) && (i0 + TILE <= n);
+  const int b0 = lane * 4;
+  float rj4[4], rhoj4[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { rj4[k] = sm.rJ[b0 + k]; rhoj4[k] = sm.rhoJ[b0 + k]; }
+  float s_clamp = 0.f, s_sq = 0.f, xmin = INFINITY, xmax = -INFINITY;
+  float colp[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int UNR = 4;
+#pragma unroll 1
+  for (int it = 0; it < TILE / (8 * UNR); ++it) {
+    float4 x4[UNR], m4[UNR], v4[UNR], f4[UNR];
+#pragma unroll
+    for (int uu = 0; uu < UNR; ++uu) {
+      const int a = (it * UNR + uu) * 8 + warp;
+      const int off = a * TILE + b0;
+      x4[uu] = ld4(xt + off);
+      m4[uu] = ld4(mt + off);
+      v4[uu] = ld4(vt + off);
+      f4[uu] = ft ? ld4(ft + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int uu = 0; uu < UNR; ++uu) {
+      const int a = (it * UNR + uu) * 8 + warp;
+      const int off = a * TILE + b0;
+      const int gi = (int)(i0 + a);
+      const float ri = sm.rI[a], rhoi = sm.rhoI[a];
+      const float4 g4 = ld4(&sm.u.gt[a][b0]);
+      const float xs[4] = {x4[uu].x, x4[uu].y, x4[uu].z, x4[uu].w};
+      const float ms[4] = {m4[uu].x, m4[uu].y, m4[uu].z, m4[uu].w};
+      const float vs[4] = {v4[uu].x, v4[uu].y, v4[uu].z, v4[uu].w};
+      const float fs[4] = {f4[uu].x, f4[uu].y, f4[uu].z, f4[uu].w};
+      const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+      float sdot[4] = {0.f, 0.f, 0.f, 0.f};
+      if (fa.k2 != 0.f) {
+#pragma unroll
+        for (int q = 0; q < HID; ++q) {
+          const float zi = sm.zI[a][q];
+          const float4 zj = ld4(&sm.zJt[q][b0]);
+          sdot[0] = fmaf(zi, zj.x, sdot[0]); sdot[1] = fmaf(zi, zj.y, sdot[1]);
+          sdot[2] = fmaf(zi, zj.z, sdot[2]); sdot[3] = fmaf(zi, zj.w, sdot[3]);
+        }
+      }
+      float xo[4], mo[4], vo[4];
+      float rowp = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int gj = (int)(j0 + b0 + k);
+        const bool valid = interior || ((gj < gi) && (gi < n));
+        const float p_ = pv.param(xs[k]);
+        const float M = pv.adj(xs[k]);
+        const float rj = rj4[k];
+        const float ah = ri * M * rj;
+        float esym = 0.f;
+        if (fa.measure == MCGRA_M_MSE) {
+          esym = 4.f * fa.k1 * (ah - fs[k]);
+        } else if (fa.measure == MCGRA_M_KL) {
+          const float xij = __expf(fs[k] - sm.lseFI[a]);
+          const float xji = __expf(fs[k] - sm.lseFJ[b0 + k]);
+          esym = fa.k1 * ((__expf(ah - sm.lseAI[a]) - xij) + (__expf(ah - sm.lseAJ[b0 + k]) - xji));
+        }
+        if (fa.k6 != 0.f && ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(2.f * fa.k6, __log2f(ah) + INV_LN2, esym);
+        if (fa.k2 != 0.f) esym = fmaf(4.f * fa.k2, ah - fmaxf(sdot[k], 0.f), esym);
+        float gg = fmaf(ri * rj, esym, rhoi + rhoj4[k] + gs[k]);
+        gg = pv.mask(xs[k]) * gg + fa.norm_coef * p_ * inv_norm;
+        const float mn = fa.beta1 * ms[k] + omb1 * gg;
+        const float vn = fa.beta2 * vs[k] + omb2 * gg * gg;
+        const float denom = sqrtf(vn) * inv_sqrt_bc2 + fa.adam_eps;
+        const float xn = p_ - step_size * (mn / denom);
+        xo[k] = valid ? xn : 0.f;
+        mo[k] = valid ? mn : 0.f;
+        vo[k] = valid ? vn : 0.f;
+        if (valid) {
+          const float c = fminf(fmaxf(xn, 0.f), 1.f);
+          s_clamp += c;
+          s_sq = fmaf(c, c, s_sq);
+          xmin = fminf(xmin, xn);
+          xmax = fmaxf(xmax, xn);
+          rowp += c;
+          colp[k] += c;
+        }
+      }
+      *reinterpret_cast<float4*>(xt + off) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+      *reinterpret_cast<float4*>(mt + off) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+      *reinterpret_cast<float4*>(vt + off) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+      rowp = warp_sum(rowp);
+      if (lane == 0 && gi < n && rowp != 0.f) atomicAdd(fa.d_next + gi, rowp);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (colp[k] != 0.f) atomicAdd(&sm.colacc[b0 + k], colp[k]);
+  __syncthreads();
+  if (tid < TILE) {
+    const int64_t gj = j0 + tid;
+    if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(fa.d_next + gj, sm.colacc[tid]);
+  }
+  block_atomic_add_d((double)s_clamp, fa.acc_next + MCGRA_ACC_SUMCLAMP, sm.red);
+  block_atomic_add_d((double)s_sq, fa.acc_next + MCGRA_ACC_SUMSQ, sm.red);
+  xmin = warp_min(xmin);
+  xmax = warp_max(xmax);
+  if (lane == 0) {
+    if (xmin != INFINITY) atomic_min_f(minmax, xmin);
+    if (xmax != -INFINITY) atomic_max_f(minmax + 1, xmax);
+  }
+}
+
+int g_fold_engine = 1;     // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2)
+
 // ---------------------------------------------------------------------------------------------------------
 // Bisection on device.  state: [0]=a [1]=b [2]=mu(last midpoint) [3]=done [4]=active
 // One pass evaluates the 7 midpoints of a depth-3 bisection tree rooted at (a,b); the update walks the tree
@@ -344,10 +593,20 @@ __global__ void k_bisect_reset(int64_t n, const float* state, double* acc_next, 
 
 extern "C" {
 
+int mcgra_set_fold_engine_(int value) { g_fold_engine = value; return 0; }
+
 int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const float* mu, int raw,
                     const mcgra_fold_args* a, float* minmax, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
+  if (g_fold_engine == 1) {
+    const size_t smem2 = sizeof(FoldMmaSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_fold_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 != cudaSuccess) return (int)e2;
+    k_fold_mma<<<(unsigned)nt, 256, smem2, (cudaStream_t)stream>>>(tiles, m, v, tri(tr0), mu, raw, *a, minmax);
+    MCGRA_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = sizeof(FoldSmem);
   cudaError_t e = cudaFuncSetAttribute(k_fold_adam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

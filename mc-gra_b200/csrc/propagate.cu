@@ -282,6 +282,280 @@ k_row_sumexp(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
   if (j0 + tid < n && colacc[tid] != 0.f) atomicAdd(sumexp + j0 + tid, colacc[tid]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// v2 engine: warp-level tensor-core MMA (mma.sync.m16n8k8 tf32) with the 3xTF32 split
+//   a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits), a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate
+// so results keep fp32-level accuracy (error ~2^-20 relative per product).  One CTA = tile row I, a run of up to
+// PROP_RUN consecutive J tiles: the direct product Y[I rows] accumulates in registers over the run and is flushed
+// once; the mirrored product Y[J rows] is flushed per tile.  Fragments are read straight from the staged tile:
+//   direct  : A[m=i][k=j] = xs[i][j]          (k slots t, t+4  -> j = k0+t, k0+t+4)
+//   mirrored: A[m=j][k=i] = xs[i][j]          (k slots t, t+4  -> i = k0+2t, k0+2t+1: conflict-free banks)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PROP_RUN = 4;
+constexpr int BJ_LD_EXTRA = 8;    // bj row stride KC+8  -> banks 8t+g distinct for rows t, cols g
+constexpr int BI_LD_EXTRA = 4;    // bi row stride KC+4  -> banks (2t)*(KC+4)+g = 8t+g (KC=32) distinct
+
+template <int KC>
+struct PropMmaSmem {
+  float xs[TILE][XS_LD];
+  float bj[TILE][KC + BJ_LD_EXTRA];
+  float bi[TILE][KC + BI_LD_EXTRA];
+  float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE];
+  float rowacc[TILE], colacc[TILE];
+  double red[32];
+};
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KC, bool ELEM>
+__global__ void __launch_bounds__(128, 2)
+k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
+                const float* __restrict__ B, float* __restrict__ Y, mcgra_elem_args ea) {
+  const int I = tr0 + (int)blockIdx.y;
+  const int Jbeg = (int)blockIdx.x * PROP_RUN;
+  if (Jbeg > I) return;
+  const int Jend = min(I + 1, Jbeg + PROP_RUN);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PropMmaSmem<KC>& sm = *reinterpret_cast<PropMmaSmem<KC>*>(smem_raw);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t i0 = (int64_t)I * TILE;
+  constexpr int NB = KC / 8;
+
+  // B rows of the I side (mirrored product operand) and r_I: once per run
+  for (int e = tid; e < TILE * KC / 4; e += 128) {
+    const int row = e / (KC / 4), c4 = e % (KC / 4);
+    float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + row < n) vi = reinterpret_cast<const float4*>(B + (i0 + row) * KC)[c4];
+    *reinterpret_cast<float4*>(&sm.bi[row][c4 * 4]) = vi;
+  }
+  if (ELEM) {
+    const int64_t gi = i0 + tid;
+    sm.rI[tid] = gi < n ? ea.r[gi] : 0.f;
+    if (ea.measure == MCGRA_M_KL) {
+      sm.lseAI[tid] = gi < n ? ea.lseA[gi] : 0.f;
+      sm.lseFI[tid] = gi < n ? ea.lseF[gi] : 0.f;
+    }
+    sm.rowacc[tid] = 0.f;
+  }
+  float acc1[2][NB][4];
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc1[mb][nb][q] = 0.f;
+  float v1 = 0.f, v6 = 0.f;
+
+  for (int J = Jbeg; J < Jend; ++J) {
+    const int64_t j0 = (int64_t)J * TILE;
+    const int64_t tix = tri((int64_t)I) + J - tri((int64_t)tr0);
+    const float4* src = reinterpret_cast<const float4*>(tiles + tix * TILE_ELEMS);
+    __syncthreads();                       // previous tile's consumers are done with xs / bj
+    for (int e = tid; e < TILE * KC / 4; e += 128) {
+      const int row = e / (KC / 4), c4 = e % (KC / 4);
+      float4 vj = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + row < n) vj = reinterpret_cast<const float4*>(B + (j0 + row) * KC)[c4];
+      *reinterpret_cast<float4*>(&sm.bj[row][c4 * 4]) = vj;
+    }
+    if (ELEM) {
+      const int64_t gj = j0 + tid;
+      sm.rJ[tid] = gj < n ? ea.r[gj] : 0.f;
+      if (ea.measure == MCGRA_M_KL) {
+        sm.lseAJ[tid] = gj < n ? ea.lseA[gj] : 0.f;
+        sm.lseFJ[tid] = gj < n ? ea.lseF[gj] : 0.f;
+      }
+      sm.colacc[tid] = 0.f;
+      __syncthreads();
+    }
+    // ---- stage the tile, fused element-wise terms ----
+    float col_e[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* fsrc = (ELEM && ea.Ftiles != nullptr) ? reinterpret_cast<const float4*>(ea.Ftiles + tix * TILE_ELEMS)
+                                                        : nullptr;
+    const bool interior = (J < I) && (i0 + TILE <= n);     // every entry valid
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+      const int row = it * 4 + warp;
+      const int idx = row * 32 + lane;
+      const float4 raw4 = src[idx];
+      const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
+      float xv[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+      bool ok[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ok[k] = interior || ((gj + k < gi) && (gi < n));
+        xv[k] = ok[k] ? pv.adj(xv[k]) : 0.f;
+      }
+      *reinterpret_cast<float4*>(&sm.xs[row][lane * 4]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+      if (ELEM) {
+        float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fsrc != nullptr) f4 = fsrc[idx];
+        const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+        const float ri = sm.rI[row];
+        float row_e = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!ok[k]) continue;
+          const float rj = sm.rJ[lane * 4 + k];
+          const float ah = ri * xv[k] * rj;
+          float esym = 0.f;   // e'_ij + e'_ji
+          if (ea.measure == MCGRA_M_MSE) {
+            const float df = ah - fv[k];
+            v1 = fmaf(2.f * df, df, v1);
+            esym = 4.f * ea.k1 * df;
+          } else if (ea.measure == MCGRA_M_KL) {
+            const float xij = __expf(fv[k] - sm.lseFI[row]);
+            const float xji = __expf(fv[k] - sm.lseFJ[lane * 4 + k]);
+            const float lij = ah - sm.lseAI[row];
+            const float lji = ah - sm.lseAJ[lane * 4 + k];
+            v1 += xij * ((fv[k] - sm.lseFI[row]) - lij) + xji * ((fv[k] - sm.lseFJ[lane * 4 + k]) - lji);
+            esym = ea.k1 * ((__expf(lij) - xij) + (__expf(lji) - xji));
+          }
+          if (ea.k6 != 0.f) {
+            const float q = fminf(fmaxf(ah, ENT_LO), ENT_HI);
+            const float lg = __log2f(q);
+            v6 = fmaf(2.f * q, lg, v6);
+            if (ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(2.f * ea.k6, lg + INV_LN2, esym);
+          }
+          const float tt = esym * xv[k];
+          row_e = fmaf(tt, rj, row_e);
+          col_e[k] = fmaf(tt, ri, col_e[k]);
+        }
+        row_e = warp_sum(row_e);
+        if (lane == 0) sm.rowacc[row] += row_e;
+      }
+    }
+    if (ELEM) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&sm.colacc[lane * 4 + k], col_e[k]);
+    }
+    __syncthreads();
+
+    // ---- direct product: rows i in [32 warp, 32 warp + 32), accumulate over the run ----
+#pragma unroll 2
+    for (int ks = 0; ks < TILE / 8; ++ks) {
+      const int k0 = ks * 8;
+      uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const int m0 = warp * 32 + mb * 16;
+        split_tf32(sm.xs[m0 + g][k0 + t], ahi[mb][0], alo[mb][0]);
+        split_tf32(sm.xs[m0 + g + 8][k0 + t], ahi[mb][1], alo[mb][1]);
+        split_tf32(sm.xs[m0 + g][k0 + t + 4], ahi[mb][2], alo[mb][2]);
+        split_tf32(sm.xs[m0 + g + 8][k0 + t + 4], ahi[mb][3], alo[mb][3]);
+      }
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(sm.bj[k0 + t][nb * 8 + g], bh0, bl0);
+        split_tf32(sm.bj[k0 + t + 4][nb * 8 + g], bh1, bl1);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          mma_tf32(acc1[mb][nb], alo[mb], bh0, bh1);
+          mma_tf32(acc1[mb][nb], ahi[mb], bl0, bl1);
+          mma_tf32(acc1[mb][nb], ahi[mb], bh0, bh1);
+        }
+      }
+    }
+    // ---- mirrored product: rows j in [32 warp, 32 warp + 32), flushed per tile ----
+    float acc2[2][NB][4];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc2[mb][nb][q] = 0.f;
+#pragma unroll 2
+    for (int ks = 0; ks < TILE / 8; ++ks) {
+      const int k0 = ks * 8;
+      uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const int m0 = warp * 32 + mb * 16;
+        split_tf32(sm.xs[k0 + 2 * t][m0 + g], ahi[mb][0], alo[mb][0]);
+        split_tf32(sm.xs[k0 + 2 * t][m0 + g + 8], ahi[mb][1], alo[mb][1]);
+        split_tf32(sm.xs[k0 + 2 * t + 1][m0 + g], ahi[mb][2], alo[mb][2]);
+        split_tf32(sm.xs[k0 + 2 * t + 1][m0 + g + 8], ahi[mb][3], alo[mb][3]);
+      }
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(sm.bi[k0 + 2 * t][nb * 8 + g], bh0, bl0);
+        split_tf32(sm.bi[k0 + 2 * t + 1][nb * 8 + g], bh1, bl1);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          mma_tf32(acc2[mb][nb], alo[mb], bh0, bh1);
+          mma_tf32(acc2[mb][nb], ahi[mb], bl0, bl1);
+          mma_tf32(acc2[mb][nb], ahi[mb], bh0, bh1);
+        }
+      }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      const int64_t ra = j0 + warp * 32 + mb * 16 + g, rb = ra + 8;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t),
+                              make_float2(acc2[mb][nb][0], acc2[mb][nb][1]));
+        if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t),
+                              make_float2(acc2[mb][nb][2], acc2[mb][nb][3]));
+      }
+    }
+    if (ELEM) {
+      const int64_t gj = j0 + tid;
+      if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(ea.eps_row + gj, sm.colacc[tid]);
+    }
+  }
+  // ---- flush the direct product of the run ----
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb) {
+    const int64_t ra = i0 + warp * 32 + mb * 16 + g, rb = ra + 8;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t),
+                            make_float2(acc1[mb][nb][0], acc1[mb][nb][1]));
+      if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t),
+                            make_float2(acc1[mb][nb][2], acc1[mb][nb][3]));
+    }
+  }
+  if (ELEM) {
+    __syncthreads();
+    const int64_t gi = i0 + tid;
+    if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(ea.eps_row + gi, sm.rowacc[tid]);
+    if (ea.measure != MCGRA_M_NONE) block_atomic_add_d((double)v1 * (double)ea.k1, ea.acc + MCGRA_ACC_C1, sm.red);
+    if (ea.k6 != 0.f) block_atomic_add_d((double)v6 * (double)ea.k6, ea.acc + MCGRA_ACC_C6, sm.red);
+  }
+}
+
+template <int KC, bool ELEM>
+int launch_prop_mma(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
+                    const mcgra_elem_args* elem, cudaStream_t st) {
+  const size_t smem = sizeof(PropMmaSmem<KC>);
+  cudaError_t e = cudaFuncSetAttribute(k_propagate_mma<KC, ELEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  mcgra_elem_args ea = {};
+  if (ELEM) ea = *elem;
+  if (tr1 - tr0 > 65535) return -3;
+  dim3 grid((unsigned)((tr1 + PROP_RUN - 1) / PROP_RUN), (unsigned)(tr1 - tr0));
+  k_propagate_mma<KC, ELEM><<<grid, 128, smem, st>>>(tiles, n, tr0, mu, raw, B, Y, ea);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int g_prop_engine = 1;    // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2)
+
 template <int KC, bool ELEM>
 int launch_prop(const float* tiles, int64_t n, int64_t t0, int64_t nt, const float* mu, int raw, const float* B,
                 float* Y, const mcgra_elem_args* elem, cudaStream_t st) {
@@ -298,6 +572,13 @@ int launch_prop(const float* tiles, int64_t n, int64_t t0, int64_t nt, const flo
 }  // namespace
 
 extern "C" {
+
+int mcgra_set_fold_engine_(int value);
+int mcgra_set_engine(int which, int value) {
+  if (which == 0) { g_prop_engine = value; return 0; }
+  if (which == 1) return mcgra_set_fold_engine_(value);
+  return -1;
+}
 
 int mcgra_degree(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, float* d, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
@@ -322,6 +603,15 @@ int mcgra_propagate(const float* tiles, int64_t n, int tr0, int tr1, const float
   if (nt <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t t0 = tri(tr0);
+  if (g_prop_engine == 1) {
+    if (K == 32)
+      return elem ? launch_prop_mma<32, true>(tiles, n, tr0, tr1, mu, raw, B, Y, elem, st)
+                  : launch_prop_mma<32, false>(tiles, n, tr0, tr1, mu, raw, B, Y, nullptr, st);
+    if (K == 16)
+      return elem ? launch_prop_mma<16, true>(tiles, n, tr0, tr1, mu, raw, B, Y, elem, st)
+                  : launch_prop_mma<16, false>(tiles, n, tr0, tr1, mu, raw, B, Y, nullptr, st);
+    return -1;
+  }
   if (K == 32) {
     return elem ? launch_prop<32, true>(tiles, n, t0, nt, mu, raw, B, Y, elem, st)
                 : launch_prop<32, false>(tiles, n, t0, nt, mu, raw, B, Y, nullptr, st);

@@ -76,3 +76,31 @@ def run_native_case(d, device="cuda:0", epochs=None, trace=True):
     return dict(loss=L["loss"], terms=L, x_iters=[x.cpu().numpy() for x in model._trace],
                 x_final=model.adj_changes.data.cpu().numpy(), modified_adj=model.modified_adj.cpu().numpy(),
                 model=model)
+
+
+def synthetic_case(n, f, c, measure="MSELoss", weights=None, lr_exp=-2.0, epochs=3, dataset="cora", seed=15,
+                   x0_scale=0.3, density=1e7, use=(True, True, True), weight_sup=1.0, gain=3.0, mean_deg=4.5):
+    """A fixture-shaped dict (same keys as tests/golden/attack_*.npz) for any size, targets from the oracle."""
+    import pgd_oracle as O
+    from mcgra_b200 import synth
+    g = synth.make_graph(n, f, c, seed=seed, mean_deg=mean_deg)
+    W = synth.gcn_weights(f, 16, c, seed=seed, gain=gain)
+    A = synth.dense_adj(n, g["edges"])
+    X = g["features"]
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    Xt, At = torch.from_numpy(X), torch.from_numpy(A)
+    rng = np.random.RandomState(seed + 77)
+    P = n * (n - 1) // 2
+    x0 = (rng.random_sample(P) * x0_scale * (rng.random_sample(P) < 0.5)).astype(np.float32) if x0_scale > 0 \
+        else np.zeros(P, np.float32)
+    wts = np.zeros(10)
+    for k, v in (weights or {1: 0.01, 6: 10, 7: 10, 9: 10, 10: 1000}).items():
+        wts[k - 1] = v
+    idx = np.random.RandomState(seed).permutation(n).astype(np.int64)
+    num_edges = int(0.5 * density * A.sum() / n ** 2 * n ** 2)
+    d = dict(X=X, adj=A.astype(np.uint8), labels=g["labels"], idx_attack=idx,
+             feature_adj=O.feature_adj_of(Xt, dataset).numpy(), H_A2=O.embed(Xt, At, Wt, 2).numpy(),
+             Y_A=O.victim(Xt, At, Wt).numpy(), num_edges=np.int64(num_edges), epochs=np.int64(epochs),
+             lr_exp=np.float64(lr_exp), eps=np.float64(0.0), weight_sup=np.float64(weight_sup), weights=wts,
+             measure=np.array(measure), dataset=np.array(dataset), use=np.array(use, dtype=np.bool_), x0=x0, **W)
+    return d

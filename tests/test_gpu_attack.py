@@ -30,3 +30,35 @@ def test_attack_matches_reference_golden(case):
     tol = 1e-3 if real.sum() >= 300 else 5e-3
     assert abs(O.roc_auc(real, got["modified_adj"].reshape(-1)) - float(d["auc"])) < tol
     assert abs(O.average_precision(real, got["modified_adj"].reshape(-1)) - float(d["ap"])) < tol
+
+
+@pytest.mark.parametrize("n,weights,density", [
+    (700, {1: 0.01, 6: 10, 7: 10, 9: 10, 10: 1000}, 1e7),           # Profile A, 6 tile rows, J-runs of 4 + 2
+    (1100, {1: 0.5, 2: 0.3, 6: 2.0, 7: 3.0, 9: 1.5, 10: 50.0}, 1.0),  # all MSE terms, budget binds (bisection)
+])
+def test_multi_tile_matches_oracle(n, weights, density):
+    from helpers import synthetic_case
+    d = synthetic_case(n, 40, 5, weights=weights, epochs=3, density=density, mean_deg=8.0)
+    prob, cfg = O.problem_from_npz(d)
+    ref = O.attack(prob, cfg, 3, x0=torch.from_numpy(d["x0"]))
+    got = run_native_case(d)
+    np.testing.assert_allclose(got["loss"], np.array(ref["loss"]), rtol=1e-4)
+    for a, b in zip(got["x_iters"], ref["x_iters"]):
+        assert np.max(np.abs(a - b.numpy())) < 2e-4
+    np.testing.assert_allclose(got["modified_adj"], ref["modified_adj"].numpy(), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_engines_agree(which):
+    """fp32-FFMA engine (v1) vs mma.sync 3xTF32 engine (v2) of propagate / fold on the same inputs."""
+    from mcgra_b200 import _native as N
+    d = np.load(os.path.join(GOLDEN, "attack_mse_all_n150.npz"))
+    try:
+        N.lib().mcgra_set_engine(which, 0)
+        a = run_native_case(d)
+        N.lib().mcgra_set_engine(which, 1)
+        b = run_native_case(d)
+    finally:
+        N.lib().mcgra_set_engine(which, 1)
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-6)
+    assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
