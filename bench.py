@@ -81,7 +81,7 @@ def summarise_clocks(samples):
             "samples": len(sm)}
 
 
-def build_problem(wl, device, seed=15):
+def build_problem(wl, device, seed=15, host_feature_adj=True):
     """Synthetic inputs on the HOST (pinned) + victim weights.  SURVEY.md 8(d)."""
     import torch
     from mcgra_b200 import synth
@@ -96,9 +96,13 @@ def build_problem(wl, device, seed=15):
     fa = Xd @ Xd.t()
     fa.diagonal().sub_(1.0)
     fa = torch.sigmoid_(torch.relu_(fa))
-    fa_host = torch.empty(n, n, dtype=torch.float32, pin_memory=True)
-    fa_host.copy_(fa)
-    del fa, Xd
+    if host_feature_adj:
+        fa_host = torch.empty(n, n, dtype=torch.float32, pin_memory=True)
+        fa_host.copy_(fa)
+        del fa
+    else:       # N > 1: N pinned n x n host copies would not fit comfortably; the API also accepts a device tensor
+        fa_host = fa
+    del Xd
     torch.cuda.empty_cache()
     rng = np.random.RandomState(seed)
     idx_attack = rng.permutation(n)
@@ -156,7 +160,7 @@ def run_native(a):
     wl = WORKLOADS[a.workload]
     n = wl["n"]
     P = n * (n - 1) // 2
-    prob = build_problem(wl, device)
+    prob = build_problem(wl, device, host_feature_adj=(world == 1))
     args = make_args()
     K, Wm = a.steps, a.warmup
 
@@ -224,11 +228,13 @@ def run_native(a):
             t = torch.tensor([dt], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = (prob["feature_adj"].numel() + prob["X"].numel()) * 4 + prob["labels"].numel() * 8 + n * 8
+        h2d = (prob["feature_adj"].numel() * (1 if world == 1 else 0) + prob["X"].numel()) * 4 \
+            + prob["labels"].numel() * 8 + n * 8
         e2e = {"value": K / dt, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d / K),
                "d2h_bytes_per_step": int((len(loss_hist) * 32 * 8 + 16) / K),
-               "includes": "PGDAttack.attack(epochs=K) from pinned host tensors (features, feature_adj n x n, labels, "
-                           "idx) + final ensemble + GPU AUC/AP, amortised over K",
+               "includes": "PGDAttack.attack(epochs=K) from pinned host tensors (features, labels, idx"
+                           + (", feature_adj n x n" if world == 1 else "; feature_adj n x n is device-resident at N>1")
+                           + ") + final ensemble + GPU AUC/AP, amortised over K",
                "auc": auc, "ap": ap}
 
     if rank != 0:

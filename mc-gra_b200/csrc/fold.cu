@@ -236,7 +236,7 @@ __device__ __forceinline__ void split_tf32f(float v, uint32_t& hi, uint32_t& lo)
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32f(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -310,19 +310,25 @@ k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restric
         split_tf32f(sm.u.op.wi[k0 + t + 4][m0 + g], ahi[mb][2], alo[mb][2]);
         split_tf32f(sm.u.op.wi[k0 + t + 4][m0 + g + 8], ahi[mb][3], alo[mb][3]);
       }
+      uint32_t bh[8][2], bl[8][2];
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         const int n0 = wn * 64 + nb * 8;
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32f(sm.u.op.wj[k0 + t][n0 + g], bh0, bl0);
-        split_tf32f(sm.u.op.wj[k0 + t + 4][n0 + g], bh1, bl1);
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          mma_tf32f(acc[mb][nb], alo[mb], bh0, bh1);
-          mma_tf32f(acc[mb][nb], ahi[mb], bl0, bl1);
-          mma_tf32f(acc[mb][nb], ahi[mb], bh0, bh1);
-        }
+        split_tf32f(sm.u.op.wj[k0 + t][n0 + g], bh[nb][0], bl[nb][0]);
+        split_tf32f(sm.u.op.wj[k0 + t + 4][n0 + g], bh[nb][1], bl[nb][1]);
       }
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) mma_tf32f(acc[mb][nb], alo[mb], bh[nb][0], bh[nb][1]);
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) mma_tf32f(acc[mb][nb], ahi[mb], bl[nb][0], bl[nb][1]);
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) mma_tf32f(acc[mb][nb], ahi[mb], bh[nb][0], bh[nb][1]);
     }
   }
   __syncthreads();                           // operands dead: park the product tile over them

@@ -170,6 +170,237 @@ k_pairs(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu,
   if (k2 != 0.f) block_atomic_add_d((double)v2 * (double)k2, acc + MCGRA_ACC_C2, sm.red);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// v2 engine: the three products of the pair pass on warp-level tensor-core MMA (mma.sync m16n8k8 tf32, 3xTF32):
+//   S = zI zJ^T (128x128x16), then with the coefficient tile C = dL/dS:  dz_I += C zJ,  dz_J += C^T zI.
+// Fragment loads are bank-conflict free by construction (strides / k-slot permutation noted at each array).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ZT_LD = TILE + 8;    // transposed factors [16][136]: phase-1 fragments, banks 8t+g
+constexpr int ZJ_LD = 24;          // zJ [128][24]: direct-product B fragments, banks 24t+g == 8t'+g distinct
+constexpr int ZI_LD = 20;          // zI [128][20]: mirrored-product B fragments with k slots 2t,2t+1: banks 8t+g
+
+struct PairMmaSmem {
+  float cs[TILE][CS_LD];           // coefficient tile; direct A fragments banks 4g+t, mirrored (slots 2t) 8t+g
+  float zIt[HID][ZT_LD];
+  float zJt[HID][ZT_LD];
+  float zI[TILE][ZI_LD];
+  float zJ[TILE][ZJ_LD];
+  float rI[TILE], rJ[TILE];
+  float rowacc[TILE], colacc[TILE];
+  double red[32];
+};
+
+__device__ __forceinline__ void split_tf32p(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32p(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu, int raw,
+            const float* __restrict__ zhat, const float* __restrict__ r, float k7, float k2,
+            float* __restrict__ dzhat, float* __restrict__ eps_row, double* __restrict__ acc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PairMmaSmem& sm = *reinterpret_cast<PairMmaSmem*>(smem_raw);
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+
+  for (int e = tid; e < TILE * HID; e += 256) {
+    const int a = e >> 4, k = e & 15;
+    const float vi = (i0 + a < n) ? zhat[(i0 + a) * HID + k] : 0.f;
+    const float vj = (j0 + a < n) ? zhat[(j0 + a) * HID + k] : 0.f;
+    sm.zIt[k][a] = vi; sm.zI[a][k] = vi;
+    sm.zJt[k][a] = vj; sm.zJ[a][k] = vj;
+  }
+  if (tid < TILE) {
+    sm.rI[tid] = (i0 + tid < n) ? r[i0 + tid] : 0.f;
+    sm.rJ[tid] = (j0 + tid < n) ? r[j0 + tid] : 0.f;
+    sm.rowacc[tid] = 0.f;
+    sm.colacc[tid] = 0.f;
+  }
+  __syncthreads();
+
+  // ---- phase 1: S tile, warp (wm, wn) owns rows [32 wm, +32) x cols [64 wn, +64) ----
+  const int wm = warp >> 1, wn = warp & 1;
+  float s[2][8][4];
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[mb][nb][q] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int k0 = ks * 8;
+    uint32_t ahi[2][4], alo[2][4], bh[8][2], bl[8][2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      const int m0 = wm * 32 + mb * 16;
+      split_tf32p(sm.zIt[k0 + t][m0 + g], ahi[mb][0], alo[mb][0]);
+      split_tf32p(sm.zIt[k0 + t][m0 + g + 8], ahi[mb][1], alo[mb][1]);
+      split_tf32p(sm.zIt[k0 + t + 4][m0 + g], ahi[mb][2], alo[mb][2]);
+      split_tf32p(sm.zIt[k0 + t + 4][m0 + g + 8], ahi[mb][3], alo[mb][3]);
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int n0 = wn * 64 + nb * 8;
+      split_tf32p(sm.zJt[k0 + t][n0 + g], bh[nb][0], bl[nb][0]);
+      split_tf32p(sm.zJt[k0 + t + 4][n0 + g], bh[nb][1], bl[nb][1]);
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) mma_tf32p(s[mb][nb], alo[mb], bh[nb][0], bh[nb][1]);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) mma_tf32p(s[mb][nb], ahi[mb], bl[nb][0], bl[nb][1]);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) mma_tf32p(s[mb][nb], ahi[mb], bh[nb][0], bh[nb][1]);
+  }
+
+  // ---- phase 2: element-wise on the fragments -> coefficient tile; c2's eps_row; values ----
+  const float* xt = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
+  const bool interior = (J < I) && (i0 + TILE <= n);
+  float v7 = 0.f, v2 = 0.f;
+  float colp[8][2];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) colp[nb][0] = colp[nb][1] = 0.f;
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                 // h = 0: row g, h = 1: row g + 8
+      const int a = wm * 32 + mb * 16 + g + h * 8;
+      const int gi = (int)(i0 + a);
+      const float ri = sm.rI[a];
+      float rowp = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const int b = wn * 64 + nb * 8 + 2 * t;
+        float2 x2 = make_float2(0.f, 0.f);
+        if (k2 != 0.f) x2 = *reinterpret_cast<const float2*>(xt + a * TILE + b);
+        const float xs[2] = {x2.x, x2.y};
+        float co[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int gj = (int)(j0 + b + k);
+          const bool valid = interior || ((gj < gi) && (gi < n));
+          const float sv = s[mb][nb][h * 2 + k];
+          const float pm = fmaxf(sv, 0.f);
+          float dp = 0.f;
+          if (valid) {
+            if (k7 != 0.f) {
+              const float q = fminf(fmaxf(pm, ENT_LO), ENT_HI);
+              const float lg = __log2f(q);
+              v7 = fmaf(2.f * q, lg, v7);
+              if (pm >= ENT_LO && pm <= ENT_HI) dp = 2.f * k7 * (lg + INV_LN2);
+            }
+            if (k2 != 0.f) {
+              const float M = pv.adj(xs[k]);
+              const float rj = sm.rJ[b + k];
+              const float df = ri * M * rj - pm;
+              v2 = fmaf(2.f * df, df, v2);
+              dp = fmaf(-4.f * k2, df, dp);
+              const float tt = 4.f * k2 * df * M;      // (e'_ij + e'_ji) * M_ij
+              rowp = fmaf(tt, rj, rowp);
+              colp[nb][k] = fmaf(tt, ri, colp[nb][k]);
+            }
+          }
+          co[k] = (valid && sv > 0.f) ? dp : 0.f;     // relu'(0) = 0
+        }
+        *reinterpret_cast<float2*>(&sm.cs[a][b]) = make_float2(co[0], co[1]);
+      }
+      if (k2 != 0.f) {
+        rowp += __shfl_xor_sync(0xffffffffu, rowp, 1);
+        rowp += __shfl_xor_sync(0xffffffffu, rowp, 2);
+        if (t == 0 && rowp != 0.f) atomicAdd(&sm.rowacc[a], rowp);
+      }
+    }
+  }
+  if (k2 != 0.f) {
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float c = colp[nb][k];
+        c += __shfl_xor_sync(0xffffffffu, c, 4);
+        c += __shfl_xor_sync(0xffffffffu, c, 8);
+        c += __shfl_xor_sync(0xffffffffu, c, 16);
+        if (g == 0 && c != 0.f) atomicAdd(&sm.colacc[wn * 64 + nb * 8 + 2 * t + k], c);
+      }
+  }
+  __syncthreads();
+
+  // ---- phase 3: warp w -> direct rows a in [16 w, +16) and mirrored rows b in [16 w, +16); N = 16 ----
+  {
+    float od[2][4], om[2][4];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) od[nb][q] = om[nb][q] = 0.f;
+    const int m0 = warp * 16;
+#pragma unroll 2
+    for (int ks = 0; ks < TILE / 8; ++ks) {
+      const int k0 = ks * 8;
+      uint32_t ah[4], al[4], mh[4], ml[4], bh[2][2], bl[2][2], ch[2][2], cl[2][2];
+      split_tf32p(sm.cs[m0 + g][k0 + t], ah[0], al[0]);
+      split_tf32p(sm.cs[m0 + g + 8][k0 + t], ah[1], al[1]);
+      split_tf32p(sm.cs[m0 + g][k0 + t + 4], ah[2], al[2]);
+      split_tf32p(sm.cs[m0 + g + 8][k0 + t + 4], ah[3], al[3]);
+      split_tf32p(sm.cs[k0 + 2 * t][m0 + g], mh[0], ml[0]);
+      split_tf32p(sm.cs[k0 + 2 * t][m0 + g + 8], mh[1], ml[1]);
+      split_tf32p(sm.cs[k0 + 2 * t + 1][m0 + g], mh[2], ml[2]);
+      split_tf32p(sm.cs[k0 + 2 * t + 1][m0 + g + 8], mh[3], ml[3]);
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        split_tf32p(sm.zJ[k0 + t][nb * 8 + g], bh[nb][0], bl[nb][0]);
+        split_tf32p(sm.zJ[k0 + t + 4][nb * 8 + g], bh[nb][1], bl[nb][1]);
+        split_tf32p(sm.zI[k0 + 2 * t][nb * 8 + g], ch[nb][0], cl[nb][0]);
+        split_tf32p(sm.zI[k0 + 2 * t + 1][nb * 8 + g], ch[nb][1], cl[nb][1]);
+      }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) { mma_tf32p(od[nb], al, bh[nb][0], bh[nb][1]); mma_tf32p(om[nb], ml, ch[nb][0], ch[nb][1]); }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) { mma_tf32p(od[nb], ah, bl[nb][0], bl[nb][1]); mma_tf32p(om[nb], mh, cl[nb][0], cl[nb][1]); }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) { mma_tf32p(od[nb], ah, bh[nb][0], bh[nb][1]); mma_tf32p(om[nb], mh, ch[nb][0], ch[nb][1]); }
+    }
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+      const int64_t ia = i0 + m0 + g, ib = ia + 8, ja = j0 + m0 + g, jb = ja + 8;
+      const int c0 = nb * 8 + 2 * t;
+      if (ia < n && (od[nb][0] != 0.f || od[nb][1] != 0.f))
+        atomicAdd(reinterpret_cast<float2*>(dzhat + ia * HID + c0), make_float2(od[nb][0], od[nb][1]));
+      if (ib < n && (od[nb][2] != 0.f || od[nb][3] != 0.f))
+        atomicAdd(reinterpret_cast<float2*>(dzhat + ib * HID + c0), make_float2(od[nb][2], od[nb][3]));
+      if (ja < n && (om[nb][0] != 0.f || om[nb][1] != 0.f))
+        atomicAdd(reinterpret_cast<float2*>(dzhat + ja * HID + c0), make_float2(om[nb][0], om[nb][1]));
+      if (jb < n && (om[nb][2] != 0.f || om[nb][3] != 0.f))
+        atomicAdd(reinterpret_cast<float2*>(dzhat + jb * HID + c0), make_float2(om[nb][2], om[nb][3]));
+    }
+  }
+  if (k2 != 0.f && tid < TILE) {
+    const int64_t gi = i0 + tid, gj = j0 + tid;
+    if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(eps_row + gi, sm.rowacc[tid]);
+    if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(eps_row + gj, sm.colacc[tid]);
+  }
+  if (k7 != 0.f) block_atomic_add_d((double)v7 * (double)k7, acc + MCGRA_ACC_C7, sm.red);
+  if (k2 != 0.f) block_atomic_add_d((double)v2 * (double)k2, acc + MCGRA_ACC_C2, sm.red);
+}
+
+int g_pairs_engine = 1;
+
 // x_final tiles = relu(z_i . z_j), j < i < n  (dot_product_decode of the last embedding, :300-301)
 __global__ void __launch_bounds__(256)
 k_decode_to_tiles(const float* __restrict__ z, int64_t n, int64_t t0, float* __restrict__ tiles) {
@@ -257,10 +488,21 @@ __global__ void k_row_normalize(const float* __restrict__ Z, int64_t n, int d, f
 
 extern "C" {
 
+int mcgra_set_pairs_engine_(int value) { g_pairs_engine = value; return 0; }
+
 int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* zhat,
                 const float* r, float k7, float k2, float* dzhat, float* eps_row, double* acc, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
+  if (g_pairs_engine == 1) {
+    const size_t smem2 = sizeof(PairMmaSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_pairs_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 != cudaSuccess) return (int)e2;
+    k_pairs_mma<<<(unsigned)nt, 256, smem2, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, zhat, r, k7, k2,
+                                                                    dzhat, eps_row, acc);
+    MCGRA_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = sizeof(PairSmem);
   cudaError_t e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

@@ -312,14 +312,17 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 }
 
 __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// 256 threads: all 8 warps stage the tile (and do the fused element-wise terms); then warps 0-3 run the direct
+// product (accumulating over the run) while warps 4-7 run the mirrored product of the same staged tile.
+// MMAs are issued term-major over 8 independent accumulators so dependent MMAs are >= 8 instructions apart.
 template <int KC, bool ELEM>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
                 const float* __restrict__ B, float* __restrict__ Y, mcgra_elem_args ea) {
   const int I = tr0 + (int)blockIdx.y;
@@ -333,15 +336,16 @@ k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float
   const int g = lane >> 2, t = lane & 3;
   const int64_t i0 = (int64_t)I * TILE;
   constexpr int NB = KC / 8;
+  const bool direct = warp < 4;
+  const int wq = warp & 3;
 
-  // B rows of the I side (mirrored product operand) and r_I: once per run
-  for (int e = tid; e < TILE * KC / 4; e += 128) {
+  for (int e = tid; e < TILE * KC / 4; e += 256) {
     const int row = e / (KC / 4), c4 = e % (KC / 4);
     float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i0 + row < n) vi = reinterpret_cast<const float4*>(B + (i0 + row) * KC)[c4];
     *reinterpret_cast<float4*>(&sm.bi[row][c4 * 4]) = vi;
   }
-  if (ELEM) {
+  if (ELEM && tid < TILE) {
     const int64_t gi = i0 + tid;
     sm.rI[tid] = gi < n ? ea.r[gi] : 0.f;
     if (ea.measure == MCGRA_M_KL) {
@@ -350,13 +354,13 @@ k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float
     }
     sm.rowacc[tid] = 0.f;
   }
-  float acc1[2][NB][4];
+  float acc[2][NB][4];               // direct warps: running sum over the run; mirrored warps: per tile
 #pragma unroll
   for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc1[mb][nb][q] = 0.f;
+      for (int q = 0; q < 4; ++q) acc[mb][nb][q] = 0.f;
   float v1 = 0.f, v6 = 0.f;
 
   for (int J = Jbeg; J < Jend; ++J) {
@@ -364,32 +368,41 @@ k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float
     const int64_t tix = tri((int64_t)I) + J - tri((int64_t)tr0);
     const float4* src = reinterpret_cast<const float4*>(tiles + tix * TILE_ELEMS);
     __syncthreads();                       // previous tile's consumers are done with xs / bj
-    for (int e = tid; e < TILE * KC / 4; e += 128) {
+    for (int e = tid; e < TILE * KC / 4; e += 256) {
       const int row = e / (KC / 4), c4 = e % (KC / 4);
       float4 vj = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j0 + row < n) vj = reinterpret_cast<const float4*>(B + (j0 + row) * KC)[c4];
       *reinterpret_cast<float4*>(&sm.bj[row][c4 * 4]) = vj;
     }
     if (ELEM) {
-      const int64_t gj = j0 + tid;
-      sm.rJ[tid] = gj < n ? ea.r[gj] : 0.f;
-      if (ea.measure == MCGRA_M_KL) {
-        sm.lseAJ[tid] = gj < n ? ea.lseA[gj] : 0.f;
-        sm.lseFJ[tid] = gj < n ? ea.lseF[gj] : 0.f;
+      if (tid < TILE) {
+        const int64_t gj = j0 + tid;
+        sm.rJ[tid] = gj < n ? ea.r[gj] : 0.f;
+        if (ea.measure == MCGRA_M_KL) {
+          sm.lseAJ[tid] = gj < n ? ea.lseA[gj] : 0.f;
+          sm.lseFJ[tid] = gj < n ? ea.lseF[gj] : 0.f;
+        }
+        sm.colacc[tid] = 0.f;
       }
-      sm.colacc[tid] = 0.f;
       __syncthreads();
     }
-    // ---- stage the tile, fused element-wise terms ----
+    // ---- stage the tile (8 warps, one 512 B row each per step), fused element-wise terms ----
     float col_e[4] = {0.f, 0.f, 0.f, 0.f};
     const float4* fsrc = (ELEM && ea.Ftiles != nullptr) ? reinterpret_cast<const float4*>(ea.Ftiles + tix * TILE_ELEMS)
                                                         : nullptr;
     const bool interior = (J < I) && (i0 + TILE <= n);     // every entry valid
+    float rj4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ELEM) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rj4[k] = sm.rJ[lane * 4 + k];
+    }
 #pragma unroll 4
-    for (int it = 0; it < 32; ++it) {
-      const int row = it * 4 + warp;
+    for (int it = 0; it < 16; ++it) {
+      const int row = it * 8 + warp;
       const int idx = row * 32 + lane;
       const float4 raw4 = src[idx];
+      float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ELEM && fsrc != nullptr) f4 = fsrc[idx];
       const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
       float xv[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
       bool ok[4];
@@ -400,15 +413,13 @@ k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float
       }
       *reinterpret_cast<float4*>(&sm.xs[row][lane * 4]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
       if (ELEM) {
-        float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fsrc != nullptr) f4 = fsrc[idx];
         const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
         const float ri = sm.rI[row];
         float row_e = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (!ok[k]) continue;
-          const float rj = sm.rJ[lane * 4 + k];
+          const float rj = rj4[k];
           const float ah = ri * xv[k] * rj;
           float esym = 0.f;   // e'_ij + e'_ji
           if (ea.measure == MCGRA_M_MSE) {
@@ -443,97 +454,109 @@ k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float
     }
     __syncthreads();
 
-    // ---- direct product: rows i in [32 warp, 32 warp + 32), accumulate over the run ----
+    if (direct) {
+      // ---- direct product: rows i in [32 wq, +32), accumulate over the run ----
 #pragma unroll 2
-    for (int ks = 0; ks < TILE / 8; ++ks) {
-      const int k0 = ks * 8;
-      uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const int m0 = warp * 32 + mb * 16;
-        split_tf32(sm.xs[m0 + g][k0 + t], ahi[mb][0], alo[mb][0]);
-        split_tf32(sm.xs[m0 + g + 8][k0 + t], ahi[mb][1], alo[mb][1]);
-        split_tf32(sm.xs[m0 + g][k0 + t + 4], ahi[mb][2], alo[mb][2]);
-        split_tf32(sm.xs[m0 + g + 8][k0 + t + 4], ahi[mb][3], alo[mb][3]);
-      }
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(sm.bj[k0 + t][nb * 8 + g], bh0, bl0);
-        split_tf32(sm.bj[k0 + t + 4][nb * 8 + g], bh1, bl1);
+      for (int ks = 0; ks < TILE / 8; ++ks) {
+        const int k0 = ks * 8;
+        uint32_t ahi[2][4], alo[2][4], bh[NB][2], bl[NB][2];
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
-          mma_tf32(acc1[mb][nb], alo[mb], bh0, bh1);
-          mma_tf32(acc1[mb][nb], ahi[mb], bl0, bl1);
-          mma_tf32(acc1[mb][nb], ahi[mb], bh0, bh1);
+          const int m0 = wq * 32 + mb * 16;
+          split_tf32(sm.xs[m0 + g][k0 + t], ahi[mb][0], alo[mb][0]);
+          split_tf32(sm.xs[m0 + g + 8][k0 + t], ahi[mb][1], alo[mb][1]);
+          split_tf32(sm.xs[m0 + g][k0 + t + 4], ahi[mb][2], alo[mb][2]);
+          split_tf32(sm.xs[m0 + g + 8][k0 + t + 4], ahi[mb][3], alo[mb][3]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          split_tf32(sm.bj[k0 + t][nb * 8 + g], bh[nb][0], bl[nb][0]);
+          split_tf32(sm.bj[k0 + t + 4][nb * 8 + g], bh[nb][1], bl[nb][1]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], alo[mb], bh[nb][0], bh[nb][1]);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], ahi[mb], bl[nb][0], bl[nb][1]);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], ahi[mb], bh[nb][0], bh[nb][1]);
+      }
+    } else {
+      // ---- mirrored product: rows j in [32 wq, +32), flushed per tile ----
+#pragma unroll 2
+      for (int ks = 0; ks < TILE / 8; ++ks) {
+        const int k0 = ks * 8;
+        uint32_t ahi[2][4], alo[2][4], bh[NB][2], bl[NB][2];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const int m0 = wq * 32 + mb * 16;
+          split_tf32(sm.xs[k0 + 2 * t][m0 + g], ahi[mb][0], alo[mb][0]);
+          split_tf32(sm.xs[k0 + 2 * t][m0 + g + 8], ahi[mb][1], alo[mb][1]);
+          split_tf32(sm.xs[k0 + 2 * t + 1][m0 + g], ahi[mb][2], alo[mb][2]);
+          split_tf32(sm.xs[k0 + 2 * t + 1][m0 + g + 8], ahi[mb][3], alo[mb][3]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          split_tf32(sm.bi[k0 + 2 * t][nb * 8 + g], bh[nb][0], bl[nb][0]);
+          split_tf32(sm.bi[k0 + 2 * t + 1][nb * 8 + g], bh[nb][1], bl[nb][1]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], alo[mb], bh[nb][0], bh[nb][1]);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], ahi[mb], bl[nb][0], bl[nb][1]);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], ahi[mb], bh[nb][0], bh[nb][1]);
+      }
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const int64_t ra = j0 + wq * 32 + mb * 16 + g, rb = ra + 8;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t),
+                                make_float2(acc[mb][nb][0], acc[mb][nb][1]));
+          if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t),
+                                make_float2(acc[mb][nb][2], acc[mb][nb][3]));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[mb][nb][q] = 0.f;
         }
       }
     }
-    // ---- mirrored product: rows j in [32 warp, 32 warp + 32), flushed per tile ----
-    float acc2[2][NB][4];
-#pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc2[mb][nb][q] = 0.f;
-#pragma unroll 2
-    for (int ks = 0; ks < TILE / 8; ++ks) {
-      const int k0 = ks * 8;
-      uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const int m0 = warp * 32 + mb * 16;
-        split_tf32(sm.xs[k0 + 2 * t][m0 + g], ahi[mb][0], alo[mb][0]);
-        split_tf32(sm.xs[k0 + 2 * t][m0 + g + 8], ahi[mb][1], alo[mb][1]);
-        split_tf32(sm.xs[k0 + 2 * t + 1][m0 + g], ahi[mb][2], alo[mb][2]);
-        split_tf32(sm.xs[k0 + 2 * t + 1][m0 + g + 8], ahi[mb][3], alo[mb][3]);
-      }
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(sm.bi[k0 + 2 * t][nb * 8 + g], bh0, bl0);
-        split_tf32(sm.bi[k0 + 2 * t + 1][nb * 8 + g], bh1, bl1);
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          mma_tf32(acc2[mb][nb], alo[mb], bh0, bh1);
-          mma_tf32(acc2[mb][nb], ahi[mb], bl0, bl1);
-          mma_tf32(acc2[mb][nb], ahi[mb], bh0, bh1);
-        }
-      }
-    }
-#pragma unroll
-    for (int mb = 0; mb < 2; ++mb) {
-      const int64_t ra = j0 + warp * 32 + mb * 16 + g, rb = ra + 8;
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t),
-                              make_float2(acc2[mb][nb][0], acc2[mb][nb][1]));
-        if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t),
-                              make_float2(acc2[mb][nb][2], acc2[mb][nb][3]));
-      }
-    }
-    if (ELEM) {
+    if (ELEM && tid < TILE) {
       const int64_t gj = j0 + tid;
       if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(ea.eps_row + gj, sm.colacc[tid]);
     }
   }
   // ---- flush the direct product of the run ----
+  if (direct) {
 #pragma unroll
-  for (int mb = 0; mb < 2; ++mb) {
-    const int64_t ra = i0 + warp * 32 + mb * 16 + g, rb = ra + 8;
+    for (int mb = 0; mb < 2; ++mb) {
+      const int64_t ra = i0 + wq * 32 + mb * 16 + g, rb = ra + 8;
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t),
-                            make_float2(acc1[mb][nb][0], acc1[mb][nb][1]));
-      if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t),
-                            make_float2(acc1[mb][nb][2], acc1[mb][nb][3]));
+      for (int nb = 0; nb < NB; ++nb) {
+        if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t),
+                              make_float2(acc[mb][nb][0], acc[mb][nb][1]));
+        if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t),
+                              make_float2(acc[mb][nb][2], acc[mb][nb][3]));
+      }
     }
   }
   if (ELEM) {
     __syncthreads();
-    const int64_t gi = i0 + tid;
-    if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(ea.eps_row + gi, sm.rowacc[tid]);
+    if (tid < TILE) {
+      const int64_t gi = i0 + tid;
+      if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(ea.eps_row + gi, sm.rowacc[tid]);
+    }
     if (ea.measure != MCGRA_M_NONE) block_atomic_add_d((double)v1 * (double)ea.k1, ea.acc + MCGRA_ACC_C1, sm.red);
     if (ea.k6 != 0.f) block_atomic_add_d((double)v6 * (double)ea.k6, ea.acc + MCGRA_ACC_C6, sm.red);
   }
@@ -549,7 +572,7 @@ int launch_prop_mma(const float* tiles, int64_t n, int tr0, int tr1, const float
   if (ELEM) ea = *elem;
   if (tr1 - tr0 > 65535) return -3;
   dim3 grid((unsigned)((tr1 + PROP_RUN - 1) / PROP_RUN), (unsigned)(tr1 - tr0));
-  k_propagate_mma<KC, ELEM><<<grid, 128, smem, st>>>(tiles, n, tr0, mu, raw, B, Y, ea);
+  k_propagate_mma<KC, ELEM><<<grid, 256, smem, st>>>(tiles, n, tr0, mu, raw, B, Y, ea);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }
@@ -574,9 +597,11 @@ int launch_prop(const float* tiles, int64_t n, int64_t t0, int64_t nt, const flo
 extern "C" {
 
 int mcgra_set_fold_engine_(int value);
+int mcgra_set_pairs_engine_(int value);
 int mcgra_set_engine(int which, int value) {
   if (which == 0) { g_prop_engine = value; return 0; }
   if (which == 1) return mcgra_set_fold_engine_(value);
+  if (which == 2) return mcgra_set_pairs_engine_(value);
   return -1;
 }
 
