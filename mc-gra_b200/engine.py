@@ -312,8 +312,15 @@ class PGDEngine:
     # ------------------------------------------------------------------------------------------------
     def losses(self):
         """Per-iteration totals from the accumulator history (one device->host copy).  Returns dict of
-        numpy arrays: loss (what loss.backward() is called on, :274), origin (:172-173), and each term."""
-        h = self.acc_hist[: self.step].cpu().numpy()
+        numpy arrays: loss (what loss.backward() is called on, :274), origin (:172-173), and each term.
+        Collective when world > 1 (every rank must call it)."""
+        hist = self.acc_hist[: self.step]
+        if self.world > 1:       # slots 0-7 (tile-level loss terms) are per-shard partials: sum them once, here
+            hist = hist.clone()
+            part = hist[:, :8].contiguous()
+            self._allreduce(part)
+            hist[:, :8] = part
+        h = hist.cpu().numpy()
         g = lambda k: h[:, ACC[k]]
         origin = g("NLL") + 0.001 * (g("SUMSQ") ** 0.5)
         c1, c2 = g("C1") + g("C1D"), g("C2") + g("C2D")
