@@ -35,7 +35,9 @@ extern "C" {
 #define MCGRA_MAXC 32           /* max classes handled by the node kernels */
 
 /* measures for the n x n terms c1/c2 and the n x d terms c9/c10 (topology_attack.py:190-208) */
-enum { MCGRA_M_NONE = 0, MCGRA_M_MSE = 1, MCGRA_M_KL = 2, MCGRA_M_HSIC = 3, MCGRA_M_CKA = 4, MCGRA_M_DP = 5 };
+enum { MCGRA_M_NONE = 0, MCGRA_M_MSE = 1, MCGRA_M_KL = 2, MCGRA_M_HSIC = 3, MCGRA_M_CKA = 4, MCGRA_M_DP = 5,
+       MCGRA_M_PRE = 6 /* element-wise gradient of the n x n terms supplied as tiles (Ftiles = dL/dA_ij + dL/dA_ji,
+                          Fdiag = dL/dA_ii): used for measures whose n x n contraction is computed upstream */ };
 
 /* slots of the per-iteration double-precision accumulator block `acc` (32 doubles).
  * Slots 0-15 are accumulated by the tile kernels over one rank's shard (all-reduced across ranks);
@@ -95,6 +97,7 @@ typedef struct {
   float k6;               /* c6 scale: -w6*1000/n^2, 0 = off                                          */
   double* acc;            /* accumulator block (slots C1, C6)                                         */
   float* eps_row;         /* [n]                                                                      */
+  const float* dlse;      /* [n] lseF - lseA evaluated in fp64 (KL value: log-ratio without cancellation)     */
 } mcgra_elem_args;
 int mcgra_propagate(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
                     const float* B, int K, float* Y, const mcgra_elem_args* elem, void* stream);
@@ -138,6 +141,10 @@ typedef struct {
   float* minmax;                         /* [2] set to {+inf, -inf}                                    */
   const float* lseA;                     /* KL: [n] log sum_j exp(A_hat_ij) incl. diagonal (or NULL)   */
   const float* lseF;                     /* KL: [n] log sum_j exp(F_ij)                                */
+  float* em;                             /* [n x 16] raw-branch embedding (kept for upstream measure stages)  */
+  const float* dlse;                     /* KL: [n] lseF - lseA (fp64-evaluated)                              */
+  int measure_nn;                        /* measure of the n x n terms (diagonal part in mcgra_node_rho);
+                                            `measure` above is the one of the n x d terms c9 / c10           */
 } mcgra_node_args;
 int mcgra_node_pre(const mcgra_node_args* a, void* stream);    /* r = d^-1/2 ; B1 = [r*S1 | S1]       */
 int mcgra_node_mid(const mcgra_node_args* a, void* stream);    /* after pass 1: H1,E1,S2,T2,B2        */
@@ -149,9 +156,11 @@ int mcgra_node_rho(const mcgra_node_args* a, void* stream);    /* after pass 4: 
 /* ---- pair pass over the decode gram M1 = relu(zhat zhat^T) (dot_product_decode :414-419,
  *      get_modified_adj_after :381-395): c7 entropy (:233-236) and c2 MSE (:221-229) values, their
  *      gradient w.r.t. zhat (dzhat, caller zero-fills) and c2's eps_row contribution.              */
+/* Optional precomputed inputs (MCGRA_M_PRE measures): EAt = tiles of dL/dA_ij + dL/dA_ji (their eps_row
+ * contribution is accumulated here), Ct = tiles of dL/dM1_ij + dL/dM1_ji (added to the coefficient tile).     */
 int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
-                const float* zhat, const float* r, float k7, float k2, float* dzhat, float* eps_row,
-                double* acc, void* stream);
+                const float* zhat, const float* r, float k7, float k2, const float* EAt, const float* Ct,
+                float* dzhat, float* eps_row, double* acc, void* stream);
 
 /* ---- gradient fold + Adam + box clamp (loss.backward()+optimizer.step()+clamp, :274-283) ---- */
 typedef struct {

@@ -13,7 +13,7 @@ TILE = 128
 HID = 16
 MAXC = 32
 ACC_N = 32
-M_NONE, M_MSE, M_KL, M_HSIC, M_CKA, M_DP = 0, 1, 2, 3, 4, 5
+M_NONE, M_MSE, M_KL, M_HSIC, M_CKA, M_DP, M_PRE = 0, 1, 2, 3, 4, 5, 6
 ACC = dict(C1=1, C2=2, C6=3, C7=4, SUMCLAMP=8, SUMSQ=9, NLL=16, C9=17, C10=18, C1D=19, C2D=20, C6D=21, C7D=22)
 
 c_fp = C.c_void_p     # device float* (passed as integer address)
@@ -22,7 +22,7 @@ i64 = C.c_int64
 
 class ElemArgs(C.Structure):
     _fields_ = [("r", c_fp), ("Ftiles", c_fp), ("lseA", c_fp), ("lseF", c_fp), ("measure", C.c_int),
-                ("k1", C.c_float), ("k6", C.c_float), ("acc", c_fp), ("eps_row", c_fp)]
+                ("k1", C.c_float), ("k6", C.c_float), ("acc", c_fp), ("eps_row", c_fp), ("dlse", c_fp)]
 
 
 class NodeArgs(C.Structure):
@@ -41,7 +41,7 @@ class NodeArgs(C.Structure):
                 ("w9", C.c_float), ("w10", C.c_float),
                 ("npad", i64),
                 ("d_next", c_fp), ("d_fill", C.c_float), ("acc_next", c_fp), ("minmax", c_fp),
-                ("lseA", c_fp), ("lseF", c_fp)]
+                ("lseA", c_fp), ("lseF", c_fp), ("em", c_fp), ("dlse", c_fp), ("measure_nn", C.c_int)]
 
 
 class FoldArgs(C.Structure):
@@ -71,7 +71,7 @@ _SIGS = {
     "mcgra_node_bwd1": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
     "mcgra_node_rho": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
     "mcgra_pairs": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp, C.c_float, C.c_float,
-                              c_fp, c_fp, c_fp, c_fp]),
+                              c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "mcgra_fold_adam": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp, C.c_int, C.POINTER(FoldArgs), c_fp,
                                   c_fp]),
     "mcgra_bisect_init": (C.c_int, [c_fp, c_fp, C.c_double, c_fp, c_fp, c_fp]),

@@ -148,6 +148,8 @@ k_fold_adam(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restri
         float esym = 0.f;
         if (fa.measure == MCGRA_M_MSE) {
           esym += 4.f * fa.k1 * (ah - fs[k]);
+        } else if (fa.measure == MCGRA_M_PRE) {
+          esym += fs[k];
         } else if (fa.measure == MCGRA_M_KL) {
           const float xij = __expf(fs[k] - sm.lseFI[a]);
           const float xji = __expf(fs[k] - sm.lseFJ[b]);
@@ -411,6 +413,8 @@ k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restric
         float esym = 0.f;
         if (fa.measure == MCGRA_M_MSE) {
           esym = 4.f * fa.k1 * (ah - fs[k]);
+        } else if (fa.measure == MCGRA_M_PRE) {
+          esym = fs[k];
         } else if (fa.measure == MCGRA_M_KL) {
           const float xij = __expf(fs[k] - sm.lseFI[a]);
           const float xji = __expf(fs[k] - sm.lseFJ[b0 + k]);

@@ -144,6 +144,7 @@ __global__ void k_node_head(mcgra_node_args a) {
     }
     a.masks2[i] = mask;
     st16(a.H2 + i * HID, h2);
+    if (a.em != nullptr) st16(a.em + i * HID, em);
 
     // ---- supervised head on the normalised branch (topology_attack.py:167,172) ----
     float lg[MCGRA_MAXC];
@@ -356,17 +357,18 @@ __global__ void k_node_rho(mcgra_node_args a) {
     // diagonal entry A_hat_ii = r^2 of the element-wise terms
     const float aii = r * r;
     float eii = 0.f;
-    if (a.k1 != 0.f && a.measure == MCGRA_M_MSE) {
+    if (a.k1 != 0.f && a.measure_nn == MCGRA_M_MSE) {
       const float f = a.Fdiag ? a.Fdiag[i] : 0.f;
       eii += 2.f * a.k1 * (aii - f);
       v1 = (double)a.k1 * (double)((aii - f) * (aii - f));
-    } else if (a.k1 != 0.f && a.measure == MCGRA_M_KL) {
+    } else if (a.k1 != 0.f && a.measure_nn == MCGRA_M_KL) {
       const float f = a.Fdiag ? a.Fdiag[i] : 0.f;
       const float xii = expf(f - a.lseF[i]);
       const float lii = aii - a.lseA[i];
       eii += a.k1 * (expf(lii) - xii);
-      v1 = (double)a.k1 * (double)(xii * ((f - a.lseF[i]) - lii));
+      v1 = (double)a.k1 * (double)(xii * ((f - aii) - a.dlse[i]));
     }
+    if (a.measure_nn == MCGRA_M_PRE && a.Fdiag != nullptr) eii += a.Fdiag[i];
     if (a.k6 != 0.f) {
       eii += a.k6 * ent_grad(aii);
       v6 = (double)a.k6 * (double)ent_val(aii);

@@ -22,6 +22,7 @@ struct PairSmem {
 __global__ void __launch_bounds__(256, 2)
 k_pairs(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu, int raw,
         const float* __restrict__ zhat, const float* __restrict__ r, float k7, float k2,
+        const float* __restrict__ EAt, const float* __restrict__ Ct,
         float* __restrict__ dzhat, float* __restrict__ eps_row, double* __restrict__ acc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PairSmem& sm = *reinterpret_cast<PairSmem*>(smem_raw);
@@ -67,6 +68,9 @@ k_pairs(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu,
 
   // ---- element-wise stage: values, coefficient tile, c2's eps_row ----
   const float* xt = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
+  const float* eat = EAt ? EAt + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+  const float* ctt = Ct ? Ct + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+  const bool needx = (k2 != 0.f) || (eat != nullptr);
   float v7 = 0.f, v2 = 0.f;
   float colp[8];
 #pragma unroll
@@ -80,9 +84,13 @@ k_pairs(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu,
 #pragma unroll
     for (int cg = 0; cg < 2; ++cg) {
       const int b0 = cg * 64 + tx * 4;
-      float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k2 != 0.f) x4 = *reinterpret_cast<const float4*>(xt + a * TILE + b0);
+      float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = x4, c4p = x4;
+      if (needx) x4 = *reinterpret_cast<const float4*>(xt + a * TILE + b0);
+      if (eat) e4 = *reinterpret_cast<const float4*>(eat + a * TILE + b0);
+      if (ctt) c4p = *reinterpret_cast<const float4*>(ctt + a * TILE + b0);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float es[4] = {e4.x, e4.y, e4.z, e4.w};
+      const float cp[4] = {c4p.x, c4p.y, c4p.z, c4p.w};
       float co[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -107,18 +115,24 @@ k_pairs(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu,
             rowp += t * rj;
             colp[cg * 4 + k] += t * ri;
           }
+          if (eat) {
+            const float t = es[k] * pv.adj(xs[k]);
+            rowp += t * sm.rJ[b];
+            colp[cg * 4 + k] += t * ri;
+          }
+          dp += cp[k];
         }
         co[k] = (valid && sv > 0.f) ? dp : 0.f;     // relu'(0) = 0
       }
       *reinterpret_cast<float4*>(&sm.cs[a][b0]) = make_float4(co[0], co[1], co[2], co[3]);
     }
-    if (k2 != 0.f) {
+    if (needx) {
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) rowp += __shfl_xor_sync(0xffffffffu, rowp, o);
       if (tx == 0) sm.rowacc[a] = rowp;
     }
   }
-  if (k2 != 0.f) {
+  if (needx) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int b = (q < 4) ? (tx * 4 + q) : (64 + tx * 4 + q - 4);
@@ -161,7 +175,7 @@ k_pairs(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu,
       }
     }
   }
-  if (k2 != 0.f && tid < TILE) {
+  if (needx && tid < TILE) {
     const int64_t gi = i0 + tid, gj = j0 + tid;
     if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(eps_row + gi, sm.rowacc[tid]);
     if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(eps_row + gj, sm.colacc[tid]);
@@ -204,6 +218,7 @@ __device__ __forceinline__ void mma_tf32p(float* c, const uint32_t* a, uint32_t 
 __global__ void __launch_bounds__(256, 2)
 k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu, int raw,
             const float* __restrict__ zhat, const float* __restrict__ r, float k7, float k2,
+            const float* __restrict__ EAt, const float* __restrict__ Ct,
             float* __restrict__ dzhat, float* __restrict__ eps_row, double* __restrict__ acc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PairMmaSmem& sm = *reinterpret_cast<PairMmaSmem*>(smem_raw);
@@ -272,6 +287,9 @@ k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
 
   // ---- phase 2: element-wise on the fragments -> coefficient tile; c2's eps_row; values ----
   const float* xt = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
+  const float* eat = EAt ? EAt + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+  const float* ctt = Ct ? Ct + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+  const bool needx = (k2 != 0.f) || (eat != nullptr);
   const bool interior = (J < I) && (i0 + TILE <= n);
   float v7 = 0.f, v2 = 0.f;
   float colp[8][2];
@@ -288,9 +306,13 @@ k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         const int b = wn * 64 + nb * 8 + 2 * t;
-        float2 x2 = make_float2(0.f, 0.f);
-        if (k2 != 0.f) x2 = *reinterpret_cast<const float2*>(xt + a * TILE + b);
+        float2 x2 = make_float2(0.f, 0.f), e2 = x2, c2p = x2;
+        if (needx) x2 = *reinterpret_cast<const float2*>(xt + a * TILE + b);
+        if (eat) e2 = *reinterpret_cast<const float2*>(eat + a * TILE + b);
+        if (ctt) c2p = *reinterpret_cast<const float2*>(ctt + a * TILE + b);
         const float xs[2] = {x2.x, x2.y};
+        const float es[2] = {e2.x, e2.y};
+        const float cp[2] = {c2p.x, c2p.y};
         float co[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -316,19 +338,25 @@ k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
               rowp = fmaf(tt, rj, rowp);
               colp[nb][k] = fmaf(tt, ri, colp[nb][k]);
             }
+            if (eat) {
+              const float tt = es[k] * pv.adj(xs[k]);
+              rowp = fmaf(tt, sm.rJ[b + k], rowp);
+              colp[nb][k] = fmaf(tt, ri, colp[nb][k]);
+            }
+            dp += cp[k];
           }
           co[k] = (valid && sv > 0.f) ? dp : 0.f;     // relu'(0) = 0
         }
         *reinterpret_cast<float2*>(&sm.cs[a][b]) = make_float2(co[0], co[1]);
       }
-      if (k2 != 0.f) {
+      if (needx) {
         rowp += __shfl_xor_sync(0xffffffffu, rowp, 1);
         rowp += __shfl_xor_sync(0xffffffffu, rowp, 2);
         if (t == 0 && rowp != 0.f) atomicAdd(&sm.rowacc[a], rowp);
       }
     }
   }
-  if (k2 != 0.f) {
+  if (needx) {
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
@@ -390,7 +418,7 @@ k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
         atomicAdd(reinterpret_cast<float2*>(dzhat + jb * HID + c0), make_float2(om[nb][2], om[nb][3]));
     }
   }
-  if (k2 != 0.f && tid < TILE) {
+  if (needx && tid < TILE) {
     const int64_t gi = i0 + tid, gj = j0 + tid;
     if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(eps_row + gi, sm.rowacc[tid]);
     if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(eps_row + gj, sm.colacc[tid]);
@@ -491,7 +519,8 @@ extern "C" {
 int mcgra_set_pairs_engine_(int value) { g_pairs_engine = value; return 0; }
 
 int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* zhat,
-                const float* r, float k7, float k2, float* dzhat, float* eps_row, double* acc, void* stream) {
+                const float* r, float k7, float k2, const float* EAt, const float* Ct, float* dzhat, float* eps_row,
+                double* acc, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
   if (g_pairs_engine == 1) {
@@ -499,15 +528,15 @@ int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu
     cudaError_t e2 = cudaFuncSetAttribute(k_pairs_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e2 != cudaSuccess) return (int)e2;
     k_pairs_mma<<<(unsigned)nt, 256, smem2, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, zhat, r, k7, k2,
-                                                                    dzhat, eps_row, acc);
+                                                                    EAt, Ct, dzhat, eps_row, acc);
     MCGRA_LAUNCH_CHECK();
     return 0;
   }
   const size_t smem = sizeof(PairSmem);
   cudaError_t e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k_pairs<<<(unsigned)nt, 256, smem, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, zhat, r, k7, k2, dzhat,
-                                                              eps_row, acc);
+  k_pairs<<<(unsigned)nt, 256, smem, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, zhat, r, k7, k2, EAt, Ct,
+                                                              dzhat, eps_row, acc);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }

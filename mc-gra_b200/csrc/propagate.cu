@@ -23,7 +23,7 @@ struct PropSmem {
   float xs[TILE][XS_LD];
   float bj[TILE][KC];
   float bi[TILE][KC];
-  float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE];
+  float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE], dlI[TILE], dlJ[TILE];
   float rowacc[TILE], colacc[TILE];
   double red[32];
 };
@@ -59,6 +59,8 @@ k_propagate(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
       sm.lseAJ[tid] = gj < n ? ea.lseA[gj] : 0.f;
       sm.lseFI[tid] = gi < n ? ea.lseF[gi] : 0.f;
       sm.lseFJ[tid] = gj < n ? ea.lseF[gj] : 0.f;
+      sm.dlI[tid] = gi < n ? ea.dlse[gi] : 0.f;
+      sm.dlJ[tid] = gj < n ? ea.dlse[gj] : 0.f;
     }
     sm.colacc[tid] = 0.f;
     __syncthreads();
@@ -106,7 +108,7 @@ k_propagate(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
           const float xji = __expf(fv[k] - sm.lseFJ[lane * 4 + k]);
           const float lij = ah - sm.lseAI[row];
           const float lji = ah - sm.lseAJ[lane * 4 + k];
-          v1 += xij * ((fv[k] - sm.lseFI[row]) - lij) + xji * ((fv[k] - sm.lseFJ[lane * 4 + k]) - lji);
+          v1 += xij * ((fv[k] - ah) - sm.dlI[row]) + xji * ((fv[k] - ah) - sm.dlJ[lane * 4 + k]);
           esym += ea.k1 * ((__expf(lij) - xij) + (__expf(lji) - xji));
         }
         if (ea.k6 != 0.f) {
@@ -301,7 +303,7 @@ struct PropMmaSmem {
   float xs[TILE][XS_LD];
   float bj[TILE][KC + BJ_LD_EXTRA];
   float bi[TILE][KC + BI_LD_EXTRA];
-  float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE];
+  float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE], dlI[TILE], dlJ[TILE];
   float rowacc[TILE], colacc[TILE];
   double red[32];
 };
@@ -351,6 +353,7 @@ k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float
     if (ea.measure == MCGRA_M_KL) {
       sm.lseAI[tid] = gi < n ? ea.lseA[gi] : 0.f;
       sm.lseFI[tid] = gi < n ? ea.lseF[gi] : 0.f;
+      sm.dlI[tid] = gi < n ? ea.dlse[gi] : 0.f;
     }
     sm.rowacc[tid] = 0.f;
   }
@@ -381,6 +384,7 @@ k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float
         if (ea.measure == MCGRA_M_KL) {
           sm.lseAJ[tid] = gj < n ? ea.lseA[gj] : 0.f;
           sm.lseFJ[tid] = gj < n ? ea.lseF[gj] : 0.f;
+          sm.dlJ[tid] = gj < n ? ea.dlse[gj] : 0.f;
         }
         sm.colacc[tid] = 0.f;
       }
@@ -431,7 +435,7 @@ k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float
             const float xji = __expf(fv[k] - sm.lseFJ[lane * 4 + k]);
             const float lij = ah - sm.lseAI[row];
             const float lji = ah - sm.lseAJ[lane * 4 + k];
-            v1 += xij * ((fv[k] - sm.lseFI[row]) - lij) + xji * ((fv[k] - sm.lseFJ[lane * 4 + k]) - lji);
+            v1 += xij * ((fv[k] - ah) - sm.dlI[row]) + xji * ((fv[k] - ah) - sm.dlJ[lane * 4 + k]);
             esym = ea.k1 * ((__expf(lij) - xij) + (__expf(lji) - xji));
           }
           if (ea.k6 != 0.f) {

@@ -87,42 +87,57 @@ class PGDEngine:
         nn2 = float(n) * float(n)
         sgn = -1.0 if measure == "HSIC" else 1.0
         self.c1_active = False
-        self.Ft = self.Fdiag = self.lseF = None
+        self.Ft = self.Fdiag = self.lseF = self.Ct = self.F_dense = None
         self.k1 = self.k2 = 0.0
         self.meas_nn = N.M_NONE       # measure code used by the element-wise n x n kernels
-        if self.measure in (N.M_HSIC, N.M_CKA, N.M_DP) and (w1 != 0 or w2 != 0):
-            raise NotImplementedError(
-                f"measure {measure} on the n x n terms c1/c2 needs the dense tcgen05 contraction (DESIGN.md, "
-                "row K6) which is not built yet; n x d terms c9/c10 are supported")
+        self.idx = idx
+        # Which engine evaluates the n x n terms c1 / c2:
+        #   "native": fused element-wise kernels (MSELoss; KL when only c1 is on)
+        #   "dense" : HSIC / CKA / DP (n^3 contractions) and KL's c2 -- evaluated upstream on dense n x n tensors with
+        #             library GEMMs + autograd (stop-gap for the tcgen05 contraction K6) and handed to the
+        #             native kernels as pre-computed gradient tiles (MCGRA_M_PRE)
+        fa = None
         if w1 != 0 and feature_adj is not None:
             fa = feature_adj.to(dev)
             # topology_attack.py:212: the term is skipped when feature_adj is constant
             if bool(fa.max() != fa.min()):
                 self.c1_active = True
                 fa = fa.to(torch.float32).contiguous()
+        native_nn = (self.measure == N.M_MSE) or (self.measure == N.M_KL and w2 == 0)
+        self.nn_mode = "native" if native_nn else "dense"
+        if not (self.c1_active or w2 != 0):
+            self.nn_mode = "off"
+        self.w1, self.w2 = w1, w2
+        if self.nn_mode == "native":
+            if self.c1_active:
                 self.Ft = torch.zeros(max(self.ntiles, 1) * TILE * TILE, **f32)
                 self.Fdiag = torch.zeros(n, **f32)
                 call("mcgra_dense_to_tiles", ptr(fa), n, n, self.tr0, self.tr1, 1, ptr(self.Ft), ptr(self.Fdiag),
                      N.stream_ptr())
-                if world > 1:
+                if world > 1:     # each rank wrote the diagonal of its own tile rows only
                     self._allreduce(self.Fdiag)
                 self.meas_nn = self.measure
                 if self.measure == N.M_MSE:
                     self.k1 = w1 * 1000 * ALIGN["c1"] / nn2
-                elif self.measure == N.M_KL:
+                else:
                     self.k1 = w1 * 1000 * ALIGN["c1"] / float(n)
-                    self.lseF = torch.logsumexp(fa, dim=1).contiguous()
-                del fa
-        if w2 != 0:
-            if self.measure != N.M_MSE:
-                raise NotImplementedError("c2 (w2) is built for --measure=MSELoss only so far (DESIGN.md)")
-            self.k2 = w2 * 100 * ALIGN["c2"] / nn2
+                    self.lseF64 = torch.logsumexp(fa.double(), dim=1)
+                    self.lseF = self.lseF64.float().contiguous()
+            if w2 != 0:
+                self.k2 = w2 * 100 * ALIGN["c2"] / nn2
+        elif self.nn_mode == "dense":
+            self.F_dense = fa if self.c1_active else None
+            self.Ft = torch.zeros(max(self.ntiles, 1) * TILE * TILE, **f32)      # dL/dA_ij + dL/dA_ji
+            self.Ct = torch.zeros(max(self.ntiles, 1) * TILE * TILE, **f32)      # dL/dM1_ij + dL/dM1_ji
+            self.Fdiag = torch.zeros(n, **f32)
+            self.meas_nn = N.M_PRE
+            self.sgn = sgn
+        del fa
         self.k6 = -w6 * 100 * ALIGN["c6"] / nn2
         self.k7 = -w7 * ALIGN["c7"] / nn2
+        self.nd_native = self.measure in (N.M_MSE, N.M_KL)
         self.w9 = sgn * w9 * ALIGN["c9"]
         self.w10 = sgn * w10 * ALIGN["c10"]
-        if self.measure in (N.M_HSIC, N.M_CKA, N.M_DP) and (w9 != 0 or w10 != 0):
-            raise NotImplementedError(f"measure {measure} on c9/c10: n x d HSIC/CKA/DP stage not built yet")
         self.budget = float(num_edges) if num_edges is not None else float("inf")
         self.proj_possible = self.budget < float(self.P)
 
@@ -150,11 +165,14 @@ class PGDEngine:
         (self.S2, self.T2, self.H2, self.dZ2, self.dZ1, self.dQ1, self.dQ2, self.demd, self.zhat,
          self.dzhat) = (z(n, HID) for _ in range(10))
         self.inv_norm, self.eps_row, self.rho = z(n), z(n), z(n)
+        self.em = z(n, HID)
         self.masks = torch.zeros(n, dtype=torch.int32, device=dev)
         self.masks2 = torch.zeros(n, dtype=torch.int32, device=dev)
         self.Wt = z(128, self.npad)
-        self.sumexp = z(n) if self.meas_nn == N.M_KL else None
-        self.lseA = z(n) if self.meas_nn == N.M_KL else None
+        kl_native = self.meas_nn == N.M_KL and self.nn_mode == "native"
+        self.sumexp = z(n) if kl_native else None
+        self.lseA = z(n) if kl_native else None
+        self.dlse = z(n) if kl_native else None
 
         self.set_parameter(x0)
 
@@ -201,16 +219,19 @@ class PGDEngine:
         a.eps_row, a.rho, a.Wt = ptr(self.eps_row), ptr(self.rho), ptr(self.Wt)
         a.Fdiag = ptr(self.Fdiag)
         a.acc = self.acc_hist[t].data_ptr()
-        a.measure = self.measure
+        a.measure = self.measure                      # n x d terms c9 / c10 (node kernel handles MSE / KL)
+        a.measure_nn = self.meas_nn                   # n x n terms: diagonal part in node_rho
         a.weight_sup = self.weight_sup
-        a.k1 = self.k1 if self.c1_active else 0.0
+        a.k1 = self.k1 if (self.c1_active and self.nn_mode == "native") else 0.0
         a.k2, a.k6, a.k7 = self.k2, self.k6, self.k7
-        a.w9, a.w10 = self.w9, self.w10
+        a.w9, a.w10 = (self.w9, self.w10) if self.nd_native else (0.0, 0.0)
         a.npad = self.npad
         a.d_next, a.d_fill = ptr(self.d_next), (1.0 if self.rank == 0 else 0.0)
         a.acc_next = self.acc_hist[t + 1].data_ptr()
         a.minmax = ptr(self.minmax)
         a.lseA, a.lseF = ptr(self.lseA), ptr(self.lseF)
+        a.em = ptr(self.em)
+        a.dlse = ptr(self.dlse)
         return a
 
     def forward_stages(self, t):
@@ -220,18 +241,22 @@ class PGDEngine:
         a = self._node_args(t)
         ap = C.byref(a)
         call("mcgra_node_pre", ap, st)
-        if self.meas_nn == N.M_KL:
+        if self.meas_nn == N.M_KL and self.nn_mode == "native":
             self.sumexp.zero_()
             call("mcgra_row_sumexp", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.r), ptr(self.sumexp), st)
             self._allreduce(self.sumexp)
-            torch.log(self.sumexp + torch.exp(self.r * self.r), out=self.lseA)   # + diagonal entry r_i^2
+            lseA64 = torch.log(self.sumexp.double() + torch.exp((self.r * self.r).double()))   # + diagonal r_i^2
+            self.lseA.copy_(lseA64)
+            self.dlse.copy_(self.lseF64 - lseA64)
         ea = None
-        if self.c1_active or self.k6 != 0.0:
+        c1_native = self.c1_active and self.nn_mode == "native"
+        if c1_native or self.k6 != 0.0:
             e = N.ElemArgs()
-            e.r, e.Ftiles, e.lseA, e.lseF = ptr(self.r), ptr(self.Ft), ptr(self.lseA), ptr(self.lseF)
-            e.measure = self.meas_nn if self.c1_active else N.M_NONE
-            e.k1, e.k6 = (self.k1 if self.c1_active else 0.0), self.k6
+            e.r, e.Ftiles, e.lseA, e.lseF = ptr(self.r), (ptr(self.Ft) if c1_native else None), ptr(self.lseA), ptr(self.lseF)
+            e.measure = self.meas_nn if c1_native else N.M_NONE
+            e.k1, e.k6 = (self.k1 if c1_native else 0.0), self.k6
             e.acc, e.eps_row = self.acc_hist[t].data_ptr(), ptr(self.eps_row)
+            e.dlse = ptr(self.dlse)
             ea = C.byref(e)
         call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B1), 32, ptr(self.Y1), ea, st, tag="propagate32_elem")
         self._allreduce(self.Y1)
@@ -250,9 +275,15 @@ class PGDEngine:
         n, tr0, tr1, mu, raw = self.n, self.tr0, self.tr1, ptr(self.mu), self.raw
         a = self.forward_stages(t)
         ap = C.byref(a)
-        if self.k7 != 0.0 or self.k2 != 0.0:
+        dense = self.nn_mode == "dense"
+        if dense:
+            self._dense_stage(t)
+        if not self.nd_native and (self.w9 != 0.0 or self.w10 != 0.0):
+            self._nd_stage(t)
+        if self.k7 != 0.0 or self.k2 != 0.0 or dense:
             call("mcgra_pairs", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.zhat), ptr(self.r),
-                 self.k7, self.k2, ptr(self.dzhat), ptr(self.eps_row), self.acc_hist[t].data_ptr(), st)
+                 self.k7, self.k2, (ptr(self.Ft) if dense else None), (ptr(self.Ct) if dense else None),
+                 ptr(self.dzhat), ptr(self.eps_row), self.acc_hist[t].data_ptr(), st)
             self._allreduce(self.dzhat)
         call("mcgra_node_bwd2", ap, st)
         call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, st, tag="propagate32")
@@ -266,11 +297,12 @@ class PGDEngine:
 
         f = N.FoldArgs()
         f.n, f.npad, f.Wt, f.r, f.rho = n, self.npad, ptr(self.Wt), ptr(self.r), ptr(self.rho)
-        f.Ftiles = ptr(self.Ft) if self.c1_active else None
+        use_f = dense or (self.c1_active and self.nn_mode == "native")
+        f.Ftiles = ptr(self.Ft) if use_f else None
         f.lseA, f.lseF = ptr(self.lseA), ptr(self.lseF)
         f.zhat = ptr(self.zhat)
-        f.measure = self.meas_nn if self.c1_active else N.M_NONE
-        f.k1, f.k6, f.k2 = (self.k1 if self.c1_active else 0.0), self.k6, self.k2
+        f.measure = self.meas_nn if use_f else N.M_NONE
+        f.k1, f.k6, f.k2 = (self.k1 if use_f else 0.0), self.k6, self.k2
         f.norm_coef = self.weight_sup * 0.001
         f.lr, f.beta1, f.beta2, f.adam_eps = self.lr, 0.9, 0.999, 1e-8
         f.step = t + 1
@@ -308,6 +340,94 @@ class PGDEngine:
         # (with world > 1 the reset writes d_next = 1 on every rank; keep rank 0's only)
         if self.world > 1 and self.rank != 0:
             self.d_next.sub_(self.bstate[4])
+
+    # ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _measure_fn(name):
+        """Algebraically equal, O(n^3)-minimal forms of the reference measures (topology_attack.py:190-208):
+        linear_HSIC(X,Y) = sum (H XX^T H) o (H YY^T H) = ||(HX)^T (HY)||_F^2 (utils.py:1060-1084)."""
+        import torch.nn.functional as F
+
+        def hsic(X, Y):
+            Xc = X - X.mean(0, keepdim=True)
+            Yc = Y - Y.mean(0, keepdim=True)
+            return ((Xc.t() @ Yc) ** 2).sum()
+        if name == "HSIC":
+            return hsic
+        if name == "CKA":
+            return lambda X, Y: hsic(X, Y) / (torch.sqrt(hsic(X, X)) * torch.sqrt(hsic(Y, Y)))
+        if name == "DP":
+            return lambda X, Y: torch.norm(Y.t() @ X, p=2)
+        if name == "KL":
+            return lambda X, Y: F.kl_div(F.log_softmax(Y, dim=1), F.softmax(X, dim=1), reduction="batchmean")
+        if name == "MSELoss":
+            return lambda X, Y: F.mse_loss(X, Y)
+        raise NotImplementedError(name)
+
+    def _dense_stage(self, t):
+        """c1 / c2 for measures that contract two n x n operands (HSIC, CKA, DP) or need row statistics of both
+        (KL's c2): dense tensors + library GEMMs + autograd, results handed to the native kernels as tiles of
+        dL/dA_ij + dL/dA_ji (self.Ft), dL/dA_ii (self.Fdiag) and dL/dM1_ij + dL/dM1_ji (self.Ct)."""
+        n, st = self.n, N.stream_ptr()
+        calc = self._measure_fn(self.measure_name)
+        sgn = self.sgn
+        Md = torch.zeros(n, n, dtype=torch.float32, device=self.dev)
+        call("mcgra_tiles_to_dense", ptr(self.xt), n, self.tr0, self.tr1, ptr(self.mu), self.raw, ptr(Md), n, st)
+        self._allreduce(Md)
+        if self.raw:
+            Md.clamp_(0, 1)
+        r = self.r
+        Md.diagonal().add_(1.0)
+        A_hat = ((r[:, None] * Md) * r[None, :]).requires_grad_(True)
+        del Md
+        M1 = torch.relu(self.zhat @ self.zhat.t())
+        M1.fill_diagonal_(0.0)
+        M1.requires_grad_(True)
+        with torch.enable_grad():
+            loss = 0.0
+            c1v = c2v = None
+            if self.c1_active:
+                c1v = self.w1 * calc(self.F_dense, A_hat) * 1000 * ALIGN["c1"]
+                loss = loss + sgn * c1v
+            if self.w2 != 0:
+                c2v = self.w2 * calc(A_hat, M1) * 100 * ALIGN["c2"]
+                loss = loss + sgn * c2v
+            GA, GM = torch.autograd.grad(loss, [A_hat, M1], allow_unused=True)
+        if c1v is not None:
+            self.acc_hist[t, ACC["C1D"]] += c1v.detach().double()
+        if c2v is not None:
+            self.acc_hist[t, ACC["C2D"]] += c2v.detach().double()
+        EA = (GA + GA.t()).contiguous()
+        call("mcgra_dense_to_tiles", ptr(EA), n, n, self.tr0, self.tr1, 0, ptr(self.Ft), ptr(self.Fdiag), st)
+        if self.world > 1:       # every rank wrote only the diagonal entries of its own tile rows
+            self._allreduce(self.Fdiag)
+        self.Fdiag.mul_(0.5)
+        if GM is not None:
+            Cm = (GM + GM.t()).contiguous()
+            call("mcgra_dense_to_tiles", ptr(Cm), n, n, self.tr0, self.tr1, 0, ptr(self.Ct), None, st)
+        else:
+            self.Ct.zero_()
+
+    def _nd_stage(self, t):
+        """c9 / c10 under HSIC / CKA / DP (n x 16 and n x c operands, O(n d^2)): small library ops + autograd on the
+        embedding produced by node_head; the gradient is added to the node-level dem buffer."""
+        import torch.nn.functional as F
+        calc = self._measure_fn(self.measure_name)
+        em = self.em.detach().clone().requires_grad_(True)
+        idx = self.idx
+        with torch.enable_grad():
+            loss = 0.0
+            if self.w9 != 0.0:
+                c9 = self.w9 * calc(self.HA[idx], em[idx])
+                loss = loss + c9
+                self.acc_hist[t, ACC["C9"]] += c9.detach().double()
+            if self.w10 != 0.0:
+                p2 = torch.softmax(F.log_softmax(em @ self.Wl.t() + self.bl, dim=1), dim=1)
+                c10 = self.w10 * calc(self.YA[idx], p2[idx])
+                loss = loss + c10
+                self.acc_hist[t, ACC["C10"]] += c10.detach().double()
+            (g,) = torch.autograd.grad(loss, [em])
+        self.demd.add_(g)
 
     # ------------------------------------------------------------------------------------------------
     def losses(self):

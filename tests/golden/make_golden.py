@@ -27,12 +27,15 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-sys.path.insert(0, os.path.join(ROOT, "mc-gra_b200"))
 
 import ref_shim  # noqa: E402
 
 ref = ref_shim.load()
-import synth  # noqa: E402  (our synthetic-graph generator; data only)
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("mcgra_synth", os.path.join(ROOT, "mc-gra_b200", "synth.py"))
+synth = importlib.util.module_from_spec(_spec)     # our synthetic-graph generator (data only); loaded by path so
+_spec.loader.exec_module(synth)                    # that `models`, `utils`, ... resolve to the REFERENCE's modules
 from sklearn.metrics import auc, average_precision_score, roc_curve  # noqa: E402
 
 R_utils = ref["utils"]
@@ -306,7 +309,7 @@ def main():
         dict(name="hsic_all_n90", n=90, f=20, c=3, measure="HSIC", weights={1: 1e-4, 2: 1e-4, 6: 2.0, 7: 3.0, 9: 1e-3, 10: 5.0},
              lr_exp=-2, epochs=5, x0_scale=0.5),
         dict(name="cka_n90", n=90, f=20, c=3, measure="CKA", weights={1: 0.01, 2: 0.01, 6: 100, 7: 1.0, 9: 1.0, 10: 1.0},
-             lr_exp=-2, epochs=5, dataset="polblogs", use=(False, True, True)),
+             lr_exp=-2, epochs=5, dataset="polblogs", use=(False, True, True), x0_scale=0.4),
         dict(name="dp_n90", n=90, f=20, c=3, measure="DP", weights={1: 1e-3, 2: 1e-3, 6: 10, 7: 1.0, 9: 0.1, 10: 1.0},
              lr_exp=-2, epochs=5, dataset="brazil", x0_scale=0.3),
         dict(name="mse_sub_n90", n=90, f=20, c=3, measure="MSELoss", weights=PROFILE_A, lr_exp=-2, epochs=5, nlabel=0.6,
