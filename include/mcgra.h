@@ -205,7 +205,7 @@ int mcgra_bisect_finish(const float* tiles, int64_t n, int tr0, int tr1, const f
 int mcgra_decode_to_tiles(const float* zhat, int64_t n, int tr0, int tr1, float* tiles, void* stream);
 /* one gram term of the ensemble: out[i,j] (+)= f(Z_i . Z_j) with the dataset's decode2 variant
  * (dot_product_decode2, :421-467): variant 0 sigmoid(relu(g - I)), 1 relu(g - I),
- * 2 relu(g/rownorm_i - I) (rownorm = ||row i of ZZ^T||, given).                                     */
+ * 2 relu(g/rownorm_i - I) (rownorm = ||row i of ZZ^T||, given), 3 plain g (gcn_parameterized.py:406-416).  */
 int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const float* rownorm,
                           float* out, int64_t ld, int64_t row0, int64_t row1, void* stream);
 /* out[i,j] += (labels[i]==labels[j])                                                                */
@@ -215,6 +215,20 @@ int mcgra_label_accumulate(const int64_t* labels, int64_t n, float* out, int64_t
 /* out += in (dense, `count` floats); F.normalize(Z, p, dim=1) with eps 1e-12                          */
 int mcgra_dense_add(float* out, const float* in, int64_t count, void* stream);
 int mcgra_row_normalize(const float* Z, int64_t n, int d, float p, float* out, void* stream);
+
+/* ---- HSIC / CKA family on m x d samples (hsic.py; utils.py:803-822, 1056-1097) ----
+ * One fused pass over the m^2 pairs, no m x m kernel stored:  K = exp(-gx |xi-xj|^2), L = exp(-gy |yi-yj|^2);
+ * rowK[i] += sum_j K_ij, rowL[i] += sum_j L_ij (caller zero-fills), out[0] += sum K.L, out[1] += sum K,
+ * out[2] += sum L (device double[3], zero on entry).  tr(KHLH) = out0 - (2/m) rowK.rowL + out1*out2/m^2.       */
+int mcgra_gauss_stats(const float* X, int dx, const float* Y, int dy, int64_t m, float gx, float gy,
+                      float* rowK, float* rowL, double* out, void* stream);
+/* dense pair matrix out[m1 x m2]: mode 0 = |xi - zj|^2 (hsic.distmat), mode 1 = exp(-gamma |xi - zj|^2)        */
+int mcgra_pair_dense(const float* X, int d, int64_t m1, const float* Z, int64_t m2, int mode, float gamma,
+                     float* out, void* stream);
+/* weighted raw moments of two factor matrices (w NULL = 1): out (device double, zero on entry) =
+ * [sum w x (dx) | sum w y (dy) | sum w x y^T (dx*dy) | sum w y y^T (dy*dy)]; linear HSIC/CKA in O(n d d')     */
+int mcgra_cross_moments(const float* X, int dx, const float* Y, int dy, const float* w, int64_t n,
+                        double* out, void* stream);
 
 /* ---- AUC / AP (main.metric_pool, main.py:66-75; gcn_parameterized.py:55-65) ----
  * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU,

@@ -478,7 +478,7 @@ k_gram_accumulate(const float* __restrict__ Z, int d, int64_t n, int variant, co
     float s = 0.f;
     for (int k = 0; k < d; ++k) s = fmaf(zi[rr][k], zj[tx][k], s);
     if (variant == 2) s = s / fmaxf(rownorm[gi], 1e-12f);
-    float v = fmaxf(s - (gi == gj ? 1.f : 0.f), 0.f);
+    float v = (variant == 3) ? s : fmaxf(s - (gi == gj ? 1.f : 0.f), 0.f);
     if (variant == 0) v = 1.f / (1.f + expf(-v));
     out[gi * ld + gj] += v;
   }

@@ -1,4 +1,6 @@
 """Math utilities with the reference's names (MC-GRA/utils.py hot subset)."""
+import math
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -38,3 +40,88 @@ def accuracy(output, labels):
         labels = torch.LongTensor(labels)
     preds = output.max(1)[1].type_as(labels)
     return preds.eq(labels).double().sum() / len(labels)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# HSIC / CKA surface (utils.py:803-822, 1056-1097) on the native fused kernels (csrc/hsic.cu)
+# ----------------------------------------------------------------------------------------------------------------
+def pairwise_distances(x):
+    """utils.py:803-806."""
+    from . import hsic as _h
+    return _h.distmat(x)
+
+
+def GaussianKernelMatrix(x, sigma=5):
+    """exp(-dist / sigma) (utils.py:809-811) -> dense."""
+    from . import _native as N
+    x = x.detach().to(torch.float32).contiguous()
+    m, d = x.shape
+    out = torch.empty(m, m, dtype=torch.float32, device=x.device)
+    N.call("mcgra_pair_dense", N.ptr(x), d, m, N.ptr(x), m, 1, 1.0 / float(sigma), N.ptr(out), N.stream_ptr())
+    return out
+
+
+def HSIC(x, y, s_x=1, s_y=1):
+    """tr(L H K H) / (m-1)^2 with K = exp(-dist/s_x), L = exp(-dist/s_y) (utils.py:814-822)."""
+    from . import hsic as _h
+    tr, m = _h._tr_khlh(x, y, 1.0 / float(s_x), 1.0 / float(s_y))
+    return (tr / ((m - 1) ** 2)).float()
+
+
+class CudaCKA(object):
+    """Same methods as the reference's CudaCKA (utils.py:1056-1097)."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def centering(self, K):
+        """H K H without the dense H products (utils.py:1060-1065)."""
+        return K - K.mean(0, keepdim=True) - K.mean(1, keepdim=True) + K.mean()
+
+    def _sigma(self, X):
+        from . import hsic as _h
+        KX = _h.distmat(X)
+        return math.sqrt(float(torch.median(KX[KX != 0])))            # utils.py:1070-1072
+
+    def rbf(self, X, sigma=None):
+        from . import _native as N
+        if sigma is None:
+            sigma = self._sigma(X)
+        X = X.detach().to(torch.float32).contiguous()
+        m, d = X.shape
+        out = torch.empty(m, m, dtype=torch.float32, device=X.device)
+        N.call("mcgra_pair_dense", N.ptr(X), d, m, N.ptr(X), m, 1, 0.5 / (sigma * sigma), N.ptr(out), N.stream_ptr())
+        return out
+
+    def kernel_HSIC(self, X, Y, sigma):
+        from . import hsic as _h
+        sx = sigma if sigma is not None else self._sigma(X)
+        sy = sigma if sigma is not None else self._sigma(Y)
+        tr, _ = _h._tr_khlh(X, Y, 0.5 / (sx * sx), 0.5 / (sy * sy))
+        return tr.float()
+
+    def linear_HSIC(self, X, Y):
+        """sum (H XX^T H) . (H YY^T H) = ||(HX)^T (HY)||_F^2 (utils.py:1080-1084), from weighted moments."""
+        from . import _native as N
+        dx, dy = X.shape[1], Y.shape[1]
+        if dx > 64 or dy > 64:          # wide operands (n x n): centred cross product as a library GEMM
+            Xc = X - X.mean(0, keepdim=True)
+            Yc = Y - Y.mean(0, keepdim=True)
+            return ((Xc.t() @ Yc) ** 2).sum()
+        X = X.detach().to(torch.float32).contiguous()
+        Y = Y.detach().to(torch.float32).contiguous()
+        m = X.shape[0]
+        out = torch.zeros(dx + dy + dx * dy + dy * dy, dtype=torch.float64, device=X.device)
+        N.call("mcgra_cross_moments", N.ptr(X), dx, N.ptr(Y), dy, None, m, N.ptr(out), N.stream_ptr())
+        Sx, Sy = out[:dx], out[dx:dx + dy]
+        Sxy = out[dx + dy:dx + dy + dx * dy].view(dx, dy)
+        G = Sxy - torch.outer(Sx, Sy) / m
+        return (G ** 2).sum().float()
+
+    def linear_CKA(self, X, Y):
+        hsic = self.linear_HSIC(X, Y)
+        return hsic / (torch.sqrt(self.linear_HSIC(X, X)) * torch.sqrt(self.linear_HSIC(Y, Y)))
+
+    def kernel_CKA(self, X, Y, sigma=None):
+        hsic = self.kernel_HSIC(X, Y, sigma)
+        return hsic / (torch.sqrt(self.kernel_HSIC(X, X, sigma)) * torch.sqrt(self.kernel_HSIC(Y, Y, sigma)))

@@ -33,7 +33,10 @@ def test_attack_matches_reference_golden(case):
         for xp in xs_prev:
             xt = torch.from_numpy(np.asarray(xp)).double()
             forced.append(float(O.iteration_terms(xt, prob, cfg)[0]))
-        np.testing.assert_allclose(got["loss"], np.array(forced), rtol=1e-4)
+        # KL over n x n rows is a ~600:1 cancellation (sum_j X_ij (F_ij - A_ij) ~ 0.6 against lseF_i - lseA_i ~ 0.6
+        # for a row KL of ~1e-3): fp32 cannot hold 1e-4 on it -- the reference's own fp32 loss is 1.5e-4 from its fp64
+        # evaluation on this fixture -- so the KL tie-break tolerance is 4e-4; every other measure keeps 1e-4
+        np.testing.assert_allclose(got["loss"], np.array(forced), rtol=4e-4 if str(d["measure"]) == "KL" else 1e-4)
     xs = np.stack(got["x_iters"])
     dx = np.abs(xs - d["x_iters"])
     if str(d["measure"]) == "MSELoss":
