@@ -21,7 +21,8 @@
  *                      together with a device scalar mu; the parameter value is clamp(x' - mu, 0, 1)
  *                      (topology_attack.py:338-347).  raw != 0 means "the buffer is a user-provided raw
  *                      parameter": value = x', forward uses clamp(x',0,1) with the clamp's gradient mask
- *                      (topology_attack.py:474-478).
+ *                      (topology_attack.py:474-478).  raw == 2: the buffer already holds the parameter in [0,1]
+ *                      (mcgra_fold_adam with store_clamped, used when the edge budget can never bind).
  */
 #ifndef MCGRA_H
 #define MCGRA_H
@@ -60,7 +61,8 @@ enum {
 };
 
 int mcgra_version(void);
-/* engine selection for A/B validation: which 0 = propagate (0 fp32 FFMA, 1 mma.sync 3xTF32 [default]),
+/* engine selection for A/B validation: which 0 = propagate (0 fp32 FFMA, 1 mma.sync 3xTF32, 2 tcgen05+mma.sync
+ * hybrid, 3 auto [default]: hybrid for the plain 32-wide passes), other selectors: 0 FFMA / 1 mma.sync [default];
  * which 1 = fold, which 2 = pairs (same values).  Returns 0, or -1 for an unknown selector.           */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */
@@ -99,8 +101,11 @@ typedef struct {
   float* eps_row;         /* [n]                                                                      */
   const float* dlse;      /* [n] lseF - lseA evaluated in fp64 (KL value: log-ratio without cancellation)     */
 } mcgra_elem_args;
+/* ws (optional, may be NULL): device scratch of mcgra_propagate_ws_bytes(n, K) bytes; with it the tcgen05 engine
+ * pre-formats B once per call (tf32 hi/lo split, K-major core-matrix layout) instead of once per tile.          */
+int64_t mcgra_propagate_ws_bytes(int64_t n, int K);
 int mcgra_propagate(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
-                    const float* B, int K, float* Y, const mcgra_elem_args* elem, void* stream);
+                    const float* B, int K, float* Y, const mcgra_elem_args* elem, void* ws, void* stream);
 /* row log-sum-exp of A_hat over the shard: sumexp[i] += sum_{j != i} exp(r_i M_ij r_j) (KL measure) */
 int mcgra_row_sumexp(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
                      const float* r, float* sumexp, void* stream);
@@ -181,6 +186,7 @@ typedef struct {
   const double* acc_prev; /* accumulator block of the state the gradient was taken at (SUMSQ)         */
   double* acc_next;       /* receives SUMCLAMP, SUMSQ, XMIN, XMAX of the new x'                       */
   float* d_next;          /* [n] += row/col sums of clamp(x',0,1) (caller pre-fills with 1)           */
+  int store_clamped;      /* != 0: the budget cannot bind -> store clamp(x',0,1) (readers then use raw = 2)   */
 } mcgra_fold_args;
 /* minmax: device float[2] = {min x', max x'} (bisection bracket, :340-341); reset by mcgra_node_rho          */
 int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const float* mu, int raw,

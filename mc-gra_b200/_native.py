@@ -49,7 +49,7 @@ class FoldArgs(C.Structure):
                 ("lseA", c_fp), ("lseF", c_fp), ("zhat", c_fp), ("measure", C.c_int),
                 ("k1", C.c_float), ("k6", C.c_float), ("k2", C.c_float), ("norm_coef", C.c_float),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
-                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp)]
+                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int)]
 
 
 _SIGS = {
@@ -61,8 +61,9 @@ _SIGS = {
     "mcgra_dense_to_tiles": (C.c_int, [c_fp, i64, i64, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp]),
     "mcgra_tiles_to_dense": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, i64, c_fp]),
     "mcgra_degree": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp]),
+    "mcgra_propagate_ws_bytes": (i64, [i64, C.c_int]),
     "mcgra_propagate": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, C.c_int, c_fp,
-                                  C.POINTER(ElemArgs), c_fp]),
+                                  C.POINTER(ElemArgs), c_fp, c_fp]),
     "mcgra_row_sumexp": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp, c_fp]),
     "mcgra_node_pre": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
     "mcgra_node_mid": (C.c_int, [C.POINTER(NodeArgs), c_fp]),

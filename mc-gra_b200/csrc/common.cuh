@@ -28,6 +28,9 @@ __device__ __forceinline__ void tile_coords(int64_t t, int& I, int& J) {
 }
 
 // parameter view: value of the optimised parameter stored lazily as x' and mu (see mcgra.h)
+// raw = 0: lazy projection (buffer = un-projected Adam output x', parameter = clamp(x' - mu, 0, 1))
+// raw = 1: user-provided raw parameter (forward uses clamp(x, 0, 1) with the clamp's gradient mask)
+// raw = 2: buffer already holds the parameter in [0, 1] (budget cannot bind: the fold kernel stored the clamped value)
 struct ParamView {
   float mu;
   int raw;
@@ -35,10 +38,10 @@ struct ParamView {
     return raw ? xs : fminf(fmaxf(xs - mu, 0.f), 1.f);
   }
   __device__ __forceinline__ float adj(float xs) const {     // entry of M = clamp(param, 0, 1)
-    return fminf(fmaxf(raw ? xs : xs - mu, 0.f), 1.f);
+    return raw == 2 ? xs : fminf(fmaxf(raw ? xs : xs - mu, 0.f), 1.f);
   }
   __device__ __forceinline__ float mask(float xs) const {    // d clamp / d param (closed interval)
-    return (!raw || (xs >= 0.f && xs <= 1.f)) ? 1.f : 0.f;
+    return (raw != 1 || (xs >= 0.f && xs <= 1.f)) ? 1.f : 0.f;
   }
 };
 __device__ __forceinline__ ParamView load_view(const float* mu, int raw) {

@@ -168,11 +168,11 @@ k_fold_adam(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restri
         const float vn = fa.beta2 * vs[k] + omb2 * g * g;
         const float denom = sqrtf(vn) / sqrt_bc2 + fa.adam_eps;
         const float xn = p_ - step_size * (mn / denom);
-        xo[k] = valid ? xn : 0.f;
+        const float c = fminf(fmaxf(xn, 0.f), 1.f);
+        xo[k] = valid ? (fa.store_clamped ? c : xn) : 0.f;
         mo[k] = valid ? mn : 0.f;
         vo[k] = valid ? vn : 0.f;
         if (valid) {
-          const float c = fminf(fmaxf(xn, 0.f), 1.f);
           s_clamp += c;
           s_sq = fmaf(c, c, s_sq);
           xmin = fminf(xmin, xn);
@@ -234,7 +234,7 @@ struct FoldMmaSmem {
 };
 
 __device__ __forceinline__ void split_tf32f(float v, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(v) & 0xffffe000u;
+  hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;      // round-to-nearest tf32: unbiased split
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32f(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
@@ -428,11 +428,11 @@ k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restric
         const float vn = fa.beta2 * vs[k] + omb2 * gg * gg;
         const float denom = sqrtf(vn) * inv_sqrt_bc2 + fa.adam_eps;
         const float xn = p_ - step_size * (mn / denom);
-        xo[k] = valid ? xn : 0.f;
+        const float c = fminf(fmaxf(xn, 0.f), 1.f);
+        xo[k] = valid ? (fa.store_clamped ? c : xn) : 0.f;
         mo[k] = valid ? mn : 0.f;
         vo[k] = valid ? vn : 0.f;
         if (valid) {
-          const float c = fminf(fmaxf(xn, 0.f), 1.f);
           s_clamp += c;
           s_sq = fmaf(c, c, s_sq);
           xmin = fminf(xmin, xn);

@@ -206,8 +206,8 @@ struct PairMmaSmem {
 };
 
 __device__ __forceinline__ void split_tf32p(float v, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(v) & 0xffffe000u;
-  lo = __float_as_uint(v - __uint_as_float(hi));
+  hi = __float_as_uint(v) & 0xffffe000u;        // truncation split (2 ops): this kernel is ALU-bound on the splits;
+  lo = __float_as_uint(v - __uint_as_float(hi));   // hi + lo == v exactly, bias of the dropped lo*lo term ~2^-22
 }
 __device__ __forceinline__ void mma_tf32p(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"

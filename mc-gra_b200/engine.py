@@ -169,6 +169,7 @@ class PGDEngine:
         self.masks = torch.zeros(n, dtype=torch.int32, device=dev)
         self.masks2 = torch.zeros(n, dtype=torch.int32, device=dev)
         self.Wt = z(128, self.npad)
+        self.prop_ws = torch.empty(int(N.lib().mcgra_propagate_ws_bytes(n, 32)), dtype=torch.uint8, device=dev)
         kl_native = self.meas_nn == N.M_KL and self.nn_mode == "native"
         self.sumexp = z(n) if kl_native else None
         self.lseA = z(n) if kl_native else None
@@ -258,10 +259,10 @@ class PGDEngine:
             e.acc, e.eps_row = self.acc_hist[t].data_ptr(), ptr(self.eps_row)
             e.dlse = ptr(self.dlse)
             ea = C.byref(e)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B1), 32, ptr(self.Y1), ea, st, tag="propagate32_elem")
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B1), 32, ptr(self.Y1), ea, ptr(self.prop_ws), st, tag="propagate32_elem")
         self._allreduce(self.Y1)
         call("mcgra_node_mid", ap, st)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B2), 32, ptr(self.Y2), None, st, tag="propagate32")
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B2), 32, ptr(self.Y2), None, ptr(self.prop_ws), st, tag="propagate32")
         self._allreduce(self.Y2)
         call("mcgra_node_head", ap, st)
         return a
@@ -286,10 +287,10 @@ class PGDEngine:
                  ptr(self.dzhat), ptr(self.eps_row), self.acc_hist[t].data_ptr(), st)
             self._allreduce(self.dzhat)
         call("mcgra_node_bwd2", ap, st)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, st, tag="propagate32")
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, ptr(self.prop_ws), st, tag="propagate32")
         self._allreduce(self.Y3)
         call("mcgra_node_bwd1", ap, st)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B4), 16, ptr(self.Y4), None, st, tag="propagate16")
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B4), 16, ptr(self.Y4), None, ptr(self.prop_ws), st, tag="propagate16")
         if self.world > 1:
             self._allreduce(self.Y4)
             self._allreduce(self.eps_row)
@@ -309,9 +310,11 @@ class PGDEngine:
         f.acc_prev = self.acc_hist[t].data_ptr()
         f.acc_next = self.acc_hist[t + 1].data_ptr()
         f.d_next = ptr(self.d_next)
+        f.store_clamped = 0 if self.proj_possible else 1
         call("mcgra_fold_adam", ptr(self.xt), ptr(self.mt), ptr(self.vt), tr0, tr1, mu, raw, C.byref(f),
              ptr(self.minmax), st)
-        self.raw = 0                     # the buffer now holds the un-projected Adam output x', mu = 0
+        # the buffer now holds the un-projected Adam output x' (mu = 0), or the clamped parameter itself
+        self.raw = 0 if self.proj_possible else 2
         self.mu.zero_()
         if self.world > 1:
             import torch.distributed as dist

@@ -227,11 +227,11 @@ class PGDAttack(BaseAttack):
         call("mcgra_tiles_to_dense", ptr(xf), n, 0, T, None, 1, ptr(out), n, st)   # :302
         # embeddings / victim output on the raw decoded adjacency (:304-308): two propagations over xf
         Y = torch.zeros(n, HID, dtype=torch.float32, device=dev)
-        call("mcgra_propagate", ptr(xf), n, 0, T, None, 1, ptr(eng.S1), HID, ptr(Y), None, st)
+        call("mcgra_propagate", ptr(xf), n, 0, T, None, 1, ptr(eng.S1), HID, ptr(Y), None, None, st)
         H1 = torch.relu(Y + b1)
         T2 = (H1 @ W2).contiguous()
         Y2 = torch.zeros(n, HID, dtype=torch.float32, device=dev)
-        call("mcgra_propagate", ptr(xf), n, 0, T, None, 1, ptr(T2), HID, ptr(Y2), None, st)
+        call("mcgra_propagate", ptr(xf), n, 0, T, None, 1, ptr(T2), HID, ptr(Y2), None, None, st)
         H2 = torch.relu(Y2 + b2)
         YA2 = F.log_softmax(H2 @ Wl.t() + bl, dim=1)
         del xf
