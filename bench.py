@@ -48,7 +48,29 @@ def make_args(measure="MSELoss"):
 
 
 def clocks_sampler(stop, out, index):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (NVML, every 20 ms; falls back to
+    nvidia-smi polling when pynvml is unavailable)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        R = pynvml
+        names = [("hw_slowdown", R.nvmlClocksEventReasonHwSlowdown if hasattr(R, "nvmlClocksEventReasonHwSlowdown") else 0x8),
+                 ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+            try:
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            flags = ["Active" if (rs & bit) else "Not Active" for _, bit in names]
+            out.append(f"{sm}, {mx}, {pw:.1f}, " + ", ".join(flags))
+            stop.wait(0.02)
+        return
+    except Exception:
+        pass
     q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -77,7 +99,14 @@ def summarise_clocks(samples):
         for nme, v in zip(names, p[3:7]):
             if v.lower().startswith("active"):
                 reasons.add(nme)
-    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+    pw = []
+    for s_ in samples:
+        try:
+            pw.append(float(s_.split(",")[2]))
+        except Exception:
+            pass
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(np.min(sm)) if sm else None,
+            "sm_max_mhz": mx or None, "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons),
             "samples": len(sm)}
 
 

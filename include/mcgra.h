@@ -62,7 +62,7 @@ enum {
 
 int mcgra_version(void);
 /* engine selection for A/B validation: which 0 = propagate (0 fp32 FFMA, 1 mma.sync 3xTF32, 2 tcgen05+mma.sync
- * hybrid, 3 auto [default]: hybrid for the plain 32-wide passes), other selectors: 0 FFMA / 1 mma.sync [default];
+ * hybrid [default], 3: hybrid for the plain 32-wide passes only), other selectors: 0 FFMA / 1 mma.sync [default];
  * which 1 = fold, which 2 = pairs (same values).  Returns 0, or -1 for an unknown selector.           */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */
@@ -106,6 +106,10 @@ typedef struct {
 int64_t mcgra_propagate_ws_bytes(int64_t n, int K);
 int mcgra_propagate(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
                     const float* B, int K, float* Y, const mcgra_elem_args* elem, void* ws, void* stream);
+/* the same element-wise terms as a stand-alone streaming pass (x and F tiles read once): lets every propagation
+ * use the plain tensor-core kernels; values into elem->acc, row sums into elem->eps_row.                        */
+int mcgra_elem_stats(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
+                     const mcgra_elem_args* elem, void* stream);
 /* row log-sum-exp of A_hat over the shard: sumexp[i] += sum_{j != i} exp(r_i M_ij r_j) (KL measure) */
 int mcgra_row_sumexp(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
                      const float* r, float* sumexp, void* stream);

@@ -64,6 +64,7 @@ _SIGS = {
     "mcgra_propagate_ws_bytes": (i64, [i64, C.c_int]),
     "mcgra_propagate": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, C.c_int, c_fp,
                                   C.POINTER(ElemArgs), c_fp, c_fp]),
+    "mcgra_elem_stats": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, C.POINTER(ElemArgs), c_fp]),
     "mcgra_row_sumexp": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp, c_fp]),
     "mcgra_node_pre": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
     "mcgra_node_mid": (C.c_int, [C.POINTER(NodeArgs), c_fp]),

@@ -244,6 +244,119 @@ __device__ __forceinline__ void mma_tf32f(float* c, const uint32_t* a, uint32_t 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+
+struct EpiConst {
+  float step_size, inv_sqrt_bc2, omb1, omb2, norm_scale;
+};
+
+// Streaming epilogue of the fold: one warp = one 512 B tile row per step, UNR rows in flight.
+// FAST: the tile is interior (every entry valid) and the buffer already holds the parameter in [0,1]
+// (raw == 2), no c2 term, MEAS is the compile-time c1 measure.  The generic instantiation handles everything else.
+template <bool FAST, int MEAS, bool ENT>
+__device__ __forceinline__ void fold_stream(FoldMmaSmem& sm, const mcgra_fold_args& fa, const ParamView& pv,
+                                            const EpiConst& ec, int64_t tix, float* __restrict__ tiles,
+                                            float* __restrict__ mbuf, float* __restrict__ vbuf, int I, int J,
+                                            float& s_clamp, float& s_sq, float& xmin, float& xmax, float* colp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = fa.n;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+  float* xt = tiles + tix * TILE_ELEMS;
+  float* mt = mbuf + tix * TILE_ELEMS;
+  float* vt = vbuf + tix * TILE_ELEMS;
+  const float* ft = fa.Ftiles ? fa.Ftiles + tix * TILE_ELEMS : nullptr;
+  const bool interior = (J < I) && (i0 + TILE <= n);
+  const int b0 = lane * 4;
+  const int meas = FAST ? MEAS : fa.measure;
+  float rj4[4], rhoj4[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { rj4[k] = sm.rJ[b0 + k]; rhoj4[k] = sm.rhoJ[b0 + k]; }
+  constexpr int UNR = 4;
+#pragma unroll 1
+  for (int it = 0; it < TILE / (8 * UNR); ++it) {
+    float4 x4[UNR], m4[UNR], v4[UNR], f4[UNR];
+#pragma unroll
+    for (int uu = 0; uu < UNR; ++uu) {
+      const int a = (it * UNR + uu) * 8 + warp;
+      const int off = a * TILE + b0;
+      x4[uu] = ld4(xt + off);
+      m4[uu] = ld4(mt + off);
+      v4[uu] = ld4(vt + off);
+      f4[uu] = (ft && meas != MCGRA_M_NONE) ? ld4(ft + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int uu = 0; uu < UNR; ++uu) {
+      const int a = (it * UNR + uu) * 8 + warp;
+      const int off = a * TILE + b0;
+      const int gi = (int)(i0 + a);
+      const float ri = sm.rI[a], rhoi = sm.rhoI[a];
+      const float4 g4 = ld4(&sm.u.gt[a][b0]);
+      const float xs[4] = {x4[uu].x, x4[uu].y, x4[uu].z, x4[uu].w};
+      const float ms[4] = {m4[uu].x, m4[uu].y, m4[uu].z, m4[uu].w};
+      const float vs[4] = {v4[uu].x, v4[uu].y, v4[uu].z, v4[uu].w};
+      const float fs[4] = {f4[uu].x, f4[uu].y, f4[uu].z, f4[uu].w};
+      const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+      float sdot[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!FAST && fa.k2 != 0.f) {
+#pragma unroll
+        for (int q = 0; q < HID; ++q) {
+          const float zi = sm.zI[a][q];
+          const float4 zj = ld4(&sm.zJt[q][b0]);
+          sdot[0] = fmaf(zi, zj.x, sdot[0]); sdot[1] = fmaf(zi, zj.y, sdot[1]);
+          sdot[2] = fmaf(zi, zj.z, sdot[2]); sdot[3] = fmaf(zi, zj.w, sdot[3]);
+        }
+      }
+      float xo[4], mo[4], vo[4];
+      float rowp = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool valid = FAST ? true : (interior || (((int)(j0 + b0 + k) < gi) && (gi < n)));
+        const float p_ = FAST ? xs[k] : pv.param(xs[k]);
+        const float M = FAST ? xs[k] : pv.adj(xs[k]);
+        const float rj = rj4[k];
+        const float ah = ri * M * rj;
+        float esym = 0.f;
+        if (meas == MCGRA_M_MSE) {
+          esym = 4.f * fa.k1 * (ah - fs[k]);
+        } else if (meas == MCGRA_M_PRE) {
+          esym = fs[k];
+        } else if (meas == MCGRA_M_KL) {
+          const float xij = __expf(fs[k] - sm.lseFI[a]);
+          const float xji = __expf(fs[k] - sm.lseFJ[b0 + k]);
+          esym = fa.k1 * ((__expf(ah - sm.lseAI[a]) - xij) + (__expf(ah - sm.lseAJ[b0 + k]) - xji));
+        }
+        if (ENT && fa.k6 != 0.f && ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(2.f * fa.k6, __log2f(ah) + INV_LN2, esym);
+        if (!FAST && fa.k2 != 0.f) esym = fmaf(4.f * fa.k2, ah - fmaxf(sdot[k], 0.f), esym);
+        float gg = fmaf(ri * rj, esym, rhoi + rhoj4[k] + gs[k]);
+        if (!FAST) gg *= pv.mask(xs[k]);
+        gg = fmaf(ec.norm_scale, p_, gg);
+        const float mn = fmaf(ec.omb1, gg - ms[k], ms[k]);                 // beta1*m + (1-beta1)*g
+        const float vn = fmaf(ec.omb2, gg * gg - vs[k], vs[k]);            // beta2*v + (1-beta2)*g^2
+        // Adam: p - step * m / (sqrt(v)/sqrt(bc2) + eps); sqrt via rsqrt (1 MUFU), divide via rcp (1 MUFU)
+        const float sq = vn > 0.f ? vn * rsqrtf(vn) : 0.f;
+        const float denom = fmaf(sq, ec.inv_sqrt_bc2, fa.adam_eps);
+        const float xn = fmaf(-ec.step_size, __fdividef(mn, denom), p_);
+        const float c = fminf(fmaxf(xn, 0.f), 1.f);
+        xo[k] = valid ? (fa.store_clamped ? c : xn) : 0.f;
+        mo[k] = valid ? mn : 0.f;
+        vo[k] = valid ? vn : 0.f;
+        if (valid) {
+          s_clamp += c;
+          s_sq = fmaf(c, c, s_sq);
+          xmin = fminf(xmin, xn);
+          xmax = fmaxf(xmax, xn);
+          rowp += c;
+          colp[k] += c;
+        }
+      }
+      *reinterpret_cast<float4*>(xt + off) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+      *reinterpret_cast<float4*>(mt + off) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+      *reinterpret_cast<float4*>(vt + off) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+      rowp = warp_sum(rowp);
+      if (lane == 0 && gi < n && rowp != 0.f) atomicAdd(fa.d_next + gi, rowp);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 2)
 k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int64_t t0, const float* mu,
            int raw, mcgra_fold_args fa, float* __restrict__ minmax) {
@@ -351,103 +464,30 @@ k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restric
   const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
   const double bc1 = 1.0 - pow((double)fa.beta1, (double)fa.step);
   const double bc2 = 1.0 - pow((double)fa.beta2, (double)fa.step);
-  const float step_size = (float)((double)fa.lr / bc1);
-  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  const float omb1 = 1.f - fa.beta1, omb2 = 1.f - fa.beta2;
-  float* xt = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
-  float* mt = mbuf + (int64_t)blockIdx.x * TILE_ELEMS;
-  float* vt = vbuf + (int64_t)blockIdx.x * TILE_ELEMS;
-  const float* ft = fa.Ftiles ? fa.Ftiles + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+  EpiConst ec;
+  ec.step_size = (float)((double)fa.lr / bc1);
+  ec.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  ec.omb1 = 1.f - fa.beta1;
+  ec.omb2 = 1.f - fa.beta2;
+  ec.norm_scale = fa.norm_coef * inv_norm;
   const bool interior = (J < I) && (i0 + TILE <= n);
-  const int b0 = lane * 4;
-  float rj4[4], rhoj4[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { rj4[k] = sm.rJ[b0 + k]; rhoj4[k] = sm.rhoJ[b0 + k]; }
   float s_clamp = 0.f, s_sq = 0.f, xmin = INFINITY, xmax = -INFINITY;
   float colp[4] = {0.f, 0.f, 0.f, 0.f};
-  constexpr int UNR = 4;
-#pragma unroll 1
-  for (int it = 0; it < TILE / (8 * UNR); ++it) {
-    float4 x4[UNR], m4[UNR], v4[UNR], f4[UNR];
-#pragma unroll
-    for (int uu = 0; uu < UNR; ++uu) {
-      const int a = (it * UNR + uu) * 8 + warp;
-      const int off = a * TILE + b0;
-      x4[uu] = ld4(xt + off);
-      m4[uu] = ld4(mt + off);
-      v4[uu] = ld4(vt + off);
-      f4[uu] = ft ? ld4(ft + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // specialise the hot combinations (uniform per CTA): plain parameter view + interior tile + MSE/none + no c2
+  const bool fastview = (pv.raw == 2) && interior && fa.k2 == 0.f && fa.measure != MCGRA_M_KL;
+  if (fastview) {
+    if (fa.measure == MCGRA_M_MSE) {
+      if (fa.k6 != 0.f) fold_stream<true, MCGRA_M_MSE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+      else fold_stream<true, MCGRA_M_MSE, false>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+    } else if (fa.measure == MCGRA_M_PRE) {
+      fold_stream<true, MCGRA_M_PRE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+    } else {
+      fold_stream<true, MCGRA_M_NONE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
     }
-#pragma unroll
-    for (int uu = 0; uu < UNR; ++uu) {
-      const int a = (it * UNR + uu) * 8 + warp;
-      const int off = a * TILE + b0;
-      const int gi = (int)(i0 + a);
-      const float ri = sm.rI[a], rhoi = sm.rhoI[a];
-      const float4 g4 = ld4(&sm.u.gt[a][b0]);
-      const float xs[4] = {x4[uu].x, x4[uu].y, x4[uu].z, x4[uu].w};
-      const float ms[4] = {m4[uu].x, m4[uu].y, m4[uu].z, m4[uu].w};
-      const float vs[4] = {v4[uu].x, v4[uu].y, v4[uu].z, v4[uu].w};
-      const float fs[4] = {f4[uu].x, f4[uu].y, f4[uu].z, f4[uu].w};
-      const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
-      float sdot[4] = {0.f, 0.f, 0.f, 0.f};
-      if (fa.k2 != 0.f) {
-#pragma unroll
-        for (int q = 0; q < HID; ++q) {
-          const float zi = sm.zI[a][q];
-          const float4 zj = ld4(&sm.zJt[q][b0]);
-          sdot[0] = fmaf(zi, zj.x, sdot[0]); sdot[1] = fmaf(zi, zj.y, sdot[1]);
-          sdot[2] = fmaf(zi, zj.z, sdot[2]); sdot[3] = fmaf(zi, zj.w, sdot[3]);
-        }
-      }
-      float xo[4], mo[4], vo[4];
-      float rowp = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int gj = (int)(j0 + b0 + k);
-        const bool valid = interior || ((gj < gi) && (gi < n));
-        const float p_ = pv.param(xs[k]);
-        const float M = pv.adj(xs[k]);
-        const float rj = rj4[k];
-        const float ah = ri * M * rj;
-        float esym = 0.f;
-        if (fa.measure == MCGRA_M_MSE) {
-          esym = 4.f * fa.k1 * (ah - fs[k]);
-        } else if (fa.measure == MCGRA_M_PRE) {
-          esym = fs[k];
-        } else if (fa.measure == MCGRA_M_KL) {
-          const float xij = __expf(fs[k] - sm.lseFI[a]);
-          const float xji = __expf(fs[k] - sm.lseFJ[b0 + k]);
-          esym = fa.k1 * ((__expf(ah - sm.lseAI[a]) - xij) + (__expf(ah - sm.lseAJ[b0 + k]) - xji));
-        }
-        if (fa.k6 != 0.f && ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(2.f * fa.k6, __log2f(ah) + INV_LN2, esym);
-        if (fa.k2 != 0.f) esym = fmaf(4.f * fa.k2, ah - fmaxf(sdot[k], 0.f), esym);
-        float gg = fmaf(ri * rj, esym, rhoi + rhoj4[k] + gs[k]);
-        gg = pv.mask(xs[k]) * gg + fa.norm_coef * p_ * inv_norm;
-        const float mn = fa.beta1 * ms[k] + omb1 * gg;
-        const float vn = fa.beta2 * vs[k] + omb2 * gg * gg;
-        const float denom = sqrtf(vn) * inv_sqrt_bc2 + fa.adam_eps;
-        const float xn = p_ - step_size * (mn / denom);
-        const float c = fminf(fmaxf(xn, 0.f), 1.f);
-        xo[k] = valid ? (fa.store_clamped ? c : xn) : 0.f;
-        mo[k] = valid ? mn : 0.f;
-        vo[k] = valid ? vn : 0.f;
-        if (valid) {
-          s_clamp += c;
-          s_sq = fmaf(c, c, s_sq);
-          xmin = fminf(xmin, xn);
-          xmax = fmaxf(xmax, xn);
-          rowp += c;
-          colp[k] += c;
-        }
-      }
-      *reinterpret_cast<float4*>(xt + off) = make_float4(xo[0], xo[1], xo[2], xo[3]);
-      *reinterpret_cast<float4*>(mt + off) = make_float4(mo[0], mo[1], mo[2], mo[3]);
-      *reinterpret_cast<float4*>(vt + off) = make_float4(vo[0], vo[1], vo[2], vo[3]);
-      rowp = warp_sum(rowp);
-      if (lane == 0 && gi < n && rowp != 0.f) atomicAdd(fa.d_next + gi, rowp);
-    }
+  } else {
+    fold_stream<false, -1, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
   }
+  const int b0 = lane * 4;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (colp[k] != 0.f) atomicAdd(&sm.colacc[b0 + k], colp[k]);

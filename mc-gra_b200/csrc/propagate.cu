@@ -961,9 +961,99 @@ int launch_prop_tc(const float* tiles, int64_t n, int tr0, int tr1, const float*
 }
 
 // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2), 2 = tcgen05 + mma.sync hybrid (v3) everywhere,
-// 3 = auto (default): v3 for the plain 32-wide passes, v2 for the fused element-wise pass and the 16-wide pass
-// (measured on B200 at n = 65536: v3 5.3 ms vs v2 5.2 ms for K = 32; v2 is faster where only 8 staging warps hurt)
-int g_prop_engine = 3;
+// 3 = v3 for the plain 32-wide passes only.  Default 2: same-process A/B on B200 at n = 65536 (tools/engine_ab.py,
+// steady clocks): K = 32: v3 5.32 ms vs v2 7.04 ms; K = 16: 3.81 vs 5.41 ms
+int g_prop_engine = 2;
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Stand-alone element-wise pass (c1 MSE/KL against feature_adj, c6 entropy; values + degree-gradient row sums).
+// A pure streaming kernel (x and F tiles read once, 8 bytes per entry) that runs at full occupancy; the propagation
+// passes then all use the plain tensor-core kernels.  Same arithmetic as the fused variants above.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4)
+k_elem_stats(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu, int raw, mcgra_elem_args ea) {
+  __shared__ float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE], dlI[TILE], dlJ[TILE];
+  __shared__ float colacc[TILE];
+  __shared__ double red[32];
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+  if (tid < TILE) {
+    const int64_t gi = i0 + tid, gj = j0 + tid;
+    rI[tid] = gi < n ? ea.r[gi] : 0.f;
+    rJ[tid] = gj < n ? ea.r[gj] : 0.f;
+    if (ea.measure == MCGRA_M_KL) {
+      lseAI[tid] = gi < n ? ea.lseA[gi] : 0.f;  lseAJ[tid] = gj < n ? ea.lseA[gj] : 0.f;
+      lseFI[tid] = gi < n ? ea.lseF[gi] : 0.f;  lseFJ[tid] = gj < n ? ea.lseF[gj] : 0.f;
+      dlI[tid] = gi < n ? ea.dlse[gi] : 0.f;    dlJ[tid] = gj < n ? ea.dlse[gj] : 0.f;
+    }
+    colacc[tid] = 0.f;
+  }
+  __syncthreads();
+  const float4* src = reinterpret_cast<const float4*>(tiles + (int64_t)blockIdx.x * TILE_ELEMS);
+  const float4* fsrc = ea.Ftiles ? reinterpret_cast<const float4*>(ea.Ftiles + (int64_t)blockIdx.x * TILE_ELEMS) : nullptr;
+  const bool interior = (J < I) && (i0 + TILE <= n);
+  float rj4[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rj4[k] = rJ[lane * 4 + k];
+  float col_e[4] = {0.f, 0.f, 0.f, 0.f};
+  float v1 = 0.f, v6 = 0.f;
+#pragma unroll 4
+  for (int it = 0; it < 16; ++it) {
+    const int row = it * 8 + warp;
+    const float4 raw4 = src[row * 32 + lane];
+    float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fsrc != nullptr) f4 = fsrc[row * 32 + lane];
+    const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
+    const float xr[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+    const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+    const float ri = rI[row];
+    float row_e = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!(interior || ((gj + k < gi) && (gi < n)))) continue;
+      const float xv = pv.adj(xr[k]);
+      const float rj = rj4[k];
+      const float ah = ri * xv * rj;
+      float esym = 0.f;   // e'_ij + e'_ji
+      if (ea.measure == MCGRA_M_MSE) {
+        const float df = ah - fv[k];
+        v1 = fmaf(2.f * df, df, v1);
+        esym = 4.f * ea.k1 * df;
+      } else if (ea.measure == MCGRA_M_KL) {
+        const float xij = __expf(fv[k] - lseFI[row]);
+        const float xji = __expf(fv[k] - lseFJ[lane * 4 + k]);
+        const float lij = ah - lseAI[row];
+        const float lji = ah - lseAJ[lane * 4 + k];
+        v1 += xij * ((fv[k] - ah) - dlI[row]) + xji * ((fv[k] - ah) - dlJ[lane * 4 + k]);
+        esym = ea.k1 * ((__expf(lij) - xij) + (__expf(lji) - xji));
+      }
+      if (ea.k6 != 0.f) {
+        const float q = fminf(fmaxf(ah, ENT_LO), ENT_HI);
+        const float lg = __log2f(q);
+        v6 = fmaf(2.f * q, lg, v6);
+        if (ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(2.f * ea.k6, lg + INV_LN2, esym);
+      }
+      const float tt = esym * xv;
+      row_e = fmaf(tt, rj, row_e);
+      col_e[k] = fmaf(tt, ri, col_e[k]);
+    }
+    row_e = warp_sum(row_e);
+    if (lane == 0 && gi < n && row_e != 0.f) atomicAdd(ea.eps_row + gi, row_e);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) atomicAdd(&colacc[lane * 4 + k], col_e[k]);
+  __syncthreads();
+  if (tid < TILE) {
+    const int64_t gj = j0 + tid;
+    if (gj < n && colacc[tid] != 0.f) atomicAdd(ea.eps_row + gj, colacc[tid]);
+  }
+  if (ea.measure != MCGRA_M_NONE) block_atomic_add_d((double)v1 * (double)ea.k1, ea.acc + MCGRA_ACC_C1, red);
+  if (ea.k6 != 0.f) block_atomic_add_d((double)v6 * (double)ea.k6, ea.acc + MCGRA_ACC_C6, red);
+}
 
 template <int KC, bool ELEM>
 int launch_prop(const float* tiles, int64_t n, int64_t t0, int64_t nt, const float* mu, int raw, const float* B,
@@ -1004,6 +1094,15 @@ int mcgra_row_sumexp(const float* tiles, int64_t n, int tr0, int tr1, const floa
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
   k_row_sumexp<<<(unsigned)nt, 128, 0, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, r, sumexp);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_elem_stats(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
+                     const mcgra_elem_args* elem, void* stream) {
+  const int64_t nt = tri(tr1) - tri(tr0);
+  if (nt <= 0 || elem == nullptr) return 0;
+  k_elem_stats<<<(unsigned)nt, 256, 0, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, *elem);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }

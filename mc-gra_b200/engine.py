@@ -175,6 +175,7 @@ class PGDEngine:
         self.lseA = z(n) if kl_native else None
         self.dlse = z(n) if kl_native else None
 
+        self.split_elem = True     # element-wise c1/c6 terms as a separate streaming pass (faster than fused, see DESIGN)
         self.set_parameter(x0)
 
     # ------------------------------------------------------------------------------------------------
@@ -259,7 +260,12 @@ class PGDEngine:
             e.acc, e.eps_row = self.acc_hist[t].data_ptr(), ptr(self.eps_row)
             e.dlse = ptr(self.dlse)
             ea = C.byref(e)
-        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B1), 32, ptr(self.Y1), ea, ptr(self.prop_ws), st, tag="propagate32_elem")
+        if ea is not None and self.split_elem:
+            # element-wise terms as their own streaming pass; the propagation then runs on the plain tcgen05 kernel
+            call("mcgra_elem_stats", ptr(self.xt), n, tr0, tr1, mu, raw, ea, st, tag="elem_stats")
+            ea = None
+        call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B1), 32, ptr(self.Y1), ea, ptr(self.prop_ws), st,
+             tag="propagate32" if ea is None else "propagate32_elem")
         self._allreduce(self.Y1)
         call("mcgra_node_mid", ap, st)
         call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B2), 32, ptr(self.Y2), None, ptr(self.prop_ws), st, tag="propagate32")

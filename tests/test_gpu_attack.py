@@ -82,7 +82,7 @@ def test_engines_agree(which):
         N.lib().mcgra_set_engine(which, 1)
         b = run_native_case(d)
     finally:
-        N.lib().mcgra_set_engine(which, 3 if which == 0 else 1)
+        N.lib().mcgra_set_engine(which, 2 if which == 0 else 1)
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-6)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
 
@@ -111,7 +111,7 @@ def test_tcgen05_propagate_engine_agrees(case):
         N.lib().mcgra_set_engine(0, 2)
         b = run_native_case(d)
     finally:
-        N.lib().mcgra_set_engine(0, 3)
+        N.lib().mcgra_set_engine(0, 2)
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-5)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5
 
@@ -126,6 +126,6 @@ def test_tcgen05_propagate_multi_tile():
         N.lib().mcgra_set_engine(0, 2)
         b = run_native_case(d)
     finally:
-        N.lib().mcgra_set_engine(0, 3)
+        N.lib().mcgra_set_engine(0, 2)
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-5)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5
