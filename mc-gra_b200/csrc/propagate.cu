@@ -936,10 +936,251 @@ k_propagate_tc(const float* __restrict__ tiles, int64_t n, int tr0, const float*
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// v4 engine: BOTH products on tcgen05.
+//   direct   Y[I] += T   * B[J] : A = staged tile (smem, K-major core layout), B = B[J] block (smem)  -> D1 (TMEM)
+//   mirrored Y[J] += T^T * B[I] : A = T^T held in TENSOR MEMORY (lane = column j, one 32-bit TMEM column per row i),
+//                                 written with tcgen05.st by 128 threads that read the staged tile column-wise
+//                                 (bank = j mod 32: conflict free), B = B[I] block (smem)                -> D2 (TMEM)
+// so the tile is staged ONCE in shared memory (hi / lo), no second (MN-major) copy and no legacy mma.sync.
+// TMEM columns: D1 [0,64) (accumulates over the run), D2 [64,128), T^T hi [128,256), T^T lo [256,384).
+// Warps 0-7: staging; warps 0-3 then transpose into TMEM, warps 4-7 drain D2 and flush it; warp 8 issues all MMAs.
+// Validated layouts / instruction forms: tools/umma_test.cu (modes 0 and 3).
+// ---------------------------------------------------------------------------------------------------------
+template <int KC>
+struct PropTc2Smem {
+  unsigned char thi[32 * TC_SJ];
+  unsigned char tlo[32 * TC_SJ];
+  unsigned char bkJ[32 * ((2 * KC) * 16 + 16)];    // B[J rows] block, K-major B operand, N = 2*KC ([hi | lo])
+  unsigned char bkI[32 * ((2 * KC) * 16 + 16)];    // B[I rows] block (mirrored product), same format
+  uint64_t bar_d, bar_m;
+  uint32_t tmem_base;
+};
+
+template <int KC>
+__device__ __forceinline__ void tc2_flush(float* __restrict__ Y, int64_t n, int64_t row, uint32_t taddr) {
+  float hi[KC], lo[KC];
+  if (KC == 32) { tc::tmem_ld32(taddr, hi); tc::tmem_ld32(taddr + 32, lo); }
+  else { tc::tmem_ld16(taddr, hi); tc::tmem_ld16(taddr + 16, lo); }
+  if (row < n) {
+    float4* dst = reinterpret_cast<float4*>(Y + row * KC);
+#pragma unroll
+    for (int c4 = 0; c4 < KC / 4; ++c4)
+      atomicAdd(dst + c4, make_float4(hi[c4 * 4] + lo[c4 * 4], hi[c4 * 4 + 1] + lo[c4 * 4 + 1],
+                                      hi[c4 * 4 + 2] + lo[c4 * 4 + 2], hi[c4 * 4 + 3] + lo[c4 * 4 + 3]));
+  }
+}
+
+// Per tile k: warps 0-7 stage tile k (hi/lo) into smem; (B1); warp 8 issues the direct MMAs; warps 0-3 transpose the
+// staged tile into tensor memory (no live prefetch registers in that loop) and then prefetch their share of tile k+1;
+// (B2: warps 0-3 + warp 8) warp 8 issues the mirrored MMAs; warps 4-7 prefetch tile k+1, then drain and flush D2(k).
+template <int KC>
+__global__ void __launch_bounds__(288, 1)
+k_propagate_tc2(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
+                const unsigned char* __restrict__ Bk, float* __restrict__ Y) {
+  const int I = tr0 + (int)blockIdx.y;
+  const int Jbeg = (int)blockIdx.x * TC_RUN;
+  if (Jbeg > I) return;
+  const int Jend = min(I + 1, Jbeg + TC_RUN);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  PropTc2Smem<KC>& sm = *reinterpret_cast<PropTc2Smem<KC>*>(smem_raw);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)I * TILE;
+  constexpr uint32_t LBO_BK = (2 * KC) * 16 + 16;
+  constexpr uint32_t COL_D1 = 0, COL_D2 = 64, COL_AH = 128, COL_AL = 256;
+  const bool tcwarp = warp == 8;
+
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
+  if (tid == 0) { tc::mbar_init(&sm.bar_d, 1); tc::mbar_init(&sm.bar_m, 1); }
+  if (tcwarp) {
+    const float4* bI = reinterpret_cast<const float4*>(Bk + (int64_t)I * (32 * LBO_BK));
+    const float4* bJ = reinterpret_cast<const float4*>(Bk + (int64_t)Jbeg * (32 * LBO_BK));
+    for (int e = lane; e < (int)(32 * LBO_BK / 16); e += 32) {
+      tc::cp_async16(reinterpret_cast<float4*>(sm.bkI) + e, bI + e);
+      tc::cp_async16(reinterpret_cast<float4*>(sm.bkJ) + e, bJ + e);
+    }
+    tc::cp_async_wait_all();
+  }
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tm = sm.tmem_base;
+  const int q = warp & 3;
+  const uint32_t tlane = tm + ((uint32_t)(q * 32) << 16);
+
+  float4 pre[16];
+  if (!tcwarp) {
+    const int64_t tix = tri((int64_t)I) + Jbeg - tri((int64_t)tr0);
+    const float4* src = reinterpret_cast<const float4*>(tiles + tix * TILE_ELEMS);
+#pragma unroll
+    for (int it = 0; it < 16; ++it) pre[it] = src[(it * 8 + warp) * 32 + lane];
+  }
+  uint32_t phase = 0;
+  for (int J = Jbeg; J < Jend; ++J) {
+    const int64_t j0 = (int64_t)J * TILE;
+    const int64_t tix = tri((int64_t)I) + J - tri((int64_t)tr0);
+    if (!tcwarp) {
+      if (J > Jbeg) {                          // direct MMAs of the previous tile are done reading thi / tlo
+        tc::mbar_wait(&sm.bar_d, phase ^ 1);
+        tc::fence_after();
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // warps 0-3 finished their column reads of the previous tile
+      const bool interior = (J < I) && (i0 + TILE <= n);
+      if (interior && pv.raw == 2) {
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int row = it * 8 + warp;
+          const float4 v = pre[it];
+          float4 h, l;
+          h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
+          h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
+          h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
+          h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
+          const uint32_t off = (uint32_t)lane * TC_SJ + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+          *reinterpret_cast<float4*>(sm.thi + off) = h;
+          *reinterpret_cast<float4*>(sm.tlo + off) = l;
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int row = it * 8 + warp;
+          const float4 raw4 = pre[it];
+          const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
+          const float xr[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+          float xh[4], xl[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool ok = interior || ((gj + k < gi) && (gi < n));
+            const float xv = ok ? pv.adj(xr[k]) : 0.f;
+            xh[k] = __uint_as_float((__float_as_uint(xv) + 0x1000u) & 0xffffe000u);
+            xl[k] = xv - xh[k];
+          }
+          const uint32_t off = (uint32_t)lane * TC_SJ + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+          *reinterpret_cast<float4*>(sm.thi + off) = make_float4(xh[0], xh[1], xh[2], xh[3]);
+          *reinterpret_cast<float4*>(sm.tlo + off) = make_float4(xl[0], xl[1], xl[2], xl[3]);
+        }
+      }
+      tc::fence_async_smem();
+    } else {
+      tc::fence_async_smem();                  // the bkJ block this warp copied
+    }
+    __syncthreads();                           // (B1) tile + B[J] staged; previous D2 drained
+
+    if (tcwarp) {
+      if (lane == 0) {                         // ---- direct product ----
+        tc::fence_after();
+        const uint64_t a_hi0 = tc::make_desc(tc::smem_u32(sm.thi), TC_SJ, 128u);
+        const uint64_t a_lo0 = tc::make_desc(tc::smem_u32(sm.tlo), TC_SJ, 128u);
+        const uint64_t b0 = tc::make_desc(tc::smem_u32(sm.bkJ), LBO_BK, 128u);
+        const uint32_t idesc_cat = tc::make_idesc_tf32(128, 2 * KC, 0, 0);
+        const uint32_t idesc_lo = tc::make_idesc_tf32(128, KC, 0, 0);
+#pragma unroll 4
+        for (int ks = 0; ks < TILE / 8; ++ks) {
+          const uint64_t da = (uint64_t)((uint32_t)ks * ((2u * TC_SJ) >> 4));
+          const uint64_t db = (uint64_t)((uint32_t)ks * ((2u * LBO_BK) >> 4));
+          tc::mma_tf32(tm + COL_D1, a_hi0 + da, b0 + db, idesc_cat, (J > Jbeg || ks > 0) ? 1u : 0u);
+          tc::mma_tf32(tm + COL_D1, a_lo0 + da, b0 + db, idesc_lo, 1u);
+        }
+        tc::mma_commit(&sm.bar_d);
+      }
+      __syncwarp();
+      asm volatile("bar.sync 2, 160;" ::: "memory");   // (B2) with warps 0-3: T^T is in tensor memory
+      if (lane == 0) {                         // ---- mirrored product: A from TMEM ----
+        tc::fence_after();
+        const uint64_t b0 = tc::make_desc(tc::smem_u32(sm.bkI), LBO_BK, 128u);
+        const uint32_t idesc_cat = tc::make_idesc_tf32(128, 2 * KC, 0, 0);
+        const uint32_t idesc_lo = tc::make_idesc_tf32(128, KC, 0, 0);
+#pragma unroll 4
+        for (int ks = 0; ks < TILE / 8; ++ks) {
+          const uint64_t db = (uint64_t)((uint32_t)ks * ((2u * LBO_BK) >> 4));
+          tc::mma_tf32_ts(tm + COL_D2, tm + COL_AH + ks * 8, b0 + db, idesc_cat, ks > 0 ? 1u : 0u);
+          tc::mma_tf32_ts(tm + COL_D2, tm + COL_AL + ks * 8, b0 + db, idesc_lo, 1u);
+        }
+        tc::mma_commit(&sm.bar_m);
+      }
+      __syncwarp();
+      if (J + 1 < Jend) {                      // refill B[J] for the next tile once the direct MMAs are done with it
+        tc::mbar_wait(&sm.bar_d, phase);
+        const float4* bJ = reinterpret_cast<const float4*>(Bk + (int64_t)(J + 1) * (32 * LBO_BK));
+        for (int e = lane; e < (int)(32 * LBO_BK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(sm.bkJ) + e, bJ + e);
+        tc::cp_async_wait_all();
+      }
+    } else if (warp < 4) {
+      // ---- T^T -> tensor memory: thread = column j of the tile, 16 rows per tcgen05.st ----
+      if (J > Jbeg) {                          // mirrored MMAs of the previous tile are done reading the TMEM operand
+        tc::mbar_wait(&sm.bar_m, phase ^ 1);
+        tc::fence_after();
+      }
+      const uint32_t cbase = (uint32_t)(tid >> 2) * TC_SJ + (uint32_t)(tid & 3) * 4u;
+#pragma unroll 2
+      for (int r0 = 0; r0 < TILE; r0 += 16) {
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const uint32_t off = cbase + (uint32_t)((r0 + u) >> 3) * 128u + (uint32_t)((r0 + u) & 7) * 16u;
+          h[u] = *reinterpret_cast<const uint32_t*>(sm.thi + off);
+          l[u] = *reinterpret_cast<const uint32_t*>(sm.tlo + off);
+        }
+        tc::tmem_st16(tlane + COL_AH + r0, h);
+        tc::tmem_st16(tlane + COL_AL + r0, l);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before();
+      asm volatile("bar.sync 2, 160;" ::: "memory");   // (B2) hand T^T to the tensor-core warp
+      if (J + 1 < Jend) {                      // prefetch this warp's share of the next tile
+        const float4* nsrc = reinterpret_cast<const float4*>(tiles + (tix + 1) * TILE_ELEMS);
+#pragma unroll
+        for (int it = 0; it < 16; ++it) pre[it] = nsrc[(it * 8 + warp) * 32 + lane];
+      }
+    } else {
+      // ---- warps 4-7: prefetch, then drain D2 (mirrored result of THIS tile) and flush it ----
+      if (J + 1 < Jend) {
+        const float4* nsrc = reinterpret_cast<const float4*>(tiles + (tix + 1) * TILE_ELEMS);
+#pragma unroll
+        for (int it = 0; it < 16; ++it) pre[it] = nsrc[(it * 8 + warp) * 32 + lane];
+      }
+      tc::mbar_wait(&sm.bar_m, phase);
+      tc::fence_after();
+      tc2_flush<KC>(Y, n, j0 + q * 32 + lane, tlane + COL_D2);
+      tc::fence_before();
+    }
+    phase ^= 1;
+  }
+  // ---- epilogue: D1 (direct product of the whole run) -> Y[I rows] ----
+  if (!tcwarp) {
+    tc::mbar_wait(&sm.bar_d, phase ^ 1);
+    tc::fence_after();
+    if (warp < 4) tc2_flush<KC>(Y, n, i0 + q * 32 + lane, tlane + COL_D1);
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, 512);
+}
+
 inline int64_t prop_ws_bk_bytes(int64_t n, int K) {
   const int64_t T = (n + TILE - 1) / TILE;
   return (T * 32 * ((2 * K) * 16 + 16) + 255) / 256 * 256;
 }
+
+template <int KC>
+int launch_prop_tc2(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
+                    void* ws, cudaStream_t st) {
+  const int64_t npad = (n + TILE - 1) / TILE * TILE;
+  unsigned char* Bk = reinterpret_cast<unsigned char*>(ws);
+  float* Bhl = reinterpret_cast<float*>(Bk + prop_ws_bk_bytes(n, KC));
+  k_prep_b<KC><<<(unsigned)((npad * KC + 255) / 256), 256, 0, st>>>(B, n, npad, Bk, Bhl);
+  const size_t smem = sizeof(PropTc2Smem<KC>) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_propagate_tc2<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  if (tr1 - tr0 > 65535) return -3;
+  dim3 grid((unsigned)((tr1 + TC_RUN - 1) / TC_RUN), (unsigned)(tr1 - tr0));
+  k_propagate_tc2<KC><<<grid, 288, smem, st>>>(tiles, n, tr0, mu, raw, Bk, Y);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
 
 template <int KC, bool ELEM>
 int launch_prop_tc(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
@@ -961,9 +1202,10 @@ int launch_prop_tc(const float* tiles, int64_t n, int tr0, int tr1, const float*
 }
 
 // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2), 2 = tcgen05 + mma.sync hybrid (v3) everywhere,
-// 3 = v3 for the plain 32-wide passes only.  Default 2: same-process A/B on B200 at n = 65536 (tools/engine_ab.py,
-// steady clocks): K = 32: v3 5.32 ms vs v2 7.04 ms; K = 16: 3.81 vs 5.41 ms
-int g_prop_engine = 2;
+// 3 = v3 for the plain 32-wide passes only, 4 = both products on tcgen05 with T^T in tensor memory (v4, default).
+// Same-process A/B on B200 at n = 65536 (tools/engine_ab.py): K = 32: v4 4.26 ms, v3 5.32 ms, v2 7.04 ms;
+// K = 16: 3.72 / 3.80 / 5.41 ms
+int g_prop_engine = 4;
 
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1118,7 +1360,12 @@ int mcgra_propagate(const float* tiles, int64_t n, int tr0, int tr1, const float
   if (nt <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t t0 = tri(tr0);
-  const bool use_tc = ws != nullptr && (g_prop_engine == 2 || (g_prop_engine == 3 && K == 32 && elem == nullptr));
+  if (ws != nullptr && g_prop_engine == 4 && elem == nullptr) {
+    if (K == 32) return launch_prop_tc2<32>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
+    if (K == 16) return launch_prop_tc2<16>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
+    return -1;
+  }
+  const bool use_tc = ws != nullptr && (g_prop_engine == 2 || g_prop_engine == 4 || (g_prop_engine == 3 && K == 32 && elem == nullptr));
   if (use_tc) {
     if (K == 32)
       return elem ? launch_prop_tc<32, true>(tiles, n, tr0, tr1, mu, raw, B, Y, elem, ws, st)

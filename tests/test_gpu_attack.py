@@ -82,7 +82,7 @@ def test_engines_agree(which):
         N.lib().mcgra_set_engine(which, 1)
         b = run_native_case(d)
     finally:
-        N.lib().mcgra_set_engine(which, 2 if which == 0 else 1)
+        N.lib().mcgra_set_engine(which, 4 if which == 0 else 1)
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-6)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
 
@@ -100,32 +100,35 @@ def test_two_gpu_sharded_attack_matches_golden():
     assert "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("eng", [2, 4])
 @pytest.mark.parametrize("case", ["mse_all_n150", "kl_C_n150"])
-def test_tcgen05_propagate_engine_agrees(case):
-    """v3 propagate engine (direct product on tcgen05/TMEM, mirrored on mma.sync) vs the exact-fp32 FFMA engine."""
+def test_tcgen05_propagate_engine_agrees(case, eng):
+    """tcgen05 propagate engines (2: direct product on tcgen05/TMEM + mirrored on mma.sync; 4: both on tcgen05 with the
+    transposed operand in tensor memory) vs the exact-fp32 FFMA engine."""
     from mcgra_b200 import _native as N
     d = np.load(os.path.join(GOLDEN, f"attack_{case}.npz"))
     try:
         N.lib().mcgra_set_engine(0, 0)
         a = run_native_case(d)
-        N.lib().mcgra_set_engine(0, 2)
+        N.lib().mcgra_set_engine(0, eng)
         b = run_native_case(d)
     finally:
-        N.lib().mcgra_set_engine(0, 2)
+        N.lib().mcgra_set_engine(0, 4)
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-5)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5
 
 
-def test_tcgen05_propagate_multi_tile():
+@pytest.mark.parametrize("eng", [2, 4])
+def test_tcgen05_propagate_multi_tile(eng):
     from helpers import synthetic_case
     from mcgra_b200 import _native as N
     d = synthetic_case(1300, 40, 5, weights={1: 0.5, 2: 0.3, 6: 2.0, 7: 3.0, 9: 1.5, 10: 50.0}, epochs=2, mean_deg=8.0)
     try:
         N.lib().mcgra_set_engine(0, 0)
         a = run_native_case(d)
-        N.lib().mcgra_set_engine(0, 2)
+        N.lib().mcgra_set_engine(0, eng)
         b = run_native_case(d)
     finally:
-        N.lib().mcgra_set_engine(0, 2)
+        N.lib().mcgra_set_engine(0, 4)
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-5)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5

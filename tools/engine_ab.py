@@ -28,8 +28,8 @@ def main():
         eng.iterate()
     out = {}
     for rounds in range(2):
-        for name, sel, split in (("v2 mma.sync fused-elem", 1, False), ("v2 mma.sync split-elem", 1, True),
-                                 ("v3 tcgen05 hybrid all", 2, True), ("auto", 3, True)):
+        for name, sel, split in (("v2 mma.sync", 1, True), ("v3 tcgen05+mma.sync hybrid", 2, True),
+                                 ("v4 tcgen05 both (T^T in TMEM)", 4, True)):
             N.lib().mcgra_set_engine(0, sel)
             eng.split_elem = split
             eng.iterate()
@@ -45,7 +45,7 @@ def main():
             N.TIMERS["on"] = None
             out[name] = {"ms_per_iter": round(e0.elapsed_time(e1) / steps, 3), **{k: v for k, v in kt.items() if v > 0.05}}
             print(name, json.dumps(out[name]), flush=True)
-    N.lib().mcgra_set_engine(0, 2)
+    N.lib().mcgra_set_engine(0, 4)
 
 
 if __name__ == "__main__":
