@@ -266,6 +266,9 @@ def run_native(a):
                            + ") + final ensemble + GPU AUC/AP, amortised over K",
                "auc": auc, "ap": ap}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = {}
@@ -278,7 +281,8 @@ def run_native(a):
     roof = None
     if prop_ms:
         ach = prop_bytes / (prop_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_propagate<32> (Y += M*B over the tiled triangle)", "achieved": ach,
+        roof = {"bound": "hbm", "kernel": "k_propagate_tc2<32> (Y += M*B over the tiled triangle; both products on "
+                                          "tcgen05, 3xTF32, accumulators + transposed operand in TMEM)", "achieved": ach,
                 "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "launch_ms": prop_ms, "algorithmic_bytes_per_launch": prop_bytes,

@@ -63,8 +63,8 @@ enum {
 int mcgra_version(void);
 /* engine selection for A/B validation: which 0 = propagate (0 fp32 FFMA, 1 mma.sync 3xTF32, 2 tcgen05+mma.sync
  * hybrid, 3: hybrid for the plain 32-wide passes only, 4: both products on tcgen05 with the transposed operand in
- * tensor memory [default]), other selectors: 0 FFMA / 1 mma.sync [default];
- * which 1 = fold, which 2 = pairs (same values).  Returns 0, or -1 for an unknown selector.           */
+ * tensor memory [default]); which 1 = fold (0 FFMA, 1 mma.sync, 2 tcgen05 [default]);
+ * which 2 = pairs (0 FFMA, 1 mma.sync [default]).  Returns 0, or -1 for an unknown selector.          */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */
 
@@ -192,7 +192,9 @@ typedef struct {
   double* acc_next;       /* receives SUMCLAMP, SUMSQ, XMIN, XMAX of the new x'                       */
   float* d_next;          /* [n] += row/col sums of clamp(x',0,1) (caller pre-fills with 1)           */
   int store_clamped;      /* != 0: the budget cannot bind -> store clamp(x',0,1) (readers then use raw = 2)   */
+  void* Wk;               /* scratch of mcgra_fold_ws_bytes(n) bytes for the tcgen05 engine (NULL: mma.sync)   */
 } mcgra_fold_args;
+int64_t mcgra_fold_ws_bytes(int64_t n);
 /* minmax: device float[2] = {min x', max x'} (bisection bracket, :340-341); reset by mcgra_node_rho          */
 int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const float* mu, int raw,
                     const mcgra_fold_args* a, float* minmax, void* stream);

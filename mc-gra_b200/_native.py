@@ -49,7 +49,7 @@ class FoldArgs(C.Structure):
                 ("lseA", c_fp), ("lseF", c_fp), ("zhat", c_fp), ("measure", C.c_int),
                 ("k1", C.c_float), ("k6", C.c_float), ("k2", C.c_float), ("norm_coef", C.c_float),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
-                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int)]
+                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int), ("Wk", c_fp)]
 
 
 _SIGS = {
@@ -74,6 +74,7 @@ _SIGS = {
     "mcgra_node_rho": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
     "mcgra_pairs": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp, C.c_float, C.c_float,
                               c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "mcgra_fold_ws_bytes": (i64, [i64]),
     "mcgra_fold_adam": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp, C.c_int, C.POINTER(FoldArgs), c_fp,
                                   c_fp]),
     "mcgra_bisect_init": (C.c_int, [c_fp, c_fp, C.c_double, c_fp, c_fp, c_fp]),

@@ -12,6 +12,7 @@
 // One CTA per 128x128 tile: rank product as an fp32 register-tiled GEMM (K = 128), then a streaming epilogue
 // that reads x', m, v (and feature_adj) once and writes x', m, v once:  24 (+4) bytes per entry.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -252,8 +253,8 @@ struct EpiConst {
 // Streaming epilogue of the fold: one warp = one 512 B tile row per step, UNR rows in flight.
 // FAST: the tile is interior (every entry valid) and the buffer already holds the parameter in [0,1]
 // (raw == 2), no c2 term, MEAS is the compile-time c1 measure.  The generic instantiation handles everything else.
-template <bool FAST, int MEAS, bool ENT>
-__device__ __forceinline__ void fold_stream(FoldMmaSmem& sm, const mcgra_fold_args& fa, const ParamView& pv,
+template <bool FAST, int MEAS, bool ENT, typename SM>
+__device__ __forceinline__ void fold_stream(SM& sm, const mcgra_fold_args& fa, const ParamView& pv,
                                             const EpiConst& ec, int64_t tix, float* __restrict__ tiles,
                                             float* __restrict__ mbuf, float* __restrict__ vbuf, int I, int J,
                                             float& s_clamp, float& s_sq, float& xmin, float& xmax, float* colp) {
@@ -506,7 +507,195 @@ k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restric
   }
 }
 
-int g_fold_engine = 1;     // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2)
+
+// ---------------------------------------------------------------------------------------------------------
+// v3 engine: the rank-128 factor product on tcgen05 (kind::tf32, 3xTF32, accumulator in TMEM).
+// Operands come pre-formatted (k_prep_w): per 128-node block, 32 K-slabs of 4 factors, each slab =
+// [hi: 16 row-groups x 128 B | lo: 16 row-groups x 128 B | 16 B pad] in the SWIZZLE_NONE K-major core layout, so the
+// same block is the A operand (U|V order) and, read 16 slabs further, the B operand (V|U order); [hi|lo] adjacent
+// gives the N = 256 concatenated B.   D[:, :128] = A_hi B_hi + A_lo B_hi,  D[:, 128:] = A_hi B_lo.
+// One CTA per tile, 2 CTAs / SM (256 TMEM columns each), K processed in 4 quarters staged with cp.async; the product
+// tile is then parked in shared memory (over the operand buffers) for the coalesced streaming epilogue.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t WSLAB = 2 * 16 * 128 + 16;         // 4112 B per K-slab (hi | lo | pad)
+constexpr uint32_t WBLOCK = 32 * WSLAB;               // per 128-node block
+
+struct FoldTcSmem {
+  union {
+    struct { unsigned char a[8 * WSLAB]; unsigned char b[8 * WSLAB]; } op;
+    float gt[TILE][G_LD];
+  } u;
+  float zI[TILE][HID + 1];
+  float zJt[HID][TILE + 4];
+  float rI[TILE], rJ[TILE], rhoI[TILE], rhoJ[TILE];
+  float lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE];
+  float colacc[TILE];
+  double red[32];
+  uint64_t bar;
+  uint32_t tmem_base;
+};
+
+__global__ void k_prep_w(const float* __restrict__ Wt, int64_t npad, unsigned char* __restrict__ Wk) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // e = k * npad + node (coalesced reads)
+  if (e >= npad * 128) return;
+  const int k = (int)(e / npad);
+  const int64_t node = e % npad;
+  const float v = Wt[e];
+  const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  const int i = (int)(node & 127);
+  unsigned char* p = Wk + (node >> 7) * (int64_t)WBLOCK + (uint32_t)(k >> 2) * WSLAB + (uint32_t)(i >> 3) * 128u +
+                     (uint32_t)(i & 7) * 16u + (uint32_t)(k & 3) * 4u;
+  *reinterpret_cast<float*>(p) = hi;
+  *reinterpret_cast<float*>(p + 2048) = v - hi;
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_fold_tc(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int64_t t0, const float* mu,
+          int raw, mcgra_fold_args fa, float* __restrict__ minmax, const unsigned char* __restrict__ Wk) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  FoldTcSmem& sm = *reinterpret_cast<FoldTcSmem*>(smem_raw);
+  int I, J;
+  tile_coords(t0 + blockIdx.x, I, J);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+  const int64_t n = fa.n;
+
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 256);
+  if (tid == 0) tc::mbar_init(&sm.bar, 1);
+  if (tid < TILE) {
+    const int64_t gi = i0 + tid, gj = j0 + tid;
+    sm.rI[tid] = gi < n ? fa.r[gi] : 0.f;
+    sm.rJ[tid] = gj < n ? fa.r[gj] : 0.f;
+    sm.rhoI[tid] = gi < n ? fa.rho[gi] : 0.f;
+    sm.rhoJ[tid] = gj < n ? fa.rho[gj] : 0.f;
+    if (fa.measure == MCGRA_M_KL) {
+      sm.lseAI[tid] = gi < n ? fa.lseA[gi] : 0.f;
+      sm.lseAJ[tid] = gj < n ? fa.lseA[gj] : 0.f;
+      sm.lseFI[tid] = gi < n ? fa.lseF[gi] : 0.f;
+      sm.lseFJ[tid] = gj < n ? fa.lseF[gj] : 0.f;
+    }
+    sm.colacc[tid] = 0.f;
+  }
+  if (fa.k2 != 0.f) {
+    for (int e = tid; e < TILE * HID; e += 256) {
+      const int a = e >> 4, k = e & 15;
+      sm.zI[a][k] = (i0 + a < n) ? fa.zhat[(i0 + a) * HID + k] : 0.f;
+      sm.zJt[k][a] = (j0 + a < n) ? fa.zhat[(j0 + a) * HID + k] : 0.f;
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tm = sm.tmem_base;
+
+  // ---- rank-128 product: 4 K-quarters of 8 slabs (32 factors), 4 K-steps of 8 each ----
+  const unsigned char* blkA = Wk + (int64_t)I * WBLOCK;
+  const unsigned char* blkB = Wk + (int64_t)J * WBLOCK;
+  uint32_t phase = 0;
+#pragma unroll 1
+  for (int qd = 0; qd < 4; ++qd) {
+    if (qd > 0) {                              // tensor cores finished reading the previous quarter
+      tc::mbar_wait(&sm.bar, phase);
+      phase ^= 1;
+      tc::fence_after();
+    }
+    const float4* sa = reinterpret_cast<const float4*>(blkA + (uint32_t)(8 * qd) * WSLAB);
+    const float4* sb = reinterpret_cast<const float4*>(blkB + (uint32_t)((8 * qd + 16) & 31) * WSLAB);
+    for (int e = tid; e < (int)(8 * WSLAB / 16); e += 256) {
+      tc::cp_async16(reinterpret_cast<float4*>(sm.u.op.a) + e, sa + e);
+      tc::cp_async16(reinterpret_cast<float4*>(sm.u.op.b) + e, sb + e);
+    }
+    tc::cp_async_wait_all();
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after();
+      const uint32_t as = tc::smem_u32(sm.u.op.a), bs = tc::smem_u32(sm.u.op.b);
+      const uint32_t id_cat = tc::make_idesc_tf32(128, 256, 0, 0);
+      const uint32_t id_lo = tc::make_idesc_tf32(128, 128, 0, 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t a_hi = tc::make_desc(as + (uint32_t)ks * 2u * WSLAB, WSLAB, 128u);
+        const uint64_t a_lo = tc::make_desc(as + (uint32_t)ks * 2u * WSLAB + 2048u, WSLAB, 128u);
+        const uint64_t bd = tc::make_desc(bs + (uint32_t)ks * 2u * WSLAB, WSLAB, 128u);
+        tc::mma_tf32(tm, a_hi, bd, id_cat, (qd > 0 || ks > 0) ? 1u : 0u);
+        tc::mma_tf32(tm, a_lo, bd, id_lo, 1u);
+      }
+      tc::mma_commit(&sm.bar);
+    }
+  }
+  tc::mbar_wait(&sm.bar, phase);
+  tc::fence_after();
+  __syncthreads();                             // operand buffers are dead (all threads observed the last commit)
+  // ---- drain: D (TMEM) -> product tile in smem; warp w: lane quarter w % 4, column half w / 4 ----
+  {
+    const int qq = warp & 3, ch = warp >> 2;
+    const int row = qq * 32 + lane;
+    const uint32_t taddr = tm + ((uint32_t)(qq * 32) << 16) + (uint32_t)(ch * 64);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float hi[32], lo[32];
+      tc::tmem_ld32(taddr + c * 32, hi);
+      tc::tmem_ld32(taddr + 128 + c * 32, lo);
+#pragma unroll
+      for (int u4 = 0; u4 < 8; ++u4)
+        *reinterpret_cast<float4*>(&sm.u.gt[row][ch * 64 + c * 32 + u4 * 4]) =
+            make_float4(hi[u4 * 4] + lo[u4 * 4], hi[u4 * 4 + 1] + lo[u4 * 4 + 1], hi[u4 * 4 + 2] + lo[u4 * 4 + 2],
+                        hi[u4 * 4 + 3] + lo[u4 * 4 + 3]);
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, 256);
+
+  // ---- streaming epilogue (shared with the mma.sync engine) ----
+  const double sumsq_prev = fa.acc_prev[MCGRA_ACC_SUMSQ];
+  const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
+  const double bc1 = 1.0 - pow((double)fa.beta1, (double)fa.step);
+  const double bc2 = 1.0 - pow((double)fa.beta2, (double)fa.step);
+  EpiConst ec;
+  ec.step_size = (float)((double)fa.lr / bc1);
+  ec.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  ec.omb1 = 1.f - fa.beta1;
+  ec.omb2 = 1.f - fa.beta2;
+  ec.norm_scale = fa.norm_coef * inv_norm;
+  const bool interior = (J < I) && (i0 + TILE <= n);
+  float s_clamp = 0.f, s_sq = 0.f, xmin = INFINITY, xmax = -INFINITY;
+  float colp[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool fastview = (pv.raw == 2) && interior && fa.k2 == 0.f && fa.measure != MCGRA_M_KL;
+  if (fastview) {
+    if (fa.measure == MCGRA_M_MSE) {
+      if (fa.k6 != 0.f) fold_stream<true, MCGRA_M_MSE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+      else fold_stream<true, MCGRA_M_MSE, false>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+    } else if (fa.measure == MCGRA_M_PRE) {
+      fold_stream<true, MCGRA_M_PRE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+    } else {
+      fold_stream<true, MCGRA_M_NONE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+    }
+  } else {
+    fold_stream<false, -1, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+  }
+  const int b0 = lane * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (colp[k] != 0.f) atomicAdd(&sm.colacc[b0 + k], colp[k]);
+  __syncthreads();
+  if (tid < TILE) {
+    const int64_t gj = j0 + tid;
+    if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(fa.d_next + gj, sm.colacc[tid]);
+  }
+  block_atomic_add_d((double)s_clamp, fa.acc_next + MCGRA_ACC_SUMCLAMP, sm.red);
+  block_atomic_add_d((double)s_sq, fa.acc_next + MCGRA_ACC_SUMSQ, sm.red);
+  xmin = warp_min(xmin);
+  xmax = warp_max(xmax);
+  if (lane == 0) {
+    if (xmin != INFINITY) atomic_min_f(minmax, xmin);
+    if (xmax != -INFINITY) atomic_max_f(minmax + 1, xmax);
+  }
+}
+
+int g_fold_engine = 2;     // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2), 2 = tcgen05 3xTF32 (v3, needs fa.Wk)
 
 // ---------------------------------------------------------------------------------------------------------
 // Bisection on device.  state: [0]=a [1]=b [2]=mu(last midpoint) [3]=done [4]=active
@@ -645,11 +834,24 @@ extern "C" {
 
 int mcgra_set_fold_engine_(int value) { g_fold_engine = value; return 0; }
 
+int64_t mcgra_fold_ws_bytes(int64_t n) { return ((n + TILE - 1) / TILE) * (int64_t)WBLOCK + 256; }
+
 int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const float* mu, int raw,
                     const mcgra_fold_args* a, float* minmax, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
-  if (g_fold_engine == 1) {
+  if (g_fold_engine == 2 && a->Wk != nullptr) {
+    const int64_t np = a->npad;
+    k_prep_w<<<(unsigned)((np * 128 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->Wt, np, (unsigned char*)a->Wk);
+    const size_t smem3 = sizeof(FoldTcSmem) + 1024;
+    cudaError_t e3 = cudaFuncSetAttribute(k_fold_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e3 != cudaSuccess) return (int)e3;
+    k_fold_tc<<<(unsigned)nt, 256, smem3, (cudaStream_t)stream>>>(tiles, m, v, tri(tr0), mu, raw, *a, minmax,
+                                                                  (const unsigned char*)a->Wk);
+    MCGRA_LAUNCH_CHECK();
+    return 0;
+  }
+  if (g_fold_engine >= 1) {
     const size_t smem2 = sizeof(FoldMmaSmem);
     cudaError_t e2 = cudaFuncSetAttribute(k_fold_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e2 != cudaSuccess) return (int)e2;

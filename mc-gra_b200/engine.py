@@ -169,6 +169,7 @@ class PGDEngine:
         self.masks = torch.zeros(n, dtype=torch.int32, device=dev)
         self.masks2 = torch.zeros(n, dtype=torch.int32, device=dev)
         self.Wt = z(128, self.npad)
+        self.fold_ws = torch.empty(int(N.lib().mcgra_fold_ws_bytes(n)), dtype=torch.uint8, device=dev)
         self.prop_ws = torch.empty(int(N.lib().mcgra_propagate_ws_bytes(n, 32)), dtype=torch.uint8, device=dev)
         kl_native = self.meas_nn == N.M_KL and self.nn_mode == "native"
         self.sumexp = z(n) if kl_native else None
@@ -317,6 +318,7 @@ class PGDEngine:
         f.acc_next = self.acc_hist[t + 1].data_ptr()
         f.d_next = ptr(self.d_next)
         f.store_clamped = 0 if self.proj_possible else 1
+        f.Wk = ptr(self.fold_ws)
         call("mcgra_fold_adam", ptr(self.xt), ptr(self.mt), ptr(self.vt), tr0, tr1, mu, raw, C.byref(f),
              ptr(self.minmax), st)
         # the buffer now holds the un-projected Adam output x' (mu = 0), or the clamped parameter itself
