@@ -116,6 +116,10 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = L
+        # developer override for same-box A/B runs and profiling: MCGRA_ENGINES="0:5,1:2" (stage:engine, see mcgra.h)
+        for item in filter(None, os.environ.get("MCGRA_ENGINES", "").split(",")):
+            which, value = item.split(":")
+            L.mcgra_set_engine(int(which), int(value))
     return _lib
 
 

@@ -12,6 +12,8 @@
 //
 // v1 engine: fp32 FFMA with a 2 x K register tile per thread (exact fp32 accumulate).  HBM traffic = one read of
 // the tile shard (4 bytes per stored entry) + O(n K).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -1159,6 +1161,278 @@ k_propagate_tc2(const float* __restrict__ tiles, int64_t n, int tr0, const float
   if (warp == 0) tc::tmem_dealloc(tm, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// v5 engine: both products on tcgen05 kind::f16 from ONE staged image per tile, no transposition pass.
+//
+// Measured on B200 (tools/umma_rate.cu): one tcgen05.mma costs a fixed ~110-140 clk for kind::tf32 (K = 8) and ~60 clk for
+// kind::f16 (K = 16) for every N <= 128, so the tf32 engines are bound by their 64 MMA instructions per tile
+// (~6-8k clk against an HBM floor of 2.8k clk per tile).  16-bit operands need a quarter of that, and -- unlike tf32 --
+// 16-bit operands may be MN-major without swizzle, so the SAME shared-memory image serves the direct product as a
+// K-major A operand (M = tile row, K = tile column) and the mirrored product as an MN-major A operand (M = tile
+// column, K = tile row) (tools/umma_test16.cu).
+//
+// Precision (fp16 x 2 on both sides, fp32 accumulation, ~2^-22 like 3xTF32):
+//   tile entry  x in [0, 1]:   h0 = fp16(x),  h1 = fp16((x - h0) * 2^11)
+//   feature     f (column c):  g = f * s_c (s_c = power of two with max_c |g| < 2^14),  g0 = fp16(g), g1 = fp16((g - g0) * 2^11)
+//   D[:, 0:2KC] += h0 * [g0 | g1]      D[:, 2KC:3KC] += h1 * g0       y_c = (d0 + (d1 + d2) * 2^-11) / s_c
+// (mixed f16 x bf16 operands are rejected by the hardware; bf16 x 3 would need 3 planes and 48 MMAs per tile).
+//
+// Plane image: element (i, j) at (j/8)*H_SJ + (i/8)*128 + (i%8)*16 + (j%8)*2, two planes per tile, two tile buffers.
+// Warps 0-7 convert their prefetched registers into the planes, arrive on ready[b], prefetch the tile after next and
+// flush the mirrored result of the previous tile; warp 8 streams the pre-formatted B[J] blocks and issues the 32 MMAs
+// of a tile.  TMEM columns: D1 [0, 3KC) | D2[0] [96, 96+3KC) | D2[1] [192, 192+3KC).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int H_RUN = 16;
+constexpr uint32_t H_SJ = 16 * 128 + 16;           // stride between 8-column groups of a plane (padded: conflict-free stores)
+constexpr uint32_t H_PLANE = 16 * H_SJ;
+
+template <int KC>
+struct PropHSmem {
+  unsigned char tile[2][2][H_PLANE];               // [buffer][plane h0 / h1]
+  unsigned char bkJ[2][16 * (2 * KC) * 16];        // 16 K-groups x (2KC rows [g0 | g1] x 16 B)
+  unsigned char bkI[16 * (2 * KC) * 16];
+  uint64_t ready[2], tile_done[2];
+  float inv_s[32];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int a_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                          // D = F32; A = B = F16 (format 0)
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// column scales: maxbits[c] = bits of max_i |B[i][c]|
+template <int KC>
+__global__ void k_colmax(const float* __restrict__ B, int64_t n, unsigned int* __restrict__ maxbits) {
+  const int c = threadIdx.x % KC;
+  float m = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * KC; e += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(B[e]));
+  if (m > 0.f) atomicMax(maxbits + c, __float_as_uint(m));
+}
+__device__ __forceinline__ float h_col_scale(unsigned int maxbits) {     // power of two s with max * s < 2^14
+  if (maxbits == 0u) return 1.f;
+  int e = (int)((maxbits >> 23) & 0xffu) - 127;                          // max < 2^(e+1)
+  int se = 13 - e;
+  se = se > 126 ? 126 : (se < -126 ? -126 : se);
+  return __uint_as_float((uint32_t)(se + 127) << 23);
+}
+// B (n x KC fp32) -> per node tile a K-major [g0 | g1] fp16 block; scale[0:KC] = s_c, scale[KC:2KC] = 1 / s_c
+template <int KC>
+__global__ void k_prep_b16(const float* __restrict__ B, int64_t n, int64_t npad, const unsigned int* __restrict__ maxbits,
+                           unsigned char* __restrict__ Bk, float* __restrict__ scale) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= npad * KC) return;
+  const int64_t node = e / KC;
+  const int c = (int)(e % KC);
+  const float s = h_col_scale(maxbits[c]);
+  if (node == 0) { scale[c] = s; scale[KC + c] = 1.f / s; }
+  const float g = node < n ? B[e] * s : 0.f;
+  const __half g0 = __float2half_rn(g);
+  const __half g1 = __float2half_rn((g - __half2float(g0)) * 2048.f);
+  const int k = (int)(node & 127);
+  unsigned char* blk = Bk + (node >> 7) * (int64_t)(16 * (2 * KC) * 16) + (uint32_t)(k >> 3) * (uint32_t)((2 * KC) * 16) + (uint32_t)(k & 7) * 2u;
+  *reinterpret_cast<__half*>(blk + (uint32_t)(c >> 3) * 128u + (uint32_t)(c & 7) * 16u) = g0;
+  const int c2 = c + KC;
+  *reinterpret_cast<__half*>(blk + (uint32_t)(c2 >> 3) * 128u + (uint32_t)(c2 & 7) * 16u) = g1;
+}
+
+// y[row][c0 + 0..15] += (d0 + (d1 + d2) * 2^-11) * inv_s   for 16 feature columns of one accumulator
+template <int KC>
+__device__ __forceinline__ void h_flush(float* __restrict__ Y, int64_t n, int64_t row, uint32_t taddr, int c0, const float* inv_s) {
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float d0[8], d1[8], d2[8];
+    const int c = c0 + half * 8;
+    tc::tmem_ld8(taddr + c, d0);
+    tc::tmem_ld8(taddr + KC + c, d1);
+    tc::tmem_ld8(taddr + 2 * KC + c, d2);
+    if (row < n) {
+      float4* dst = reinterpret_cast<float4*>(Y + row * KC + c);
+      const float* is = inv_s + half * 8;
+#pragma unroll
+      for (int c4 = 0; c4 < 2; ++c4) {
+        float4 v;
+        v.x = (d0[c4 * 4 + 0] + (d1[c4 * 4 + 0] + d2[c4 * 4 + 0]) * (1.f / 2048.f)) * is[c4 * 4 + 0];
+        v.y = (d0[c4 * 4 + 1] + (d1[c4 * 4 + 1] + d2[c4 * 4 + 1]) * (1.f / 2048.f)) * is[c4 * 4 + 1];
+        v.z = (d0[c4 * 4 + 2] + (d1[c4 * 4 + 2] + d2[c4 * 4 + 2]) * (1.f / 2048.f)) * is[c4 * 4 + 2];
+        v.w = (d0[c4 * 4 + 3] + (d1[c4 * 4 + 3] + d2[c4 * 4 + 3]) * (1.f / 2048.f)) * is[c4 * 4 + 3];
+        atomicAdd(dst + c4, v);
+      }
+    }
+  }
+}
+
+template <int KC>
+__global__ void __launch_bounds__(288, 1)
+k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
+              const unsigned char* __restrict__ Bk, const float* __restrict__ scale, float* __restrict__ Y) {
+  const int I = tr0 + (int)blockIdx.y;
+  const int Jbeg = (int)blockIdx.x * H_RUN;
+  if (Jbeg > I) return;
+  const int Jend = min(I + 1, Jbeg + H_RUN);
+  const int nt = Jend - Jbeg;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PropHSmem<KC>& sm = *reinterpret_cast<PropHSmem<KC>*>(smem_raw);
+  const ParamView pv = load_view(mu, raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)I * TILE;
+  constexpr uint32_t LBO_B = (2 * KC) * 16;
+  constexpr uint32_t BLK = 16 * LBO_B;
+  constexpr uint32_t COL_D1 = 0, COL_D2 = 96;
+  const bool tcwarp = warp == 8;
+  const bool rows_ok = (i0 + TILE <= n) && (pv.raw == 2);
+  const int64_t tix0 = tri((int64_t)I) - tri((int64_t)tr0);
+
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
+  if (tid == 0) {
+    tc::mbar_init(&sm.ready[0], 256); tc::mbar_init(&sm.ready[1], 256);
+    tc::mbar_init(&sm.tile_done[0], 1); tc::mbar_init(&sm.tile_done[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid >= 32 && tid < 32 + KC) sm.inv_s[tid - 32] = scale[KC + tid - 32];
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tm = sm.tmem_base;
+
+  if (tcwarp) {
+    // =================================== B-block producer + MMA issuer ===================================
+    auto load_block = [&](int node_tile, unsigned char* dst) {
+      const float4* src = reinterpret_cast<const float4*>(Bk + (int64_t)node_tile * BLK);
+#pragma unroll 4
+      for (int e = lane; e < (int)(BLK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(dst) + e, src + e);
+    };
+    load_block(I, sm.bkI);
+    load_block(Jbeg, sm.bkJ[0]);
+    tc::cp_async_commit();
+    const uint32_t id_cat = make_idesc_f16(128, 2 * KC, 0), id_one = make_idesc_f16(128, KC, 0);
+    const uint32_t id_cat_t = make_idesc_f16(128, 2 * KC, 1), id_one_t = make_idesc_f16(128, KC, 1);
+    const uint64_t bI0 = tc::make_desc(tc::smem_u32(sm.bkI), LBO_B, 128u);
+    for (int k = 0; k < nt; ++k) {
+      const int b = k & 1;
+      if (k + 1 < nt) {                        // B[J+1] into the other buffer once tile k-1 is done with it
+        if (k >= 1) tc::mbar_wait(&sm.tile_done[b ^ 1], (uint32_t)(((k - 1) >> 1) & 1));
+        load_block(Jbeg + k + 1, sm.bkJ[b ^ 1]);
+        tc::cp_async_commit();
+        tc::cp_async_wait_group<1>();          // B[J] (committed one tile ago) has landed
+      } else {
+        tc::cp_async_wait_all();
+      }
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_wait(&sm.ready[b], (uint32_t)((k >> 1) & 1));
+        tc::fence_after();
+        const uint32_t p0 = tc::smem_u32(sm.tile[b][0]), p1 = tc::smem_u32(sm.tile[b][1]);
+        const uint64_t bJ0 = tc::make_desc(tc::smem_u32(sm.bkJ[b]), LBO_B, 128u);
+        const uint32_t d2 = tm + COL_D2 + (uint32_t)b * 96u;
+#pragma unroll 2
+        for (int ks = 0; ks < TILE / 16; ++ks) {
+          const uint64_t db = (uint64_t)((uint32_t)ks * ((2u * LBO_B) >> 4));
+          const uint32_t acc1 = (k > 0 || ks > 0) ? 1u : 0u, acc2 = ks > 0 ? 1u : 0u;
+          // direct: A K-major (M = row: SBO 128 between 8-row groups; K = column: LBO H_SJ between 8-column groups)
+          mma_f16(tm + COL_D1, tc::make_desc(p0 + (uint32_t)ks * 2u * H_SJ, H_SJ, 128u), bJ0 + db, id_cat, acc1);
+          mma_f16(tm + COL_D1 + 2 * KC, tc::make_desc(p1 + (uint32_t)ks * 2u * H_SJ, H_SJ, 128u), bJ0 + db, id_one, acc1);
+          // mirrored: the same image as an MN-major A operand (M = column: SBO H_SJ; K = row: LBO 128)
+          mma_f16(d2, tc::make_desc(p0 + (uint32_t)ks * 256u, 128u, H_SJ), bI0 + db, id_cat_t, acc2);
+          mma_f16(d2 + 2 * KC, tc::make_desc(p1 + (uint32_t)ks * 256u, 128u, H_SJ), bI0 + db, id_one_t, acc2);
+        }
+        tc::mma_commit(&sm.tile_done[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =================================== converter warps ===================================
+    const int q = warp & 3, cg = warp >> 2;           // TMEM lane quarter; 16-column group this warp flushes
+    const int ltid = q * 32 + lane;
+    const uint32_t tlane = tm + ((uint32_t)(q * 32) << 16);
+    const bool flusher = cg < KC / 16;
+    const float* inv_s = sm.inv_s + (flusher ? cg * 16 : 0);
+
+    auto fetch = [&](int J, float4 (&dst)[16]) {
+      const float4* src = reinterpret_cast<const float4*>(tiles + (tix0 + J) * TILE_ELEMS);
+#pragma unroll
+      for (int it = 0; it < 16; ++it) dst[it] = src[(it * 8 + warp) * 32 + lane];
+    };
+    auto step = [&](int k, float4 (&cur)[16], float4 (&nxt)[16]) {
+      const int J = Jbeg + k, b = k & 1;
+      const int64_t j0 = (int64_t)J * TILE;
+      if (k + 1 < nt) fetch(J + 1, nxt);       // a full tile ahead of its use
+      if (k >= 2) tc::mbar_wait(&sm.tile_done[b], (uint32_t)(((k - 2) >> 1) & 1));   // MMAs of tile k-2 released buffer b
+      const bool fast = rows_ok && (J < I);
+      const bool interior = (J < I) && (i0 + TILE <= n);
+      unsigned char* pl0 = sm.tile[b][0];
+      unsigned char* pl1 = sm.tile[b][1];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int row = it * 8 + warp;
+        float xv[4] = {cur[it].x, cur[it].y, cur[it].z, cur[it].w};
+        if (!fast) {
+          const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const bool ok = interior || ((gj + c < gi) && (gi < n));
+            xv[c] = ok ? pv.adj(xv[c]) : 0.f;
+          }
+        }
+        const __half2 a01 = __floats2half2_rn(xv[0], xv[1]), a23 = __floats2half2_rn(xv[2], xv[3]);
+        const float2 f01 = __half22float2(a01), f23 = __half22float2(a23);
+        const __half2 r01 = __floats2half2_rn((xv[0] - f01.x) * 2048.f, (xv[1] - f01.y) * 2048.f);
+        const __half2 r23 = __floats2half2_rn((xv[2] - f23.x) * 2048.f, (xv[3] - f23.y) * 2048.f);
+        const uint32_t off = (uint32_t)(lane >> 1) * H_SJ + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(lane & 1) * 8u;
+        *reinterpret_cast<uint2*>(pl0 + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23));
+        *reinterpret_cast<uint2*>(pl1 + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&r01), *reinterpret_cast<const uint32_t*>(&r23));
+      }
+      tc::fence_async_smem();
+      mbar_arrive(&sm.ready[b]);
+      if (k >= 1) {                            // flush the mirrored result of the previous tile
+        tc::mbar_wait(&sm.tile_done[b ^ 1], (uint32_t)(((k - 1) >> 1) & 1));
+        tc::fence_after();
+        if (flusher) h_flush<KC>(Y, n, (j0 - TILE) + ltid, tlane + COL_D2 + (uint32_t)(b ^ 1) * 96u, cg * 16, inv_s);
+        tc::fence_before();
+      }
+    };
+    float4 ra[16], rb[16];
+    fetch(Jbeg, ra);
+    for (int k = 0; k < nt; k += 2) {
+      step(k, ra, rb);
+      if (k + 1 < nt) step(k + 1, rb, ra);
+    }
+    // ---- epilogue: the last tile's D2 and the run's D1 ----
+    const int bl = (nt - 1) & 1;
+    tc::mbar_wait(&sm.tile_done[bl], (uint32_t)(((nt - 1) >> 1) & 1));
+    tc::fence_after();
+    if (flusher) {
+      h_flush<KC>(Y, n, (int64_t)(Jend - 1) * TILE + ltid, tlane + COL_D2 + (uint32_t)bl * 96u, cg * 16, inv_s);
+      h_flush<KC>(Y, n, i0 + ltid, tlane + COL_D1, cg * 16, inv_s);
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, 512);
+}
+
+template <int KC>
+int launch_prop_h(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
+                  void* ws, cudaStream_t st);
+
 inline int64_t prop_ws_bk_bytes(int64_t n, int K) {
   const int64_t T = (n + TILE - 1) / TILE;
   return (T * 32 * ((2 * K) * 16 + 16) + 255) / 256 * 256;
@@ -1181,6 +1455,27 @@ int launch_prop_tc2(const float* tiles, int64_t n, int tr0, int tr1, const float
   return 0;
 }
 
+
+template <int KC>
+int launch_prop_h(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
+                  void* ws, cudaStream_t st) {
+  const int64_t npad = (n + TILE - 1) / TILE * TILE;
+  unsigned char* Bk = reinterpret_cast<unsigned char*>(ws);
+  float* scale = reinterpret_cast<float*>(Bk + prop_ws_bk_bytes(n, KC));        // [s_c | 1/s_c | max bits]
+  unsigned int* maxbits = reinterpret_cast<unsigned int*>(scale + 2 * KC);
+  cudaError_t e = cudaMemsetAsync(maxbits, 0, KC * sizeof(unsigned int), st);
+  if (e != cudaSuccess) return (int)e;
+  k_colmax<KC><<<(unsigned)min((int64_t)592, (n * KC + 255) / 256), 256, 0, st>>>(B, n, maxbits);
+  k_prep_b16<KC><<<(unsigned)((npad * KC + 255) / 256), 256, 0, st>>>(B, n, npad, maxbits, Bk, scale);
+  const size_t smem = sizeof(PropHSmem<KC>);
+  e = cudaFuncSetAttribute(k_propagate_h<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  if (tr1 - tr0 > 65535) return -3;
+  dim3 grid((unsigned)((tr1 + H_RUN - 1) / H_RUN), (unsigned)(tr1 - tr0));
+  k_propagate_h<KC><<<grid, 288, smem, st>>>(tiles, n, tr0, mu, raw, Bk, scale, Y);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
 
 template <int KC, bool ELEM>
 int launch_prop_tc(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
@@ -1360,12 +1655,17 @@ int mcgra_propagate(const float* tiles, int64_t n, int tr0, int tr1, const float
   if (nt <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t t0 = tri(tr0);
+  if (ws != nullptr && g_prop_engine == 5 && elem == nullptr) {
+    if (K == 32) return launch_prop_h<32>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
+    if (K == 16) return launch_prop_h<16>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
+    return -1;
+  }
   if (ws != nullptr && g_prop_engine == 4 && elem == nullptr) {
     if (K == 32) return launch_prop_tc2<32>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
     if (K == 16) return launch_prop_tc2<16>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
     return -1;
   }
-  const bool use_tc = ws != nullptr && (g_prop_engine == 2 || g_prop_engine == 4 || (g_prop_engine == 3 && K == 32 && elem == nullptr));
+  const bool use_tc = ws != nullptr && (g_prop_engine == 2 || g_prop_engine == 4 || g_prop_engine == 5 || (g_prop_engine == 3 && K == 32 && elem == nullptr));
   if (use_tc) {
     if (K == 32)
       return elem ? launch_prop_tc<32, true>(tiles, n, tr0, tr1, mu, raw, B, Y, elem, ws, st)

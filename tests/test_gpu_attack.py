@@ -91,7 +91,7 @@ def test_engines_agree(which, eng):
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
 
 
-@pytest.mark.parametrize("eng", [2, 4])
+@pytest.mark.parametrize("eng", [2, 4, 5])
 @pytest.mark.parametrize("case", ["mse_all_n150", "kl_C_n150"])
 def test_tcgen05_propagate_engine_agrees(case, eng):
     """tcgen05 propagate engines (2: direct product on tcgen05/TMEM + mirrored on mma.sync; 4: both on tcgen05 with the
@@ -109,7 +109,7 @@ def test_tcgen05_propagate_engine_agrees(case, eng):
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5
 
 
-@pytest.mark.parametrize("eng", [2, 4])
+@pytest.mark.parametrize("eng", [2, 4, 5])
 def test_tcgen05_propagate_multi_tile(eng):
     from helpers import synthetic_case
     from mcgra_b200 import _native as N

@@ -29,7 +29,8 @@ def main():
     out = {}
     for rounds in range(2):
         for name, sel, split in (("v2 mma.sync", 1, True), ("v3 tcgen05+mma.sync hybrid", 2, True),
-                                 ("v4 tcgen05 both (T^T in TMEM)", 4, True)):
+                                 ("v4 tcgen05 both (T^T in TMEM)", 4, True),
+                                 ("v5 tcgen05 both, cp.async raw staging", 5, True)):
             N.lib().mcgra_set_engine(0, sel)
             eng.split_elem = split
             eng.iterate()
