@@ -62,8 +62,9 @@ enum {
 
 int mcgra_version(void);
 /* engine selection for A/B validation: which 0 = propagate (0 fp32 FFMA, 1 mma.sync 3xTF32, 2 tcgen05+mma.sync
- * hybrid, 3: hybrid for the plain 32-wide passes only, 4: both products on tcgen05 with the transposed operand in
- * tensor memory [default]); which 1 = fold (0 FFMA, 1 mma.sync, 2 tcgen05 [default]);
+ * hybrid, 3: hybrid for the plain 32-wide passes only, 4: both products on tcgen05 kind::tf32 with the transposed
+ * operand in tensor memory, 5: both products on tcgen05 kind::f16 from one fp16x2 image per tile [default]; values
+ * >= 100 set developer timing bits and are not for production use); which 1 = fold (0 FFMA, 1 mma.sync, 2 tcgen05 [default]);
  * which 2 = pairs (0 FFMA, 1 mma.sync [default]).  Returns 0, or -1 for an unknown selector.          */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */

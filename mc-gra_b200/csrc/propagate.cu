@@ -1183,14 +1183,15 @@ k_propagate_tc2(const float* __restrict__ tiles, int64_t n, int tr0, const float
 // flush the mirrored result of the previous tile; warp 8 streams the pre-formatted B[J] blocks and issues the 32 MMAs
 // of a tile.  TMEM columns: D1 [0, 3KC) | D2[0] [96, 96+3KC) | D2[1] [192, 192+3KC).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int H_RUN = 16;
+constexpr int H_RUN = 32;
+int g_prop_dbg = 0;                                // timing experiments only: mcgra_set_engine(0, 100 + bits)
 constexpr uint32_t H_SJ = 16 * 128 + 16;           // stride between 8-column groups of a plane (padded: conflict-free stores)
 constexpr uint32_t H_PLANE = 16 * H_SJ;
 
 template <int KC>
 struct PropHSmem {
   unsigned char tile[2][2][H_PLANE];               // [buffer][plane h0 / h1]
-  unsigned char bkJ[2][16 * (2 * KC) * 16];        // 16 K-groups x (2KC rows [g0 | g1] x 16 B)
+  unsigned char bkJ[3][16 * (2 * KC) * 16];        // 16 K-groups x (2KC rows [g0 | g1] x 16 B); ring of 3
   unsigned char bkI[16 * (2 * KC) * 16];
   uint64_t ready[2], tile_done[2];
   float inv_s[32];
@@ -1253,28 +1254,43 @@ __global__ void k_prep_b16(const float* __restrict__ B, int64_t n, int64_t npad,
   *reinterpret_cast<__half*>(blk + (uint32_t)(c2 >> 3) * 128u + (uint32_t)(c2 & 7) * 16u) = g1;
 }
 
+// one chunk (4 consecutive tile columns of a row) -> 8 bytes of each fp16 plane
+__device__ __forceinline__ void h_convert_store(float x0, float x1, float x2, float x3, unsigned char* p0, unsigned char* p1) {
+  const __half2 a01 = __floats2half2_rn(x0, x1), a23 = __floats2half2_rn(x2, x3);
+  const float2 f01 = __half22float2(a01), f23 = __half22float2(a23);
+  const __half2 r01 = __floats2half2_rn((x0 - f01.x) * 2048.f, (x1 - f01.y) * 2048.f);
+  const __half2 r23 = __floats2half2_rn((x2 - f23.x) * 2048.f, (x3 - f23.y) * 2048.f);
+  *reinterpret_cast<uint2*>(p0) = make_uint2(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23));
+  *reinterpret_cast<uint2*>(p1) = make_uint2(*reinterpret_cast<const uint32_t*>(&r01), *reinterpret_cast<const uint32_t*>(&r23));
+}
+// register-array element by run-time index without local memory (rolled generic path)
+__device__ __forceinline__ float4 h_pick(const float4 (&a)[16], int it) {
+  float4 v = a[0];
+#pragma unroll
+  for (int u = 1; u < 16; ++u) if (it == u) v = a[u];
+  return v;
+}
+
 // y[row][c0 + 0..15] += (d0 + (d1 + d2) * 2^-11) * inv_s   for 16 feature columns of one accumulator
 template <int KC>
 __device__ __forceinline__ void h_flush(float* __restrict__ Y, int64_t n, int64_t row, uint32_t taddr, int c0, const float* inv_s) {
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
-    float d0[8], d1[8], d2[8];
+    uint32_t d0[8], d1[8], d2[8];
     const int c = c0 + half * 8;
-    tc::tmem_ld8(taddr + c, d0);
-    tc::tmem_ld8(taddr + KC + c, d1);
-    tc::tmem_ld8(taddr + 2 * KC + c, d2);
+    tc::tmem_ld8_nowait(taddr + c, d0);
+    tc::tmem_ld8_nowait(taddr + KC + c, d1);
+    tc::tmem_ld8_nowait(taddr + 2 * KC + c, d2);
+    tc::tmem_ld_wait();
     if (row < n) {
       float4* dst = reinterpret_cast<float4*>(Y + row * KC + c);
       const float* is = inv_s + half * 8;
+      float v[8];
 #pragma unroll
-      for (int c4 = 0; c4 < 2; ++c4) {
-        float4 v;
-        v.x = (d0[c4 * 4 + 0] + (d1[c4 * 4 + 0] + d2[c4 * 4 + 0]) * (1.f / 2048.f)) * is[c4 * 4 + 0];
-        v.y = (d0[c4 * 4 + 1] + (d1[c4 * 4 + 1] + d2[c4 * 4 + 1]) * (1.f / 2048.f)) * is[c4 * 4 + 1];
-        v.z = (d0[c4 * 4 + 2] + (d1[c4 * 4 + 2] + d2[c4 * 4 + 2]) * (1.f / 2048.f)) * is[c4 * 4 + 2];
-        v.w = (d0[c4 * 4 + 3] + (d1[c4 * 4 + 3] + d2[c4 * 4 + 3]) * (1.f / 2048.f)) * is[c4 * 4 + 3];
-        atomicAdd(dst + c4, v);
-      }
+      for (int u = 0; u < 8; ++u)
+        v[u] = (__uint_as_float(d0[u]) + (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * (1.f / 2048.f)) * is[u];
+      atomicAdd(dst, make_float4(v[0], v[1], v[2], v[3]));
+      atomicAdd(dst + 1, make_float4(v[4], v[5], v[6], v[7]));
     }
   }
 }
@@ -1282,12 +1298,16 @@ __device__ __forceinline__ void h_flush(float* __restrict__ Y, int64_t n, int64_
 template <int KC>
 __global__ void __launch_bounds__(288, 1)
 k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
-              const unsigned char* __restrict__ Bk, const float* __restrict__ scale, float* __restrict__ Y) {
+              const unsigned char* __restrict__ Bk, const float* __restrict__ scale, float* __restrict__ Y, int dbg) {
   const int I = tr0 + (int)blockIdx.y;
   const int Jbeg = (int)blockIdx.x * H_RUN;
   if (Jbeg > I) return;
   const int Jend = min(I + 1, Jbeg + H_RUN);
   const int nt = Jend - Jbeg;
+  // the tiles of a run are visited in a rotated order (start depends on the tile row) so that concurrently resident
+  // CTAs of neighbouring tile rows do not add their mirrored results to the same rows of Y at the same time
+  const int rot = (I * 5) % nt;
+  auto tile_of = [&](int k) { const int r = k + rot; return Jbeg + (r >= nt ? r - nt : r); };
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PropHSmem<KC>& sm = *reinterpret_cast<PropHSmem<KC>*>(smem_raw);
   const ParamView pv = load_view(mu, raw);
@@ -1320,16 +1340,17 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
       for (int e = lane; e < (int)(BLK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(dst) + e, src + e);
     };
     load_block(I, sm.bkI);
-    load_block(Jbeg, sm.bkJ[0]);
+    load_block(tile_of(0), sm.bkJ[0]);
     tc::cp_async_commit();
     const uint32_t id_cat = make_idesc_f16(128, 2 * KC, 0), id_one = make_idesc_f16(128, KC, 0);
     const uint32_t id_cat_t = make_idesc_f16(128, 2 * KC, 1), id_one_t = make_idesc_f16(128, KC, 1);
     const uint64_t bI0 = tc::make_desc(tc::smem_u32(sm.bkI), LBO_B, 128u);
     for (int k = 0; k < nt; ++k) {
       const int b = k & 1;
-      if (k + 1 < nt) {                        // B[J+1] into the other buffer once tile k-1 is done with it
-        if (k >= 1) tc::mbar_wait(&sm.tile_done[b ^ 1], (uint32_t)(((k - 1) >> 1) & 1));
-        load_block(Jbeg + k + 1, sm.bkJ[b ^ 1]);
+      if (k + 1 < nt) {                        // B[J+1] into ring slot (k+1)%3, last read by tile k-2 (long complete:
+        // the converters could not have filled tile buffer b for tile k otherwise -- checked below through ready[b])
+        if (k >= 2) tc::mbar_wait(&sm.tile_done[b], (uint32_t)(((k - 2) >> 1) & 1));
+        load_block(tile_of(k + 1), sm.bkJ[(k + 1) % 3]);
         tc::cp_async_commit();
         tc::cp_async_wait_group<1>();          // B[J] (committed one tile ago) has landed
       } else {
@@ -1341,10 +1362,10 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
         tc::mbar_wait(&sm.ready[b], (uint32_t)((k >> 1) & 1));
         tc::fence_after();
         const uint32_t p0 = tc::smem_u32(sm.tile[b][0]), p1 = tc::smem_u32(sm.tile[b][1]);
-        const uint64_t bJ0 = tc::make_desc(tc::smem_u32(sm.bkJ[b]), LBO_B, 128u);
+        const uint64_t bJ0 = tc::make_desc(tc::smem_u32(sm.bkJ[k % 3]), LBO_B, 128u);
         const uint32_t d2 = tm + COL_D2 + (uint32_t)b * 96u;
 #pragma unroll 2
-        for (int ks = 0; ks < TILE / 16; ++ks) {
+        for (int ks = 0; ks < ((dbg & 2) ? 0 : TILE / 16); ++ks) {
           const uint64_t db = (uint64_t)((uint32_t)ks * ((2u * LBO_B) >> 4));
           const uint32_t acc1 = (k > 0 || ks > 0) ? 1u : 0u, acc2 = ks > 0 ? 1u : 0u;
           // direct: A K-major (M = row: SBO 128 between 8-row groups; K = column: LBO H_SJ between 8-column groups)
@@ -1363,7 +1384,7 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
     const int q = warp & 3, cg = warp >> 2;           // TMEM lane quarter; 16-column group this warp flushes
     const int ltid = q * 32 + lane;
     const uint32_t tlane = tm + ((uint32_t)(q * 32) << 16);
-    const bool flusher = cg < KC / 16;
+    const bool flusher = cg < KC / 16 && !(dbg & 1);
     const float* inv_s = sm.inv_s + (flusher ? cg * 16 : 0);
 
     auto fetch = [&](int J, float4 (&dst)[16]) {
@@ -1372,45 +1393,45 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
       for (int it = 0; it < 16; ++it) dst[it] = src[(it * 8 + warp) * 32 + lane];
     };
     auto step = [&](int k, float4 (&cur)[16], float4 (&nxt)[16]) {
-      const int J = Jbeg + k, b = k & 1;
+      const int J = tile_of(k), b = k & 1;
       const int64_t j0 = (int64_t)J * TILE;
-      if (k + 1 < nt) fetch(J + 1, nxt);       // a full tile ahead of its use
       if (k >= 2) tc::mbar_wait(&sm.tile_done[b], (uint32_t)(((k - 2) >> 1) & 1));   // MMAs of tile k-2 released buffer b
-      const bool fast = rows_ok && (J < I);
-      const bool interior = (J < I) && (i0 + TILE <= n);
-      unsigned char* pl0 = sm.tile[b][0];
-      unsigned char* pl1 = sm.tile[b][1];
+      // this thread's 16 chunks: row = it * 8 + warp, columns 4 * lane .. + 3  ->  8 bytes per plane at
+      // (lane/2) * H_SJ + it * 128 + warp * 16 + (lane%2) * 8
+      unsigned char* pl0 = sm.tile[b][0] + (uint32_t)(lane >> 1) * H_SJ + (uint32_t)warp * 16u + (uint32_t)(lane & 1) * 8u;
+      unsigned char* pl1 = pl0 + H_PLANE;
+      if (rows_ok && J < I) {
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int row = it * 8 + warp;
-        float xv[4] = {cur[it].x, cur[it].y, cur[it].z, cur[it].w};
-        if (!fast) {
-          const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
+        for (int it = 0; it < 16; ++it) h_convert_store(cur[it].x, cur[it].y, cur[it].z, cur[it].w, pl0 + it * 128, pl1 + it * 128);
+      } else {                                 // diagonal / last tile row / lazily projected parameter: mask + view
+        const bool interior = (J < I) && (i0 + TILE <= n);
+        const int gj = (int)(j0 + lane * 4);
+#pragma unroll 1
+        for (int it = 0; it < 16; ++it) {
+          const int gi = (int)(i0 + it * 8 + warp);
+          const float4 v = h_pick(cur, it);
+          float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const bool ok = interior || ((gj + c < gi) && (gi < n));
             xv[c] = ok ? pv.adj(xv[c]) : 0.f;
           }
+          h_convert_store(xv[0], xv[1], xv[2], xv[3], pl0 + it * 128, pl1 + it * 128);
         }
-        const __half2 a01 = __floats2half2_rn(xv[0], xv[1]), a23 = __floats2half2_rn(xv[2], xv[3]);
-        const float2 f01 = __half22float2(a01), f23 = __half22float2(a23);
-        const __half2 r01 = __floats2half2_rn((xv[0] - f01.x) * 2048.f, (xv[1] - f01.y) * 2048.f);
-        const __half2 r23 = __floats2half2_rn((xv[2] - f23.x) * 2048.f, (xv[3] - f23.y) * 2048.f);
-        const uint32_t off = (uint32_t)(lane >> 1) * H_SJ + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(lane & 1) * 8u;
-        *reinterpret_cast<uint2*>(pl0 + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23));
-        *reinterpret_cast<uint2*>(pl1 + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&r01), *reinterpret_cast<const uint32_t*>(&r23));
       }
       tc::fence_async_smem();
       mbar_arrive(&sm.ready[b]);
+      if (k + 2 < nt) fetch(tile_of(k + 2), cur);   // two tiles ahead, into the registers just consumed
       if (k >= 1) {                            // flush the mirrored result of the previous tile
         tc::mbar_wait(&sm.tile_done[b ^ 1], (uint32_t)(((k - 1) >> 1) & 1));
         tc::fence_after();
-        if (flusher) h_flush<KC>(Y, n, (j0 - TILE) + ltid, tlane + COL_D2 + (uint32_t)(b ^ 1) * 96u, cg * 16, inv_s);
+        if (flusher) h_flush<KC>(Y, n, (int64_t)tile_of(k - 1) * TILE + ltid, tlane + COL_D2 + (uint32_t)(b ^ 1) * 96u, cg * 16, inv_s);
         tc::fence_before();
       }
     };
     float4 ra[16], rb[16];
-    fetch(Jbeg, ra);
+    fetch(tile_of(0), ra);
+    if (nt > 1) fetch(tile_of(1), rb);
     for (int k = 0; k < nt; k += 2) {
       step(k, ra, rb);
       if (k + 1 < nt) step(k + 1, rb, ra);
@@ -1420,7 +1441,7 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
     tc::mbar_wait(&sm.tile_done[bl], (uint32_t)(((nt - 1) >> 1) & 1));
     tc::fence_after();
     if (flusher) {
-      h_flush<KC>(Y, n, (int64_t)(Jend - 1) * TILE + ltid, tlane + COL_D2 + (uint32_t)bl * 96u, cg * 16, inv_s);
+      h_flush<KC>(Y, n, (int64_t)tile_of(nt - 1) * TILE + ltid, tlane + COL_D2 + (uint32_t)bl * 96u, cg * 16, inv_s);
       h_flush<KC>(Y, n, i0 + ltid, tlane + COL_D1, cg * 16, inv_s);
     }
   }
@@ -1472,7 +1493,7 @@ int launch_prop_h(const float* tiles, int64_t n, int tr0, int tr1, const float* 
   if (e != cudaSuccess) return (int)e;
   if (tr1 - tr0 > 65535) return -3;
   dim3 grid((unsigned)((tr1 + H_RUN - 1) / H_RUN), (unsigned)(tr1 - tr0));
-  k_propagate_h<KC><<<grid, 288, smem, st>>>(tiles, n, tr0, mu, raw, Bk, scale, Y);
+  k_propagate_h<KC><<<grid, 288, smem, st>>>(tiles, n, tr0, mu, raw, Bk, scale, Y, g_prop_dbg);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }
@@ -1500,7 +1521,7 @@ int launch_prop_tc(const float* tiles, int64_t n, int tr0, int tr1, const float*
 // 3 = v3 for the plain 32-wide passes only, 4 = both products on tcgen05 with T^T in tensor memory (v4, default).
 // Same-process A/B on B200 at n = 65536 (tools/engine_ab.py): K = 32: v4 4.26 ms, v3 5.32 ms, v2 7.04 ms;
 // K = 16: 3.72 / 3.80 / 5.41 ms
-int g_prop_engine = 4;
+int g_prop_engine = 5;
 
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1612,6 +1633,7 @@ extern "C" {
 int mcgra_set_fold_engine_(int value);
 int mcgra_set_pairs_engine_(int value);
 int mcgra_set_engine(int which, int value) {
+  if (which == 0 && value >= 100) { g_prop_dbg = value - 100; return 0; }
   if (which == 0) { g_prop_engine = value; return 0; }
   if (which == 1) return mcgra_set_fold_engine_(value);
   if (which == 2) return mcgra_set_pairs_engine_(value);

@@ -71,10 +71,10 @@ def test_multi_tile_matches_oracle(n, weights, density):
     np.testing.assert_allclose(got["modified_adj"], ref["modified_adj"].numpy(), rtol=1e-3, atol=1e-3)
 
 
-DEFAULT_ENGINE = {0: 4, 1: 2, 2: 1}      # propagate: tcgen05 (v4); fold: tcgen05; pairs: mma.sync
+DEFAULT_ENGINE = {0: 5, 1: 2, 2: 1}      # propagate: tcgen05 fp16x2 (v5); fold: tcgen05; pairs: mma.sync
 
 
-@pytest.mark.parametrize("which,eng", [(0, 1), (0, 4), (1, 1), (1, 2), (2, 1)])
+@pytest.mark.parametrize("which,eng", [(0, 1), (0, 4), (0, 5), (1, 1), (1, 2), (2, 1)])
 def test_engines_agree(which, eng):
     """exact-fp32 FFMA engine (v1) vs the tensor-core engines (mma.sync 3xTF32, tcgen05 3xTF32) of propagate (0) /
     fold (1) / pairs (2) on the same inputs."""
@@ -104,7 +104,7 @@ def test_tcgen05_propagate_engine_agrees(case, eng):
         N.lib().mcgra_set_engine(0, eng)
         b = run_native_case(d)
     finally:
-        N.lib().mcgra_set_engine(0, 4)
+        N.lib().mcgra_set_engine(0, DEFAULT_ENGINE[0])
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-5)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5
 
@@ -120,6 +120,6 @@ def test_tcgen05_propagate_multi_tile(eng):
         N.lib().mcgra_set_engine(0, eng)
         b = run_native_case(d)
     finally:
-        N.lib().mcgra_set_engine(0, 4)
+        N.lib().mcgra_set_engine(0, DEFAULT_ENGINE[0])
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-5)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5

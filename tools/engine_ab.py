@@ -27,11 +27,14 @@ def main():
     for _ in range(3):
         eng.iterate()
     out = {}
-    for rounds in range(2):
-        for name, sel, split in (("v2 mma.sync", 1, True), ("v3 tcgen05+mma.sync hybrid", 2, True),
+    for rounds in range(1):
+        for name, sel, split in (
                                  ("v4 tcgen05 both (T^T in TMEM)", 4, True),
-                                 ("v5 tcgen05 both, cp.async raw staging", 5, True)):
+                                 ("v5 tcgen05 fp16x2 single image", 5, True),
+                                 ("v5 dbg: no flush", 5, 101), ("v5 dbg: no MMA", 5, 102), ("v5 dbg: neither", 5, 103)):
             N.lib().mcgra_set_engine(0, sel)
+            N.lib().mcgra_set_engine(0, split if split is not True else 100)
+            split = True
             eng.split_elem = split
             eng.iterate()
             torch.cuda.synchronize()
@@ -46,7 +49,8 @@ def main():
             N.TIMERS["on"] = None
             out[name] = {"ms_per_iter": round(e0.elapsed_time(e1) / steps, 3), **{k: v for k, v in kt.items() if v > 0.05}}
             print(name, json.dumps(out[name]), flush=True)
-    N.lib().mcgra_set_engine(0, 4)
+    N.lib().mcgra_set_engine(0, 100)
+    N.lib().mcgra_set_engine(0, 5)
 
 
 if __name__ == "__main__":

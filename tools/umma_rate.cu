@@ -7,7 +7,7 @@
 
 constexpr uint32_t SJ = 2048 + 16;
 
-__global__ void __launch_bounds__(128) k_rate(long long* out, int n_mma, int N, int ts, int distinct, int sw, int M, int f16) {
+__global__ void __launch_bounds__(128) k_rate(long long* out, int n_mma, int N, int ts, int distinct, int sw, int M, int f16, int amn) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint32_t tmem_base;
   __shared__ uint64_t bar;
@@ -26,14 +26,15 @@ __global__ void __launch_bounds__(128) k_rate(long long* out, int n_mma, int N, 
     const uint64_t a0 = sw ? tc::make_desc_sw(tc::smem_u32(sm), 16u, 1024u, 2u) : tc::make_desc(tc::smem_u32(sm), SJ, 128u);
     const uint64_t b0 = sw ? tc::make_desc_sw(tc::smem_u32(sm + 32 * 1024), 16u, 1024u, 2u) : tc::make_desc(tc::smem_u32(sm + 32 * SJ), lbo_b, 128u);
     uint32_t idesc = tc::make_idesc_tf32(M, N, 0, 0);
-    if (f16) idesc = (idesc & ~((7u << 7) | (7u << 10))) | (1u << 7) | (1u << 10);   // a/b format = BF16
+    if (f16) idesc = (idesc & ~((7u << 7) | (7u << 10))) | ((uint32_t)amn << 15);   // a/b format = F16, optional MN-major A
+    const uint64_t a_mn = tc::make_desc(tc::smem_u32(sm), 128u, SJ);
     const long long t0 = clock64();
     for (int i = 0; i < n_mma; ++i) {
       const int ks = distinct ? (i & 3) : 0;
       const uint64_t da = sw ? (uint64_t)(ks * 2) : (uint64_t)((uint32_t)ks * ((2u * SJ) >> 4));
       const uint64_t db = sw ? (uint64_t)(ks * 2) : (uint64_t)((uint32_t)ks * ((2u * lbo_b) >> 4));
       if (f16) {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(a0 + da), "l"(b0 + db), "r"(idesc), "r"(1u) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(amn ? a_mn + (uint64_t)(ks * 16) : a0 + da), "l"(b0 + db), "r"(idesc), "r"(1u) : "memory");
       } else if (ts) tc::mma_tf32_ts(tm, tm + 256 + ks * 8, b0 + db, idesc, 1u);
       else tc::mma_tf32(tm, a0 + da, b0 + db, idesc, 1u);
     }
@@ -56,19 +57,20 @@ int main() {
   cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int Ns[] = {32, 64, 128, 256};
   for (int f16 = 0; f16 < 2; ++f16)
-  for (int M = 64; M <= 128; M += 64)
-  for (int sw = 0; sw < 2; ++sw)
+  for (int M = 128; M <= 128; M += 64)
+  for (int sw = 0; sw < 1 + f16; ++sw)
   for (int ts = 0; ts < 2; ++ts)
     for (int N : Ns) {
         if (f16 && ts) continue;
+        const int amn = f16 ? sw : 0;
         const int distinct = 1;
         const int n_mma = 2048;
-        k_rate<<<1, 128, smem>>>(d, n_mma, N, ts, distinct, sw, M, f16);
+        k_rate<<<1, 128, smem>>>(d, n_mma, N, ts, distinct, f16 ? 0 : sw, M, f16, amn);
         long long h[2];
         cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
         printf("%s M=%3d %s A in %s  N=%3d: issue %.1f clk/MMA, complete %.1f clk/MMA  (floor max(M,128)*N/256 = %d)\n",
-               f16 ? "bf16 K=16" : "tf32 K=8 ", M, sw ? "SW128" : "NOSWZ", ts ? "TMEM" : "smem", N, (double)h[0] / n_mma, (double)h[1] / n_mma, N / 2);
+               f16 ? "f16  K=16" : "tf32 K=8 ", M, f16 ? (amn ? "A MN-major" : "A K-major ") : (sw ? "SW128" : "NOSWZ"), ts ? "TMEM" : "smem", N, (double)h[0] / n_mma, (double)h[1] / n_mma, N / 2);
       }
   return 0;
 }
