@@ -215,6 +215,7 @@ __device__ __forceinline__ void mma_tf32p(float* c, const uint32_t* a, uint32_t 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+template <bool K7, bool K2, bool DENSE>
 __global__ void __launch_bounds__(256, 2)
 k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu, int raw,
             const float* __restrict__ zhat, const float* __restrict__ r, float k7, float k2,
@@ -285,88 +286,84 @@ k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
       for (int mb = 0; mb < 2; ++mb) mma_tf32p(s[mb][nb], ahi[mb], bh[nb][0], bh[nb][1]);
   }
 
-  // ---- phase 2: element-wise on the fragments -> coefficient tile; c2's eps_row; values ----
+  // ---- phase 2: the S tile goes through shared memory so that the element-wise stage is a compact loop (the fully
+  // unrolled fragment form was instruction-fetch bound): warp w owns rows w, w+8, ..; lane = 4 consecutive columns.
+  // S is overwritten in place by the coefficient tile dL/dS. ----
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int a0 = wm * 32 + mb * 16 + g, b0 = wn * 64 + nb * 8 + 2 * t;
+      *reinterpret_cast<float2*>(&sm.cs[a0][b0]) = make_float2(s[mb][nb][0], s[mb][nb][1]);
+      *reinterpret_cast<float2*>(&sm.cs[a0 + 8][b0]) = make_float2(s[mb][nb][2], s[mb][nb][3]);
+    }
+  __syncthreads();
   const float* xt = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
-  const float* eat = EAt ? EAt + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
-  const float* ctt = Ct ? Ct + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
-  const bool needx = (k2 != 0.f) || (eat != nullptr);
+  const float* eat = (DENSE && EAt) ? EAt + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+  const float* ctt = (DENSE && Ct) ? Ct + (int64_t)blockIdx.x * TILE_ELEMS : nullptr;
+  const bool needx = K2 || (eat != nullptr);
   const bool interior = (J < I) && (i0 + TILE <= n);
   float v7 = 0.f, v2 = 0.f;
-  float colp[8][2];
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) colp[nb][0] = colp[nb][1] = 0.f;
-#pragma unroll
-  for (int mb = 0; mb < 2; ++mb) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {                 // h = 0: row g, h = 1: row g + 8
-      const int a = wm * 32 + mb * 16 + g + h * 8;
+  {
+    const int c4 = lane * 4;
+    const float4 rj4 = *reinterpret_cast<const float4*>(&sm.rJ[c4]);
+    const float rj[4] = {rj4.x, rj4.y, rj4.z, rj4.w};
+    const int gj0 = (int)(j0 + c4);
+    float colp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int a = it * 8 + warp;
       const int gi = (int)(i0 + a);
+      const float4 s4 = *reinterpret_cast<const float4*>(&sm.cs[a][c4]);
+      float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = x4, p4 = x4;
+      if (needx) x4 = __ldg(reinterpret_cast<const float4*>(xt + a * TILE + c4));
+      if (DENSE && eat) e4 = __ldg(reinterpret_cast<const float4*>(eat + a * TILE + c4));
+      if (DENSE && ctt) p4 = __ldg(reinterpret_cast<const float4*>(ctt + a * TILE + c4));
       const float ri = sm.rI[a];
+      const float sv4[4] = {s4.x, s4.y, s4.z, s4.w};
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float es[4] = {e4.x, e4.y, e4.z, e4.w};
+      const float cp[4] = {p4.x, p4.y, p4.z, p4.w};
+      float co[4];
       float rowp = 0.f;
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        const int b = wn * 64 + nb * 8 + 2 * t;
-        float2 x2 = make_float2(0.f, 0.f), e2 = x2, c2p = x2;
-        if (needx) x2 = *reinterpret_cast<const float2*>(xt + a * TILE + b);
-        if (eat) e2 = *reinterpret_cast<const float2*>(eat + a * TILE + b);
-        if (ctt) c2p = *reinterpret_cast<const float2*>(ctt + a * TILE + b);
-        const float xs[2] = {x2.x, x2.y};
-        const float es[2] = {e2.x, e2.y};
-        const float cp[2] = {c2p.x, c2p.y};
-        float co[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int gj = (int)(j0 + b + k);
-          const bool valid = interior || ((gj < gi) && (gi < n));
-          const float sv = s[mb][nb][h * 2 + k];
-          const float pm = fmaxf(sv, 0.f);
-          float dp = 0.f;
-          if (valid) {
-            if (k7 != 0.f) {
-              const float q = fminf(fmaxf(pm, ENT_LO), ENT_HI);
-              const float lg = __log2f(q);
-              v7 = fmaf(2.f * q, lg, v7);
-              if (pm >= ENT_LO && pm <= ENT_HI) dp = 2.f * k7 * (lg + INV_LN2);
-            }
-            if (k2 != 0.f) {
-              const float M = pv.adj(xs[k]);
-              const float rj = sm.rJ[b + k];
-              const float df = ri * M * rj - pm;
-              v2 = fmaf(2.f * df, df, v2);
-              dp = fmaf(-4.f * k2, df, dp);
-              const float tt = 4.f * k2 * df * M;      // (e'_ij + e'_ji) * M_ij
-              rowp = fmaf(tt, rj, rowp);
-              colp[nb][k] = fmaf(tt, ri, colp[nb][k]);
-            }
-            if (eat) {
-              const float tt = es[k] * pv.adj(xs[k]);
-              rowp = fmaf(tt, sm.rJ[b + k], rowp);
-              colp[nb][k] = fmaf(tt, ri, colp[nb][k]);
-            }
-            dp += cp[k];
-          }
-          co[k] = (valid && sv > 0.f) ? dp : 0.f;     // relu'(0) = 0
+      for (int k = 0; k < 4; ++k) {
+        const bool valid = interior || ((gj0 + k < gi) && (gi < n));
+        const float sv = sv4[k];
+        const float pm = fmaxf(sv, 0.f);
+        float dp = 0.f;
+        if (K7) {
+          const float q = fminf(fmaxf(pm, ENT_LO), ENT_HI);
+          const float lg = __log2f(q);
+          v7 = valid ? fmaf(2.f * q, lg, v7) : v7;
+          dp = (pm >= ENT_LO && pm <= ENT_HI) ? 2.f * k7 * (lg + INV_LN2) : 0.f;
         }
-        *reinterpret_cast<float2*>(&sm.cs[a][b]) = make_float2(co[0], co[1]);
+        if (K2 || DENSE) {
+          const float M = valid ? pv.adj(xs[k]) : 0.f;      // M = 0 removes every contribution of an invalid entry
+          float tt = 0.f;
+          if (K2) {
+            const float df = ri * M * rj[k] - pm;
+            v2 = valid ? fmaf(2.f * df, df, v2) : v2;
+            dp = fmaf(-4.f * k2, df, dp);
+            tt = 4.f * k2 * df * M;                         // (e'_ij + e'_ji) * M_ij
+          }
+          if (DENSE) { tt = fmaf(es[k], M, tt); dp += cp[k]; }
+          rowp = fmaf(tt, rj[k], rowp);
+          colp[k] = fmaf(tt, ri, colp[k]);
+        }
+        co[k] = (valid && sv > 0.f) ? dp : 0.f;             // relu'(0) = 0
       }
-      if (needx) {
-        rowp += __shfl_xor_sync(0xffffffffu, rowp, 1);
-        rowp += __shfl_xor_sync(0xffffffffu, rowp, 2);
-        if (t == 0 && rowp != 0.f) atomicAdd(&sm.rowacc[a], rowp);
+      *reinterpret_cast<float4*>(&sm.cs[a][c4]) = make_float4(co[0], co[1], co[2], co[3]);
+      if (K2 || DENSE) {
+        rowp = warp_sum(rowp);
+        if (lane == 0) sm.rowacc[a] = rowp;                 // every row is visited by exactly one warp iteration
       }
     }
-  }
-  if (needx) {
+    if (K2 || DENSE) {
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        float c = colp[nb][k];
-        c += __shfl_xor_sync(0xffffffffu, c, 4);
-        c += __shfl_xor_sync(0xffffffffu, c, 8);
-        c += __shfl_xor_sync(0xffffffffu, c, 16);
-        if (g == 0 && c != 0.f) atomicAdd(&sm.colacc[wn * 64 + nb * 8 + 2 * t + k], c);
-      }
+      for (int k = 0; k < 4; ++k)
+        if (colp[k] != 0.f) atomicAdd(&sm.colacc[c4 + k], colp[k]);
+    }
   }
   __syncthreads();
 
@@ -512,6 +509,19 @@ __global__ void k_row_normalize(const float* __restrict__ Z, int64_t n, int d, f
   for (int k = 0; k < d; ++k) out[i * d + k] = Z[i * d + k] * inv;
 }
 
+template <bool K7, bool K2, bool DENSE>
+int launch_pairs_mma(const float* tiles, int64_t n, int tr0, int64_t nt, const float* mu, int raw, const float* zhat,
+                     const float* r, float k7, float k2, const float* EAt, const float* Ct, float* dzhat,
+                     float* eps_row, double* acc, cudaStream_t st) {
+  const size_t smem = sizeof(PairMmaSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_pairs_mma<K7, K2, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_pairs_mma<K7, K2, DENSE><<<(unsigned)nt, 256, smem, st>>>(tiles, n, tri(tr0), mu, raw, zhat, r, k7, k2, EAt, Ct,
+                                                             dzhat, eps_row, acc);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -524,13 +534,16 @@ int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
   if (g_pairs_engine == 1) {
-    const size_t smem2 = sizeof(PairMmaSmem);
-    cudaError_t e2 = cudaFuncSetAttribute(k_pairs_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e2 != cudaSuccess) return (int)e2;
-    k_pairs_mma<<<(unsigned)nt, 256, smem2, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, zhat, r, k7, k2,
-                                                                    EAt, Ct, dzhat, eps_row, acc);
-    MCGRA_LAUNCH_CHECK();
-    return 0;
+    const bool f7 = k7 != 0.f, f2 = k2 != 0.f, fd = (EAt != nullptr) || (Ct != nullptr);
+#define MCGRA_PAIRS_CASE(A, B, D)                                                                                  \
+    if (f7 == A && f2 == B && fd == D)                                                                             \
+      return launch_pairs_mma<A, B, D>(tiles, n, tr0, nt, mu, raw, zhat, r, k7, k2, EAt, Ct, dzhat, eps_row, acc,  \
+                                       (cudaStream_t)stream);
+    MCGRA_PAIRS_CASE(false, false, false) MCGRA_PAIRS_CASE(false, false, true)
+    MCGRA_PAIRS_CASE(false, true, false) MCGRA_PAIRS_CASE(false, true, true)
+    MCGRA_PAIRS_CASE(true, false, false) MCGRA_PAIRS_CASE(true, false, true)
+    MCGRA_PAIRS_CASE(true, true, false) MCGRA_PAIRS_CASE(true, true, true)
+#undef MCGRA_PAIRS_CASE
   }
   const size_t smem = sizeof(PairSmem);
   cudaError_t e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
