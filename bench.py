@@ -281,9 +281,15 @@ def run_native(a):
     roof = None
     if prop_ms:
         ach = prop_bytes / (prop_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_propagate_tc2<32> (Y += M*B over the tiled triangle; both products on "
-                                          "tcgen05, 3xTF32, accumulators + transposed operand in TMEM)", "achieved": ach,
-                "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
+        # workload (profiles/ncu_traffic.json, written by profiles/ncu_summary.py); null when no capture is committed
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if world == 1 and os.path.exists(tp):
+            traffic = json.load(open(tp)).get(wl["name"], {}).get("k_propagate_h<32>")
+        roof = {"bound": "hbm", "kernel": "k_propagate_h<32> (Y += M*B over the tiled triangle; both products on tcgen05 "
+                                          "kind::f16 from one fp16x2 image per tile, fp32 accumulators in TMEM)",
+                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "launch_ms": prop_ms, "algorithmic_bytes_per_launch": prop_bytes,
                 "per_kernel_ms": kt}
