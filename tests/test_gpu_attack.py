@@ -123,3 +123,22 @@ def test_tcgen05_propagate_multi_tile(eng):
         N.lib().mcgra_set_engine(0, DEFAULT_ENGINE[0])
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-5)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5
+
+
+def test_two_gpu_sharded_attack_matches_golden():
+    """Tile-row sharding over 2 ranks (NCCL): same trajectories as the single-GPU golden fixtures (tests/mgpu_check.py
+    under torchrun).  Skipped on a 1-GPU box; `gpurun --gpus 2` runs it."""
+    import socket
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "mgpu_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
