@@ -226,6 +226,30 @@ int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const f
 int mcgra_label_accumulate(const int64_t* labels, int64_t n, float* out, int64_t ld, int64_t row0,
                            int64_t row1, void* stream);
 
+/* The whole ensemble sum of :300-322 in ONE pass over the n x n result (each term above re-reads and re-writes it):
+ * out[i,j] = M_ij (symmetric zero-diagonal expansion of `tiles`, skipped when tiles == NULL: out starts from 0)
+ *            + term_0 + term_1 + ... added left to right in fp32, so the value equals the sequence of
+ * mcgra_tiles_to_dense / mcgra_gram_accumulate / mcgra_dense_add / mcgra_label_accumulate calls bit for bit.       */
+#define MCGRA_ENSEMBLE_MAX 8
+enum { MCGRA_TERM_GRAM = 0, MCGRA_TERM_DENSE = 1, MCGRA_TERM_LABEL = 2 };
+typedef struct {
+  int kind;                 /* MCGRA_TERM_*                                                            */
+  int d;                    /* gram: factor width (<= 32)                                              */
+  int variant;              /* gram: as mcgra_gram_accumulate                                          */
+  int pad_;
+  const float* Z;           /* gram: n x d factors                                                     */
+  const float* rownorm;     /* gram variant 2                                                          */
+  const float* dense;       /* dense: n x n row-major addend (leading dimension n)                     */
+  const int64_t* labels;    /* label: adds (labels[i] == labels[j])                                    */
+} mcgra_ensemble_term;
+typedef struct {
+  int nterms;
+  int pad_;
+  mcgra_ensemble_term t[MCGRA_ENSEMBLE_MAX];
+} mcgra_ensemble_args;
+int mcgra_ensemble(const float* tiles, int64_t n, const mcgra_ensemble_args* args, float* out, int64_t ld,
+                   int64_t row0, int64_t row1, void* stream);
+
 /* out += in (dense, `count` floats); F.normalize(Z, p, dim=1) with eps 1e-12                          */
 int mcgra_dense_add(float* out, const float* in, int64_t count, void* stream);
 int mcgra_row_normalize(const float* Z, int64_t n, int d, float p, float* out, void* stream);

@@ -52,6 +52,19 @@ class FoldArgs(C.Structure):
                 ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int), ("Wk", c_fp)]
 
 
+ENSEMBLE_MAX = 8
+TERM_GRAM, TERM_DENSE, TERM_LABEL = 0, 1, 2
+
+
+class EnsembleTerm(C.Structure):
+    _fields_ = [("kind", C.c_int), ("d", C.c_int), ("variant", C.c_int), ("pad_", C.c_int), ("Z", c_fp),
+                ("rownorm", c_fp), ("dense", c_fp), ("labels", c_fp)]
+
+
+class EnsembleArgs(C.Structure):
+    _fields_ = [("nterms", C.c_int), ("pad_", C.c_int), ("t", EnsembleTerm * ENSEMBLE_MAX)]
+
+
 _SIGS = {
     "mcgra_version": (C.c_int, []),
     "mcgra_set_engine": (C.c_int, [C.c_int, C.c_int]),
@@ -85,6 +98,7 @@ _SIGS = {
     "mcgra_gram_accumulate": (C.c_int, [c_fp, C.c_int, i64, C.c_int, c_fp, c_fp, i64, i64, i64, c_fp]),
     "mcgra_label_accumulate": (C.c_int, [c_fp, i64, c_fp, i64, i64, i64, c_fp]),
     "mcgra_dense_add": (C.c_int, [c_fp, c_fp, i64, c_fp]),
+    "mcgra_ensemble": (C.c_int, [c_fp, i64, C.POINTER(EnsembleArgs), c_fp, i64, i64, i64, c_fp]),
     "mcgra_row_normalize": (C.c_int, [c_fp, i64, C.c_int, C.c_float, c_fp, c_fp]),
     "mcgra_gauss_stats": (C.c_int, [c_fp, C.c_int, c_fp, C.c_int, i64, C.c_float, C.c_float, c_fp, c_fp, c_fp, c_fp]),
     "mcgra_pair_dense": (C.c_int, [c_fp, C.c_int, i64, c_fp, i64, C.c_int, C.c_float, c_fp, c_fp]),

@@ -481,6 +481,79 @@ k_gram_accumulate(const float* __restrict__ Z, int d, int64_t n, int variant, co
   }
 }
 
+// fused ensemble: 32 x 32 output block per CTA, thread (tx, ty) owns column tx of rows ty, ty+8, ty+16, ty+24; the
+// partial sums stay in registers across the terms and the block is written once.  Per-term arithmetic is the code of
+// the stand-alone kernels (k_tiles_to_dense view, k_gram_accumulate, k_dense_add, k_label_accumulate).
+__global__ void __launch_bounds__(256)
+k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, float* __restrict__ out, int64_t ld,
+           int64_t row0) {
+  __shared__ float zi[32][33], zj[32][33];
+  const int64_t bi = row0 + (int64_t)blockIdx.y * 32, bj = (int64_t)blockIdx.x * 32;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (tiles != nullptr) {
+    // stage the stored block (rows of the larger index, columns of the smaller one), read it straight or transposed
+    const int64_t br = bi >= bj ? bi : bj, bc = bi >= bj ? bj : bi;
+    const float* tl = tiles + (tri(br / TILE) + bc / TILE) * (int64_t)TILE_ELEMS + (br % TILE) * TILE + (bc % TILE);
+    for (int rr = ty; rr < 32; rr += 8) {
+      const float v = tl[rr * TILE + tx];
+      zi[rr][tx] = fminf(fmaxf(v, 0.f), 1.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rr = ty + q * 8;
+      const int64_t gi = bi + rr, gj = bj + tx;
+      float v = 0.f;
+      if (gi < n && gj < n && gi != gj) v = gi > gj ? zi[rr][tx] : zi[tx][rr];   // entry (max, min) of the stored block
+      acc[q] = v;
+    }
+    __syncthreads();
+  }
+  for (int tm = 0; tm < ea.nterms; ++tm) {
+    const mcgra_ensemble_term& T = ea.t[tm];
+    if (T.kind == MCGRA_TERM_GRAM) {
+      const int d = T.d;
+      for (int e = tid; e < 32 * d; e += 256) {
+        const int a = e / d, k = e % d;
+        zi[a][k] = (bi + a < n) ? T.Z[(bi + a) * d + k] : 0.f;
+        zj[a][k] = (bj + a < n) ? T.Z[(bj + a) * d + k] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int rr = ty + q * 8;
+        const int64_t gi = bi + rr, gj = bj + tx;
+        if (gi >= n || gj >= n) continue;
+        float s = 0.f;
+        for (int k = 0; k < d; ++k) s = fmaf(zi[rr][k], zj[tx][k], s);
+        if (T.variant == 2) s = s / fmaxf(T.rownorm[gi], 1e-12f);
+        float v = (T.variant == 3) ? s : fmaxf(s - (gi == gj ? 1.f : 0.f), 0.f);
+        if (T.variant == 0) v = 1.f / (1.f + expf(-v));
+        acc[q] += v;
+      }
+      __syncthreads();
+    } else if (T.kind == MCGRA_TERM_DENSE) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t gi = bi + ty + q * 8, gj = bj + tx;
+        if (gi < n && gj < n) acc[q] += T.dense[gi * n + gj];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t gi = bi + ty + q * 8, gj = bj + tx;
+        if (gi < n && gj < n && T.labels[gi] == T.labels[gj]) acc[q] += 1.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t gi = bi + ty + q * 8, gj = bj + tx;
+    if (gi < n && gj < n) out[gi * ld + gj] = acc[q];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_label_accumulate(const int64_t* __restrict__ labels, int64_t n, float* __restrict__ out, int64_t ld, int64_t row0,
                    int64_t row1) {
@@ -569,6 +642,20 @@ int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const f
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((row1 - row0 + 31) / 32));
   if (grid.y > 65535) return -3;
   k_gram_accumulate<<<grid, 256, 0, (cudaStream_t)stream>>>(Z, d, n, variant, rownorm, out, ld, row0);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_ensemble(const float* tiles, int64_t n, const mcgra_ensemble_args* args, float* out, int64_t ld,
+                   int64_t row0, int64_t row1, void* stream) {
+  if (args == nullptr || args->nterms < 0 || args->nterms > MCGRA_ENSEMBLE_MAX) return -1;
+  if ((row0 & 31) != 0) return -1;
+  for (int t = 0; t < args->nterms; ++t)
+    if (args->t[t].kind == MCGRA_TERM_GRAM && (args->t[t].d < 1 || args->t[t].d > 32)) return -1;
+  if (row1 <= row0) return 0;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((row1 - row0 + 31) / 32));
+  if (grid.y > 65535) return -3;
+  k_ensemble<<<grid, 256, 0, (cudaStream_t)stream>>>(tiles, n, *args, out, ld, row0);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }

@@ -115,6 +115,22 @@ class PGDAttack(BaseAttack):
             raise NotImplementedError("--eps != 0 (un-symmetrised n x n Gaussian noise, :474-478) is not built yet")
         dev = torch.device(self.device)
         n = self.nnodes
+        timing = {} if kwargs.get("_timing") else None      # bench hook: phase wall-clock (adds synchronisations)
+        import time as _time
+
+        def _mark(name, _t=[None]):
+            if timing is None:
+                return
+            torch.cuda.synchronize(dev)
+            now = _time.perf_counter()
+            if _t[0] is not None:
+                timing[name] = timing.get(name, 0.0) + now - _t[0]
+            _t[0] = now
+        _mark("start")
+        # release the previous call's device state first: the allocator can then recycle its blocks instead of growing
+        # (x', m, v, F tiles and the n x n result are tens of GB at n = 65 536; cudaMalloc of such blocks costs ~0.1 s each)
+        self.engine = None
+        self.modified_adj = None
         victim_model = self.surrogate
         victim_model.eval()
         if self.embedding is not None:
@@ -143,7 +159,9 @@ class PGDAttack(BaseAttack):
             E1 = torch.relu(self._mm_adj(adj_d, S1) + b1)
             HA_loop = torch.relu(self._mm_adj(adj_d, E1 @ W2) + b2)
             YA_loop = F.log_softmax(HA_loop @ Wl.t() + bl, dim=1)
+        _mark("inputs_and_constants")
         fa = feature_adj.to(dev) if torch.is_tensor(feature_adj) else _dense(feature_adj, dev)
+        _mark("feature_adj_h2d")
 
         rank, world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -155,7 +173,9 @@ class PGDAttack(BaseAttack):
                                 x0=x0, device=dev, rank=rank, world=world,
                                 max_epochs=max(int(epochs), int(kwargs.get('_engine_epochs', 1)), 1))
         eng = self.engine
+        _mark("engine_setup")
         self._trace = []
+        self._timing = timing
         for _ in range(int(epochs)):
             eng.iterate()
             if kwargs.get("_trace"):             # test hook: parameter after every iteration's projection
@@ -164,7 +184,9 @@ class PGDAttack(BaseAttack):
             return 0, 0, 0, 0
         if int(epochs) == 0:
             eng.forward_stages(0)
+        _mark("iterations")
         self._finalize(eng, args, fa, labels_t, W2, b1, b2, Wl, bl)
+        _mark("finalize")
         return 0, 0, 0, 0
 
     # ------------------------------------------------------------------------------------------------
@@ -223,8 +245,6 @@ class PGDAttack(BaseAttack):
         packed = torch.empty(P, dtype=torch.float32, device=dev)
         call("mcgra_tiles_to_tril", ptr(xf), n, 0, T, None, 1, ptr(packed), st)
         self.adj_changes.data = packed                                   # :301
-        out = torch.zeros(n, n, dtype=torch.float32, device=dev)
-        call("mcgra_tiles_to_dense", ptr(xf), n, 0, T, None, 1, ptr(out), n, st)   # :302
         # embeddings / victim output on the raw decoded adjacency (:304-308): two propagations over xf
         Y = torch.zeros(n, HID, dtype=torch.float32, device=dev)
         call("mcgra_propagate", ptr(xf), n, 0, T, None, 1, ptr(eng.S1), HID, ptr(Y), None, None, st)
@@ -234,23 +254,45 @@ class PGDAttack(BaseAttack):
         call("mcgra_propagate", ptr(xf), n, 0, T, None, 1, ptr(T2), HID, ptr(Y2), None, None, st)
         H2 = torch.relu(Y2 + b2)
         YA2 = F.log_softmax(H2 @ Wl.t() + bl, dim=1)
-        del xf
-        # cur_adj = modified_adj + H_A1 + H_A2 + feature_adj + Y_A2 (+ ori_HA) (+ ori_YA) (+ label_adj), in this order
-        self._gram_add(out, H1)
-        self._gram_add(out, H2)
-        call("mcgra_dense_add", ptr(out), ptr(fa.to(torch.float32).contiguous()), n * n, st)
-        self._gram_add(out, YA2)
+        # cur_adj = modified_adj (:302) + H_A1 + H_A2 + feature_adj + Y_A2 (+ ori_HA) (+ ori_YA) (+ label_adj), summed in
+        # this order in ONE pass over the n x n result (mcgra_ensemble)
+        ea = N.EnsembleArgs()
+        keep = []                                   # operands must outlive the launch
+
+        def gram(Z):
+            Zp, variant, rown = self._decode2_spec(Z.to(torch.float32))
+            keep.append((Zp, rown))
+            t = ea.t[ea.nterms]
+            t.kind, t.d, t.variant, t.Z, t.rownorm = N.TERM_GRAM, int(Zp.shape[1]), variant, ptr(Zp), ptr(rown)
+            ea.nterms += 1
+
+        def dense(M):
+            M = M.to(torch.float32).contiguous()
+            keep.append(M)
+            t = ea.t[ea.nterms]
+            t.kind, t.dense = N.TERM_DENSE, ptr(M)
+            ea.nterms += 1
+
+        gram(H1)
+        gram(H2)
+        dense(fa)
+        gram(YA2)
         if args.useH_A:
-            self._gram_add(out, self.H_A.detach().to(dev))
+            gram(self.H_A.detach().to(dev))
         if args.useY_A:
-            self._gram_add(out, self.Y_A.detach().to(dev))
+            gram(self.Y_A.detach().to(dev))
         if args.useY:
             path = "./saved_data/" + args.dataset + ".npy"
             if os.path.exists(path):                                      # :133-134
-                lab = torch.from_numpy(np.load(path)).to(dev, torch.float32).contiguous()
-                call("mcgra_dense_add", ptr(out), ptr(lab), n * n, st)
+                dense(torch.from_numpy(np.load(path)).to(dev))
             else:    # same matrix built from the labels (main.prepare, main.py:440-450)
-                call("mcgra_label_accumulate", ptr(labels_t), n, ptr(out), n, 0, n, st)
+                t = ea.t[ea.nterms]
+                t.kind, t.labels = N.TERM_LABEL, ptr(labels_t)
+                ea.nterms += 1
+        out = torch.empty(n, n, dtype=torch.float32, device=dev)
+        import ctypes as _C
+        call("mcgra_ensemble", ptr(xf), n, _C.byref(ea), ptr(out), n, 0, n, st)
+        del xf, keep
         self.modified_adj = out.detach()
 
     # ------------------------------------------------------------------------------------------------

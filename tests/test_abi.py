@@ -45,7 +45,7 @@ def test_struct_sizes_match_c(native):
     code = textwrap.dedent("""
         #include <stdio.h>
         #include "mcgra.h"
-        int main(){ printf("%zu %zu %zu\\n", sizeof(mcgra_elem_args), sizeof(mcgra_node_args), sizeof(mcgra_fold_args)); return 0; }
+        int main(){ printf("%zu %zu %zu %zu\\n", sizeof(mcgra_elem_args), sizeof(mcgra_node_args), sizeof(mcgra_fold_args), sizeof(mcgra_ensemble_args)); return 0; }
     """)
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "s.c")
@@ -53,7 +53,8 @@ def test_struct_sizes_match_c(native):
         exe = os.path.join(td, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    assert sizes == [ctypes.sizeof(native.ElemArgs), ctypes.sizeof(native.NodeArgs), ctypes.sizeof(native.FoldArgs)]
+    assert sizes == [ctypes.sizeof(native.ElemArgs), ctypes.sizeof(native.NodeArgs), ctypes.sizeof(native.FoldArgs),
+                     ctypes.sizeof(native.EnsembleArgs)]
 
 
 def test_no_cpu_fallback():

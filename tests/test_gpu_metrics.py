@@ -70,3 +70,47 @@ def test_metric_pool_api():
     real = d["adj"][idx][:, idx].reshape(-1)
     pred = d["modified_adj"][idx][:, idx].reshape(-1)
     assert abs(sub - O.roc_auc(real, pred)) < 1e-9
+
+
+@pytest.mark.parametrize("n", [97, 300, 515])
+def test_fused_ensemble_is_bitwise_the_sequence_of_terms(n):
+    """mcgra_ensemble (one pass over the n x n result) == mcgra_tiles_to_dense followed by mcgra_gram_accumulate /
+    mcgra_dense_add / mcgra_label_accumulate in the same order, bit for bit (topology_attack.py:300-322)."""
+    import ctypes
+    from mcgra_b200 import _native as N
+    from mcgra_b200._native import call, ptr
+    g = torch.Generator(device="cuda").manual_seed(n)
+    T = (n + N.TILE - 1) // N.TILE
+    st = N.stream_ptr()
+    packed = torch.rand(n * (n - 1) // 2, device="cuda", generator=g)
+    tiles = torch.zeros(T * (T + 1) // 2 * N.TILE * N.TILE, device="cuda")
+    call("mcgra_tril_to_tiles", ptr(packed), n, 0, T, ptr(tiles), st)
+    Z1 = torch.randn(n, 16, device="cuda", generator=g)
+    Z2 = torch.randn(n, 7, device="cuda", generator=g)
+    rown = torch.rand(n, device="cuda", generator=g) + 0.5
+    D = torch.randn(n, n, device="cuda", generator=g)
+    lab = torch.randint(0, 4, (n,), device="cuda", generator=g)
+    seq = torch.zeros(n, n, device="cuda")
+    call("mcgra_tiles_to_dense", ptr(tiles), n, 0, T, None, 1, ptr(seq), n, st)
+    call("mcgra_gram_accumulate", ptr(Z1), 16, n, 0, None, ptr(seq), n, 0, n, st)
+    call("mcgra_gram_accumulate", ptr(Z2), 7, n, 1, None, ptr(seq), n, 0, n, st)
+    call("mcgra_dense_add", ptr(seq), ptr(D), n * n, st)
+    call("mcgra_gram_accumulate", ptr(Z1), 16, n, 2, ptr(rown), ptr(seq), n, 0, n, st)
+    call("mcgra_label_accumulate", ptr(lab), n, ptr(seq), n, 0, n, st)
+    ea = N.EnsembleArgs()
+    spec = [(N.TERM_GRAM, Z1, 0, None), (N.TERM_GRAM, Z2, 1, None), (N.TERM_DENSE, D, 0, None),
+            (N.TERM_GRAM, Z1, 2, rown), (N.TERM_LABEL, lab, 0, None)]
+    for k, (kind, t, variant, rn) in enumerate(spec):
+        e = ea.t[k]
+        e.kind, e.variant = kind, variant
+        if kind == N.TERM_GRAM:
+            e.d, e.Z, e.rownorm = t.shape[1], ptr(t), ptr(rn)
+        elif kind == N.TERM_DENSE:
+            e.dense = ptr(t)
+        else:
+            e.labels = ptr(t)
+    ea.nterms = len(spec)
+    fused = torch.full((n, n), float("nan"), device="cuda")
+    call("mcgra_ensemble", ptr(tiles), n, ctypes.byref(ea), ptr(fused), n, 0, n, st)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, seq)
