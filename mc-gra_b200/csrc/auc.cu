@@ -129,12 +129,20 @@ __device__ __forceinline__ int64_t upper_bound(const uint32_t* a, int64_t n, uin
   return lo;
 }
 
-// every negative against the sorted positives
+// every negative against the sorted positives.  A 1024-entry sample of the sorted keys sits in shared memory: the
+// search does ~10 steps there and only log2(npos / 1024) steps in global memory; upper_bound continues from lower_bound
+// only when a positive has the same key, so a negative costs ~10 global loads instead of 2 * log2(npos).
+constexpr int RANK_TAB = 1024;
 __global__ void __launch_bounds__(256)
 k_rank_negatives(const float* __restrict__ scores, const uint8_t* __restrict__ labels, int64_t N,
                  const uint32_t* __restrict__ pos, const unsigned long long* __restrict__ counter,
                  unsigned long long* __restrict__ hist /*[npos+1]*/, unsigned long long* __restrict__ sums /*[2]*/) {
-  const int64_t npos = (int64_t)*counter;
+  __shared__ uint32_t tab[RANK_TAB];
+  const int npos = (int)*counter;
+  const int step = (npos + RANK_TAB - 1) / RANK_TAB > 0 ? (npos + RANK_TAB - 1) / RANK_TAB : 1;
+  const int ntab = (npos + step - 1) / step;               // tab[t] = pos[t * step]
+  for (int t = threadIdx.x; t < ntab; t += blockDim.x) tab[t] = pos[(int64_t)t * step];
+  __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   unsigned long long twice = 0, nneg = 0;
   const int lane = threadIdx.x & 31;
@@ -142,11 +150,23 @@ k_rank_negatives(const float* __restrict__ scores, const uint8_t* __restrict__ l
   for (int64_t rd = 0; rd < nround; ++rd) {
     const int64_t g = rd * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool neg = (g < N) && !labels[g];
-    int64_t ub = -1 - lane;     // unique sentinel so inactive lanes do not aggregate
+    int ub = -1 - lane;         // unique sentinel so inactive lanes do not aggregate
     if (neg) {
       const uint32_t k = fkey(scores[g]);
-      const int64_t lb = lower_bound(pos, npos, k);
-      ub = upper_bound(pos, npos, k);
+      // first sample >= k in the table: lower_bound(pos, k) lies in ((t-1) * step, t * step]
+      int lo = 0, hi = ntab;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid] < k) lo = mid + 1; else hi = mid;
+      }
+      int l = lo == 0 ? 0 : (lo - 1) * step + 1;
+      int h = lo == ntab ? npos : lo * step;
+      while (l < h) {
+        const int mid = (l + h) >> 1;
+        if (pos[mid] < k) l = mid + 1; else h = mid;
+      }
+      const int lb = l;
+      ub = (lb < npos && pos[lb] == k) ? (int)upper_bound(pos, npos, k) : lb;    // ties with a positive are rare
       twice += 2ull * (unsigned long long)(npos - ub) + (unsigned long long)(ub - lb);
       nneg += 1;
     }

@@ -481,76 +481,125 @@ k_gram_accumulate(const float* __restrict__ Z, int d, int64_t n, int variant, co
   }
 }
 
-// fused ensemble: 32 x 32 output block per CTA, thread (tx, ty) owns column tx of rows ty, ty+8, ty+16, ty+24; the
-// partial sums stay in registers across the terms and the block is written once.  Per-term arithmetic is the code of
-// the stand-alone kernels (k_tiles_to_dense view, k_gram_accumulate, k_dense_add, k_label_accumulate).
+// fused ensemble: 64 x 64 output block per CTA, thread (tx, ty) owns the 4 x 4 micro-tile rows 4 ty.., columns 4 tx..;
+// the partial sums stay in registers across the terms and the block is written once.  Factors are staged transposed
+// ([k][row]) so that one k step is two 16-byte shared loads for 16 FMAs (the 32 x 32 scalar form was LDS-bound).
+// Per-element arithmetic (order of the fmaf chain over k, the variant transforms, the left-to-right sum of the terms)
+// is exactly that of k_tiles_to_dense / k_gram_accumulate / k_dense_add / k_label_accumulate.
+constexpr int EB = 64;
 __global__ void __launch_bounds__(256)
 k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, float* __restrict__ out, int64_t ld,
            int64_t row0) {
-  __shared__ float zi[32][33], zj[32][33];
-  const int64_t bi = row0 + (int64_t)blockIdx.y * 32, bj = (int64_t)blockIdx.x * 32;
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  __shared__ __align__(16) float buf[2 * 32 * EB + EB];       // M stage: [64][65]; gram stage: ziT[32][64] | zjT[32][64]
+  const int64_t bi = row0 + (int64_t)blockIdx.y * EB, bj = (int64_t)blockIdx.x * EB;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
   if (tiles != nullptr) {
-    // stage the stored block (rows of the larger index, columns of the smaller one), read it straight or transposed
+    // stage the stored block (rows of the larger index, columns of the smaller one); entry (max, min) is read from it
     const int64_t br = bi >= bj ? bi : bj, bc = bi >= bj ? bj : bi;
     const float* tl = tiles + (tri(br / TILE) + bc / TILE) * (int64_t)TILE_ELEMS + (br % TILE) * TILE + (bc % TILE);
-    for (int rr = ty; rr < 32; rr += 8) {
-      const float v = tl[rr * TILE + tx];
-      zi[rr][tx] = fminf(fmaxf(v, 0.f), 1.f);
+    for (int e = tid; e < EB * EB; e += 256) {
+      const int rr = e >> 6, cc = e & 63;
+      buf[rr * (EB + 1) + cc] = fminf(fmaxf(tl[rr * TILE + cc], 0.f), 1.f);
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int rr = ty + q * 8;
-      const int64_t gi = bi + rr, gj = bj + tx;
-      float v = 0.f;
-      if (gi < n && gj < n && gi != gj) v = gi > gj ? zi[rr][tx] : zi[tx][rr];   // entry (max, min) of the stored block
-      acc[q] = v;
-    }
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4 + q;
+        const int a = (int)(gi > gj ? gi - br : gj - br), c = (int)(gi > gj ? gj - bc : gi - bc);
+        acc[p][q] = (gi < n && gj < n && gi != gj) ? buf[a * (EB + 1) + c] : 0.f;
+      }
     __syncthreads();
   }
+  float* ziT = buf;
+  float* zjT = buf + 32 * EB;
   for (int tm = 0; tm < ea.nterms; ++tm) {
     const mcgra_ensemble_term& T = ea.t[tm];
     if (T.kind == MCGRA_TERM_GRAM) {
       const int d = T.d;
-      for (int e = tid; e < 32 * d; e += 256) {
+      for (int e = tid; e < EB * d; e += 256) {
         const int a = e / d, k = e % d;
-        zi[a][k] = (bi + a < n) ? T.Z[(bi + a) * d + k] : 0.f;
-        zj[a][k] = (bj + a < n) ? T.Z[(bj + a) * d + k] : 0.f;
+        ziT[k * EB + a] = (bi + a < n) ? T.Z[(bi + a) * d + k] : 0.f;
+        zjT[k * EB + a] = (bj + a < n) ? T.Z[(bj + a) * d + k] : 0.f;
       }
       __syncthreads();
+      float s[4][4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int rr = ty + q * 8;
-        const int64_t gi = bi + rr, gj = bj + tx;
-        if (gi >= n || gj >= n) continue;
-        float s = 0.f;
-        for (int k = 0; k < d; ++k) s = fmaf(zi[rr][k], zj[tx][k], s);
-        if (T.variant == 2) s = s / fmaxf(T.rownorm[gi], 1e-12f);
-        float v = (T.variant == 3) ? s : fmaxf(s - (gi == gj ? 1.f : 0.f), 0.f);
-        if (T.variant == 0) v = 1.f / (1.f + expf(-v));
-        acc[q] += v;
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[p][q] = 0.f;
+      for (int k = 0; k < d; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(ziT + k * EB + ty * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(zjT + k * EB + tx * 4);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s[p][q] = fmaf(av[p], bv[q], s[p][q]);
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int64_t gi = bi + ty * 4 + p;
+        const float rn = (T.variant == 2 && gi < n) ? fmaxf(T.rownorm[gi], 1e-12f) : 1.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t gj = bj + tx * 4 + q;
+          float sv = s[p][q];
+          if (T.variant == 2) sv = sv / rn;
+          float v = (T.variant == 3) ? sv : fmaxf(sv - (gi == gj ? 1.f : 0.f), 0.f);
+          if (T.variant == 0) v = 1.f / (1.f + expf(-v));
+          acc[p][q] += v;
+        }
       }
       __syncthreads();
     } else if (T.kind == MCGRA_TERM_DENSE) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t gi = bi + ty + q * 8, gj = bj + tx;
-        if (gi < n && gj < n) acc[q] += T.dense[gi * n + gj];
+      for (int p = 0; p < 4; ++p) {
+        const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4;
+        if (gi >= n) continue;
+        if ((n & 3) == 0) {                       // rows are 16-byte aligned: one vector load (gj + 3 < n since n % 4 == 0)
+          if (gj < n) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(T.dense + gi * n + gj));
+            acc[p][0] += v.x; acc[p][1] += v.y; acc[p][2] += v.z; acc[p][3] += v.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (gj + q < n) acc[p][q] += T.dense[gi * n + gj + q];
+        }
       }
     } else {
+      int64_t lj[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t gi = bi + ty + q * 8, gj = bj + tx;
-        if (gi < n && gj < n && T.labels[gi] == T.labels[gj]) acc[q] += 1.f;
+      for (int q = 0; q < 4; ++q) lj[q] = (bj + tx * 4 + q < n) ? T.labels[bj + tx * 4 + q] : -1;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int64_t gi = bi + ty * 4 + p;
+        if (gi >= n) continue;
+        const int64_t li = T.labels[gi];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (bj + tx * 4 + q < n && li == lj[q]) acc[p][q] += 1.f;
       }
     }
   }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int64_t gi = bi + ty + q * 8, gj = bj + tx;
-    if (gi < n && gj < n) out[gi * ld + gj] = acc[q];
+  for (int p = 0; p < 4; ++p) {
+    const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4;
+    if (gi >= n) continue;
+    if ((ld & 3) == 0 && gj + 3 < n && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+      *reinterpret_cast<float4*>(out + gi * ld + gj) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (gj + q < n) out[gi * ld + gj + q] = acc[p][q];
+    }
   }
 }
 
@@ -649,11 +698,11 @@ int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const f
 int mcgra_ensemble(const float* tiles, int64_t n, const mcgra_ensemble_args* args, float* out, int64_t ld,
                    int64_t row0, int64_t row1, void* stream) {
   if (args == nullptr || args->nterms < 0 || args->nterms > MCGRA_ENSEMBLE_MAX) return -1;
-  if ((row0 & 31) != 0) return -1;
+  if ((row0 & 63) != 0) return -1;
   for (int t = 0; t < args->nterms; ++t)
     if (args->t[t].kind == MCGRA_TERM_GRAM && (args->t[t].d < 1 || args->t[t].d > 32)) return -1;
   if (row1 <= row0) return 0;
-  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((row1 - row0 + 31) / 32));
+  dim3 grid((unsigned)((n + EB - 1) / EB), (unsigned)((row1 - row0 + EB - 1) / EB));
   if (grid.y > 65535) return -3;
   k_ensemble<<<grid, 256, 0, (cudaStream_t)stream>>>(tiles, n, *args, out, ld, row0);
   MCGRA_LAUNCH_CHECK();
