@@ -31,6 +31,13 @@ WORKLOADS = {
     "tiny": dict(n=1024, f=64, c=4, name="synthetic n=1024 (debug)"),
 }
 PROFILE_A = (0.01, 0, 0, 0, 0, 10, 10, 0, 10, 1000)
+# SURVEY 8(d) Profile B = README Polblogs all-priors command (MC-GRA/README.md:90), measure HSIC, lr 10^-2.5
+PROFILE_B = (0.01, 0.01, 0, 0, 0, 10000, 100, 0, 0.001, 1000)
+PROFILES = {"A": dict(w=PROFILE_A, measure="MSELoss", lr=-2.0,
+                      flags="Profile A: README Cora MSELoss w1=.01 w6=10 w7=10 w9=10 w10=1000 lr=1e-2"),
+            "B": dict(w=PROFILE_B, measure="HSIC", lr=-2.5,
+                      flags="Profile B: README Polblogs HSIC w1=.01 w2=.01 w6=1e4 w7=100 w9=.001 w10=1000 lr=10^-2.5 "
+                            "(n x n HSIC stage on library GEMMs, DESIGN.md 1)")}
 SAMPLE_N = 3072           # CPU baseline sample size (reference algorithm is O(n^3) per iteration)
 
 
@@ -38,11 +45,12 @@ class Args:
     pass
 
 
-def make_args(measure="MSELoss"):
+def make_args(profile="A"):
+    pr = PROFILES[profile]
     a = Args()
-    a.max_eval, a.lr, a.eps, a.measure, a.dataset = 100, -2.0, 0.0, measure, "cora"
+    a.max_eval, a.lr, a.eps, a.measure, a.dataset = 100, pr["lr"], 0.0, pr["measure"], "cora"
     a.useH_A = a.useY_A = a.useY = True
-    for k, w in enumerate(PROFILE_A, 1):
+    for k, w in enumerate(pr["w"], 1):
         setattr(a, f"w{k}", w)
     return a
 
@@ -190,14 +198,15 @@ def run_native(a):
     n = wl["n"]
     P = n * (n - 1) // 2
     prob = build_problem(wl, device, host_feature_adj=(world == 1))
-    args = make_args()
+    args = make_args(a.profile)
+    PROFILE_W = PROFILES[a.profile]["w"]
     K, Wm = a.steps, a.warmup
 
     # ------------------------------------------------------------------ device-resident steps (`value`)
     atk, adj = make_attack(prob, device)
-    num_edges = int(0.5 * 1e7 * (2 * prob["nedges"]) / n ** 2 * n ** 2)          # main.py:247-248, --density 1e7
+    num_edges = int(0.5 * a.density * (2 * prob["nedges"]) / n ** 2 * n ** 2)    # main.py:247-248 (--density, default 1e7)
     # epochs=0: builds the engine (constants, tiled feature_adj) without iterating; then we drive iterate() here
-    atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_A, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
+    atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_W, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
                prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=0,
                _engine_epochs=K + Wm + 8, _skip_finalize=True)
     eng = atk.engine
@@ -210,7 +219,7 @@ def run_native(a):
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
     th.start()
     N.TIMERS['on'] = {}
-    l0 = N.LAUNCHES["count"]
+    l0 = N.LAUNCHES["kernels"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
@@ -218,7 +227,7 @@ def run_native(a):
         eng.iterate()
     ev1.record()
     torch.cuda.synchronize()
-    launches = N.LAUNCHES["count"] - l0
+    launches = N.LAUNCHES["kernels"] - l0      # hand-written kernels launched inside the timed region
     stop.set()
     th.join()
     ms = ev0.elapsed_time(ev1)
@@ -239,7 +248,7 @@ def run_native(a):
         atk, adj = make_attack(prob, device)
         labels_pos = prob["edges"]
         # one warm call at 1 epoch so allocator / lazy init are not in the timed region
-        atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_A, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
+        atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_W, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
                    prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=1)
         metrics.auc_ap_from_edges(atk.modified_adj, labels_pos)
         atk.adj_changes.data.zero_()
@@ -247,7 +256,7 @@ def run_native(a):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_A, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
+        atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_W, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
                    prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=K)
         loss_hist = atk.engine.losses()["loss"]            # D2H of the per-iteration loss history
         auc, ap = metrics.auc_ap_from_edges(atk.modified_adj, labels_pos)     # D2H of two scalars
@@ -286,7 +295,7 @@ def run_native(a):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if world == 1 and os.path.exists(tp):
-            traffic = json.load(open(tp)).get(wl["name"], {}).get("k_propagate_h<32>")
+            traffic = json.load(open(tp)).get(a.workload, {}).get("k_propagate_h<32>")
         roof = {"bound": "hbm", "kernel": "k_propagate_h<32> (Y += M*B over the tiled triangle; both products on tcgen05 "
                                           "kind::f16 from one fp16x2 image per tile, fp32 accumulators in TMEM)",
                 "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
@@ -297,8 +306,8 @@ def run_native(a):
     out = {"metric": "PGD attack iterations/s (fwd+bwd+prior losses+Adam+projection)", "value": K / (ms * 1e-3),
            "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": wl["name"], "n": n, "flags": "Profile A: README Cora MSELoss w1=.01 w6=10 w7=10 w9=10 "
-                      "w10=1000 lr=1e-2, density 1e7", "l2": "inputs larger than L2 (tiled x/m/v/F >> 126 MB)"
+           "config": {"workload": wl["name"], "n": n, "flags": PROFILES[a.profile]["flags"] + f", density {a.density:g}"
+                      + (" (budget binds: bisection every iteration)" if num_edges < P else ""), "l2": "inputs larger than L2 (tiled x/m/v/F >> 126 MB)"
                       if 4 * P > 4e8 else "flush: none (working set fits L2 at this size)",
                       "sharding": f"tile-row shards x{world}" if world > 1 else "single GPU"},
            "roofline": roof, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
@@ -384,6 +393,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="large", choices=list(WORKLOADS))
+    ap.add_argument("--profile", default="A", choices=list(PROFILES), help="flag profile of SURVEY 8(d)")
+    ap.add_argument("--density", type=float, default=1e7, help="main.py --density (1e7: budget never binds; 1: it does)")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     a = ap.parse_args()

@@ -159,7 +159,13 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-LAUNCHES = {"count": 0}
+LAUNCHES = {"count": 0, "kernels": 0}
+# hand-written kernels launched per C entry with the default engines (everything else launches exactly one):
+# propagate = k_colmax + k_prep_b16 + k_propagate_h; fold_adam = k_prep_w + k_fold_tc; auc_ap = compact + 4 x (hist, scan,
+# scatter) + rank + finish; argsort_desc = make_keys + 4 x 3
+KERNELS_PER_CALL = {"mcgra_propagate": 3, "mcgra_fold_adam": 2, "mcgra_auc_ap": 15, "mcgra_argsort_desc": 13,
+                    "mcgra_version": 0, "mcgra_set_engine": 0, "mcgra_tiles_in_rows": 0, "mcgra_propagate_ws_bytes": 0,
+                    "mcgra_fold_ws_bytes": 0, "mcgra_auc_workspace_bytes": 0, "mcgra_sort_workspace_bytes": 0}
 
 
 TIMERS = {"on": None}     # when a dict: name -> list of (start, end) CUDA events around each call
@@ -168,6 +174,7 @@ TIMERS = {"on": None}     # when a dict: name -> list of (start, end) CUDA event
 def call(name, *args, tag=None):
     """Call a C-ABI entry point, check its return code, count the launch (bench.py's gpu_launches)."""
     LAUNCHES["count"] += 1
+    LAUNCHES["kernels"] += KERNELS_PER_CALL.get(name, 1)
     tm = TIMERS["on"]
     if tm is not None:
         import torch

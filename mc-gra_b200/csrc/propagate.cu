@@ -1404,8 +1404,13 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
       if (rows_ok && J < I) {
 #pragma unroll
         for (int it = 0; it < 16; ++it) h_convert_store(cur[it].x, cur[it].y, cur[it].z, cur[it].w, pl0 + it * 128, pl1 + it * 128);
-      } else {                                 // diagonal / last tile row / lazily projected parameter: mask + view
-        const bool interior = (J < I) && (i0 + TILE <= n);
+      } else if ((J < I) && (i0 + TILE <= n)) {   // interior tile of a lazily projected / raw parameter: apply the view
+#pragma unroll
+        for (int it = 0; it < 16; ++it)
+          h_convert_store(pv.adj(cur[it].x), pv.adj(cur[it].y), pv.adj(cur[it].z), pv.adj(cur[it].w), pl0 + it * 128,
+                          pl1 + it * 128);
+      } else {                                 // diagonal / last tile row: validity mask + view
+        const bool interior = false;
         const int gj = (int)(j0 + lane * 4);
 #pragma unroll 1
         for (int it = 0; it < 16; ++it) {
