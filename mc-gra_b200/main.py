@@ -97,6 +97,10 @@ def main(argv=None):
     device = torch.device("cuda:0")
     np.random.seed(args.seed); random.seed(args.seed); torch.manual_seed(args.seed); torch.cuda.manual_seed(args.seed)
     adj_sp, feats, labels = load_graph(args.dataset)
+    if args.dataset.startswith("synthetic"):
+        # the reference's dataset-keyed tables (feature similarity main.py:44-55, dot_product_decode2
+        # topology_attack.py:421-467) have no synthetic entry: synthetic graphs use the Cora branches
+        args.dataset = "cora"
     n = adj_sp.shape[0]
     rng = np.random.RandomState(args.seed)
     perm = rng.permutation(n)
