@@ -27,6 +27,29 @@ __device__ __forceinline__ void tile_coords(int64_t t, int& I, int& J) {
   J = (int)(t - tri((int64_t)i));
 }
 
+// b-th CTA of a shard of tile rows [tr0, tr1) -> tile (I, J) in an L2-friendly order: blocks of R tile rows are swept
+// column by column, so the per-column operand block is re-used by R consecutive CTAs and the R per-row blocks stay
+// resident for the whole sweep.  tix = storage index of the tile inside the shard (row-major triangle order).
+__device__ __forceinline__ void tile_coords_blocked(int64_t b, int tr0, int tr1, int R, int& I, int& J, int64_t& tix) {
+  int Ib, Jb;
+  tile_coords(tri((int64_t)tr0) + b, Ib, Jb);
+  const int I0 = tr0 + ((Ib - tr0) / R) * R;
+  const int I1 = min(I0 + R, tr1);
+  const int rows = I1 - I0;
+  int64_t rb = b - (tri((int64_t)I0) - tri((int64_t)tr0));
+  const int64_t full = (int64_t)(I0 + 1) * rows;        // columns 0..I0 hold all `rows` tiles
+  if (rb < full) {
+    J = (int)(rb / rows);
+    I = I0 + (int)(rb % rows);
+  } else {
+    rb -= full;
+    J = I0 + 1;
+    while (rb >= I1 - J) { rb -= I1 - J; ++J; }         // triangular tail: column J holds rows J..I1-1
+    I = J + (int)rb;
+  }
+  tix = tri((int64_t)I) + J - tri((int64_t)tr0);
+}
+
 // parameter view: value of the optimised parameter stored lazily as x' and mu (see mcgra.h)
 // raw = 0: lazy projection (buffer = un-projected Adam output x', parameter = clamp(x' - mu, 0, 1))
 // raw = 1: user-provided raw parameter (forward uses clamp(x, 0, 1) with the clamp's gradient mask)

@@ -550,12 +550,13 @@ __global__ void k_prep_w(const float* __restrict__ Wt, int64_t npad, unsigned ch
 }
 
 __global__ void __launch_bounds__(256, 2)
-k_fold_tc(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int64_t t0, const float* mu,
+k_fold_tc(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int tr0, int tr1, const float* mu,
           int raw, mcgra_fold_args fa, float* __restrict__ minmax, const unsigned char* __restrict__ Wk) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   FoldTcSmem& sm = *reinterpret_cast<FoldTcSmem*>(smem_raw);
   int I, J;
-  tile_coords(t0 + blockIdx.x, I, J);
+  int64_t tix;
+  tile_coords_blocked(blockIdx.x, tr0, tr1, 8, I, J, tix);      // L2-friendly sweep: factor blocks are re-read from L2, not HBM
   const ParamView pv = load_view(mu, raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
@@ -666,15 +667,15 @@ k_fold_tc(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
   const bool fastview = (pv.raw == 2) && interior && fa.k2 == 0.f && fa.measure != MCGRA_M_KL;
   if (fastview) {
     if (fa.measure == MCGRA_M_MSE) {
-      if (fa.k6 != 0.f) fold_stream<true, MCGRA_M_MSE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
-      else fold_stream<true, MCGRA_M_MSE, false>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+      if (fa.k6 != 0.f) fold_stream<true, MCGRA_M_MSE, true>(sm, fa, pv, ec, tix, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+      else fold_stream<true, MCGRA_M_MSE, false>(sm, fa, pv, ec, tix, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
     } else if (fa.measure == MCGRA_M_PRE) {
-      fold_stream<true, MCGRA_M_PRE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+      fold_stream<true, MCGRA_M_PRE, true>(sm, fa, pv, ec, tix, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
     } else {
-      fold_stream<true, MCGRA_M_NONE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+      fold_stream<true, MCGRA_M_NONE, true>(sm, fa, pv, ec, tix, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
     }
   } else {
-    fold_stream<false, -1, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
+    fold_stream<false, -1, true>(sm, fa, pv, ec, tix, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
   }
   const int b0 = lane * 4;
 #pragma unroll
@@ -846,7 +847,7 @@ int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const fl
     const size_t smem3 = sizeof(FoldTcSmem) + 1024;
     cudaError_t e3 = cudaFuncSetAttribute(k_fold_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
     if (e3 != cudaSuccess) return (int)e3;
-    k_fold_tc<<<(unsigned)nt, 256, smem3, (cudaStream_t)stream>>>(tiles, m, v, tri(tr0), mu, raw, *a, minmax,
+    k_fold_tc<<<(unsigned)nt, 256, smem3, (cudaStream_t)stream>>>(tiles, m, v, tr0, tr1, mu, raw, *a, minmax,
                                                                   (const unsigned char*)a->Wk);
     MCGRA_LAUNCH_CHECK();
     return 0;
