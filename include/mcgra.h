@@ -194,6 +194,8 @@ typedef struct {
   float* d_next;          /* [n] += row/col sums of clamp(x',0,1) (caller pre-fills with 1)           */
   int store_clamped;      /* != 0: the budget cannot bind -> store clamp(x',0,1) (readers then use raw = 2)   */
   void* Wk;               /* scratch of mcgra_fold_ws_bytes(n) bytes for the tcgen05 engine (NULL: mma.sync)   */
+  const int* step_ptr;    /* optional: device counter of completed iterations; Adam step = *step_ptr + 1 (overrides
+                             `step`) so that the launch carries no per-iteration host scalar (CUDA-graph replay) */
 } mcgra_fold_args;
 int64_t mcgra_fold_ws_bytes(int64_t n);
 /* minmax: device float[2] = {min x', max x'} (bisection bracket, :340-341); reset by mcgra_node_rho          */
@@ -213,6 +215,11 @@ int mcgra_bisect_update(double budget, float epsilon, float* state, double* cand
  * reset != 0 first discards the fold's mu = 0 statistics (d_next = 1, SUMSQ = 0).                   */
 int mcgra_bisect_finish(const float* tiles, int64_t n, int tr0, int tr1, const float* state,
                         const float* mu, double* acc_next, float* d_next, int reset, void* stream);
+
+/* hist[*step][0:MCGRA_ACC_N] = row; (*step)++  -- one tiny launch at the end of an iteration: the accumulator rows can
+ * then be a fixed ring of two and the Adam step a device counter, which makes the whole iteration replayable as a CUDA
+ * graph (the launch-bound regime of small graphs).  No-op beyond max_rows.                                        */
+int mcgra_history_push(const double* row, double* hist, int64_t max_rows, int* step, void* stream);
 
 /* ---- finalisation (topology_attack.py:300-322) ---- */
 /* x_final tiles = relu(zf_i . zf_j) for j<i (dot_product_decode of the last embedding)              */

@@ -49,7 +49,7 @@ class FoldArgs(C.Structure):
                 ("lseA", c_fp), ("lseF", c_fp), ("zhat", c_fp), ("measure", C.c_int),
                 ("k1", C.c_float), ("k6", C.c_float), ("k2", C.c_float), ("norm_coef", C.c_float),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
-                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int), ("Wk", c_fp)]
+                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int), ("Wk", c_fp), ("step_ptr", c_fp)]
 
 
 ENSEMBLE_MAX = 8
@@ -98,6 +98,7 @@ _SIGS = {
     "mcgra_gram_accumulate": (C.c_int, [c_fp, C.c_int, i64, C.c_int, c_fp, c_fp, i64, i64, i64, c_fp]),
     "mcgra_label_accumulate": (C.c_int, [c_fp, i64, c_fp, i64, i64, i64, c_fp]),
     "mcgra_dense_add": (C.c_int, [c_fp, c_fp, i64, c_fp]),
+    "mcgra_history_push": (C.c_int, [c_fp, c_fp, i64, c_fp, c_fp]),
     "mcgra_ensemble": (C.c_int, [c_fp, i64, C.POINTER(EnsembleArgs), c_fp, i64, i64, i64, c_fp]),
     "mcgra_row_normalize": (C.c_int, [c_fp, i64, C.c_int, C.c_float, c_fp, c_fp]),
     "mcgra_gauss_stats": (C.c_int, [c_fp, C.c_int, c_fp, C.c_int, i64, C.c_float, C.c_float, c_fp, c_fp, c_fp, c_fp]),

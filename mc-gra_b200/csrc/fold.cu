@@ -101,8 +101,9 @@ k_fold_adam(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restri
   // ---- streaming epilogue: element-wise terms, Adam, clamp statistics ------------------------------------
   const double sumsq_prev = fa.acc_prev[MCGRA_ACC_SUMSQ];
   const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
-  const double bc1 = 1.0 - pow((double)fa.beta1, (double)fa.step);
-  const double bc2 = 1.0 - pow((double)fa.beta2, (double)fa.step);
+  const int adam_step = fa.step_ptr != nullptr ? (*fa.step_ptr + 1) : fa.step;
+  const double bc1 = 1.0 - pow((double)fa.beta1, (double)adam_step);
+  const double bc2 = 1.0 - pow((double)fa.beta2, (double)adam_step);
   const float step_size = (float)((double)fa.lr / bc1);
   const float sqrt_bc2 = (float)sqrt(bc2);
   const float omb1 = 1.f - fa.beta1, omb2 = 1.f - fa.beta2;
@@ -463,8 +464,9 @@ k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restric
   // ---- streaming epilogue ----
   const double sumsq_prev = fa.acc_prev[MCGRA_ACC_SUMSQ];
   const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
-  const double bc1 = 1.0 - pow((double)fa.beta1, (double)fa.step);
-  const double bc2 = 1.0 - pow((double)fa.beta2, (double)fa.step);
+  const int adam_step = fa.step_ptr != nullptr ? (*fa.step_ptr + 1) : fa.step;
+  const double bc1 = 1.0 - pow((double)fa.beta1, (double)adam_step);
+  const double bc2 = 1.0 - pow((double)fa.beta2, (double)adam_step);
   EpiConst ec;
   ec.step_size = (float)((double)fa.lr / bc1);
   ec.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
@@ -653,8 +655,9 @@ k_fold_tc(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
   // ---- streaming epilogue (shared with the mma.sync engine) ----
   const double sumsq_prev = fa.acc_prev[MCGRA_ACC_SUMSQ];
   const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
-  const double bc1 = 1.0 - pow((double)fa.beta1, (double)fa.step);
-  const double bc2 = 1.0 - pow((double)fa.beta2, (double)fa.step);
+  const int adam_step = fa.step_ptr != nullptr ? (*fa.step_ptr + 1) : fa.step;
+  const double bc1 = 1.0 - pow((double)fa.beta1, (double)adam_step);
+  const double bc2 = 1.0 - pow((double)fa.beta2, (double)adam_step);
   EpiConst ec;
   ec.step_size = (float)((double)fa.lr / bc1);
   ec.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));

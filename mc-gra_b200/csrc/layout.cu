@@ -5,6 +5,13 @@
 
 namespace {
 
+__global__ void k_history_push(const double* __restrict__ row, double* __restrict__ hist, int64_t max_rows, int* step) {
+  const int s = *step;
+  if (s < max_rows && threadIdx.x < MCGRA_ACC_N) hist[(int64_t)s * MCGRA_ACC_N + threadIdx.x] = row[threadIdx.x];
+  __syncwarp();
+  if (threadIdx.x == 0) *step = s + 1;
+}
+
 // one CTA per tile, 256 threads, each thread handles float4 groups of a tile row
 __global__ void k_tril_to_tiles(const float* __restrict__ packed, int64_t n, int64_t t0, float* __restrict__ tiles) {
   int I, J;
@@ -96,6 +103,12 @@ __global__ void k_tiles_to_dense(const float* __restrict__ tiles, int64_t n, int
 extern "C" {
 
 int mcgra_version(void) { return 1; }
+
+int mcgra_history_push(const double* row, double* hist, int64_t max_rows, int* step, void* stream) {
+  k_history_push<<<1, 32, 0, (cudaStream_t)stream>>>(row, hist, max_rows, step);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
 
 int64_t mcgra_tiles_in_rows(int tr0, int tr1) { return tri(tr1) - tri(tr0); }
 

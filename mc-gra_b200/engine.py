@@ -14,6 +14,7 @@ PyTorch is used for device memory, streams and the collective only.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -24,6 +25,10 @@ HID = N.HID
 TILE = N.TILE
 MEASURES = {"MSELoss": N.M_MSE, "KL": N.M_KL, "HSIC": N.M_HSIC, "CKA": N.M_CKA, "DP": N.M_DP}
 ALIGN = {"c1": 100, "c2": 1000, "c6": 10, "c7": 10, "c9": 1, "c10": 1}      # MC-GRA/utils.py:1100-1111
+
+
+# largest n for which the iteration is replayed as a CUDA graph (0 disables); env override for A/B runs
+GRAPH_MAX_N = int(os.environ.get("MCGRA_GRAPH_MAX_N", "8192"))
 
 
 def tri(i):
@@ -151,6 +156,15 @@ class PGDEngine:
         self.step = 0
         self.max_epochs = max_epochs
         self.acc_hist = torch.zeros(max_epochs + 2, N.ACC_N, dtype=torch.float64, device=dev)
+        # Ring mode (small graphs, launch-bound): the accumulator rows are a fixed ring of two, the Adam step is a device
+        # counter and a tiny kernel appends the finished row to acc_hist, so that no launch carries a per-iteration host
+        # scalar and two consecutive iterations can be replayed as ONE CUDA graph (run()).  Large graphs keep the direct
+        # history rows: launch overhead is < 1 % there and per-kernel CUDA-event timing stays possible.
+        self.ring_mode = (GRAPH_MAX_N > 0 and n <= GRAPH_MAX_N and world == 1 and self.nn_mode in ("native", "off")
+                          and self.measure == N.M_MSE)
+        self.acc_ring = torch.zeros(2, N.ACC_N, dtype=torch.float64, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._graph = None
         self.minmax = torch.zeros(2, **f32)
         self.bstate = torch.zeros(8, **f32)
         self.cand = torch.zeros(8, dtype=torch.float64, device=dev)
@@ -193,6 +207,8 @@ class PGDEngine:
         self.mu.zero_()
         self.step = 0
         self.acc_hist.zero_()
+        self.acc_ring.zero_()
+        self.step_dev.zero_()
         if x_packed is None:
             self.xt.zero_()
             self.raw = 0
@@ -203,10 +219,14 @@ class PGDEngine:
             call("mcgra_tril_to_tiles", ptr(xp), self.n, self.tr0, self.tr1, ptr(self.xt), st)
             self.raw = 1
             sumsq = float((xp.double() ** 2).sum())
-        self.acc_hist[0, ACC["SUMSQ"]] = sumsq
+        self._acc_row(0)[ACC["SUMSQ"]] = sumsq
         self.d.fill_(1.0 if self.rank == 0 else 0.0)
         call("mcgra_degree", ptr(self.xt), self.n, self.tr0, self.tr1, ptr(self.mu), self.raw, ptr(self.d), st)
         self._allreduce(self.d)
+
+    def _acc_row(self, t):
+        """Accumulator row of iteration t (tensor view): a history row, or one of the two ring rows."""
+        return self.acc_ring[t & 1] if self.ring_mode else self.acc_hist[t]
 
     def _node_args(self, t):
         a = N.NodeArgs()
@@ -221,7 +241,7 @@ class PGDEngine:
         a.inv_norm, a.masks, a.masks2 = ptr(self.inv_norm), ptr(self.masks), ptr(self.masks2)
         a.eps_row, a.rho, a.Wt = ptr(self.eps_row), ptr(self.rho), ptr(self.Wt)
         a.Fdiag = ptr(self.Fdiag)
-        a.acc = self.acc_hist[t].data_ptr()
+        a.acc = self._acc_row(t).data_ptr()
         a.measure = self.measure                      # n x d terms c9 / c10 (node kernel handles MSE / KL)
         a.measure_nn = self.meas_nn                   # n x n terms: diagonal part in node_rho
         a.weight_sup = self.weight_sup
@@ -230,7 +250,7 @@ class PGDEngine:
         a.w9, a.w10 = (self.w9, self.w10) if self.nd_native else (0.0, 0.0)
         a.npad = self.npad
         a.d_next, a.d_fill = ptr(self.d_next), (1.0 if self.rank == 0 else 0.0)
-        a.acc_next = self.acc_hist[t + 1].data_ptr()
+        a.acc_next = self._acc_row(t + 1).data_ptr()
         a.minmax = ptr(self.minmax)
         a.lseA, a.lseF = ptr(self.lseA), ptr(self.lseF)
         a.em = ptr(self.em)
@@ -258,7 +278,7 @@ class PGDEngine:
             e.r, e.Ftiles, e.lseA, e.lseF = ptr(self.r), (ptr(self.Ft) if c1_native else None), ptr(self.lseA), ptr(self.lseF)
             e.measure = self.meas_nn if c1_native else N.M_NONE
             e.k1, e.k6 = (self.k1 if c1_native else 0.0), self.k6
-            e.acc, e.eps_row = self.acc_hist[t].data_ptr(), ptr(self.eps_row)
+            e.acc, e.eps_row = self._acc_row(t).data_ptr(), ptr(self.eps_row)
             e.dlse = ptr(self.dlse)
             ea = C.byref(e)
         if ea is not None and self.split_elem:
@@ -291,7 +311,7 @@ class PGDEngine:
         if self.k7 != 0.0 or self.k2 != 0.0 or dense:
             call("mcgra_pairs", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.zhat), ptr(self.r),
                  self.k7, self.k2, (ptr(self.Ft) if dense else None), (ptr(self.Ct) if dense else None),
-                 ptr(self.dzhat), ptr(self.eps_row), self.acc_hist[t].data_ptr(), st)
+                 ptr(self.dzhat), ptr(self.eps_row), self._acc_row(t).data_ptr(), st)
             self._allreduce(self.dzhat)
         call("mcgra_node_bwd2", ap, st)
         call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, ptr(self.prop_ws), st, tag="propagate32")
@@ -314,8 +334,9 @@ class PGDEngine:
         f.norm_coef = self.weight_sup * 0.001
         f.lr, f.beta1, f.beta2, f.adam_eps = self.lr, 0.9, 0.999, 1e-8
         f.step = t + 1
-        f.acc_prev = self.acc_hist[t].data_ptr()
-        f.acc_next = self.acc_hist[t + 1].data_ptr()
+        f.acc_prev = self._acc_row(t).data_ptr()
+        f.acc_next = self._acc_row(t + 1).data_ptr()
+        f.step_ptr = ptr(self.step_dev) if self.ring_mode else None
         f.d_next = ptr(self.d_next)
         f.store_clamped = 0 if self.proj_possible else 1
         f.Wk = ptr(self.fold_ws)
@@ -326,20 +347,61 @@ class PGDEngine:
         self.mu.zero_()
         if self.world > 1:
             import torch.distributed as dist
-            self._allreduce(self.acc_hist[t + 1, :16])
+            self._allreduce(self._acc_row(t + 1)[:16])
             self._allreduce(self.minmax[0:1], dist.ReduceOp.MIN)
             self._allreduce(self.minmax[1:2], dist.ReduceOp.MAX)
         if self.proj_possible:
             self._project(t)
         self._allreduce(self.d_next)
         self.d, self.d_next = self.d_next, self.d
+        if self.ring_mode:       # hist[step_dev] = finished row; step_dev += 1
+            call("mcgra_history_push", self._acc_row(t).data_ptr(), ptr(self.acc_hist), self.acc_hist.shape[0],
+                 ptr(self.step_dev), st)
         self.step = t + 1
+
+    def run(self, epochs, on_iter=None, use_graph="auto"):
+        """`epochs` iterations.  In ring mode (small graphs) two consecutive iterations are captured once as a CUDA graph
+        and replayed: the loop is launch-bound there (~40 launches of a few microseconds each per iteration).  Capture costs
+        about as much as 100 iterations save at the Cora shape (0.60 vs 0.72 ms per iteration), so "auto" only does it for
+        long runs or when the engine already holds a captured graph; True forces it (tests, bench)."""
+        k = int(epochs)
+        if use_graph == "auto":
+            use_graph = self._graph is not None or k >= 128
+        if on_iter is not None or not use_graph or not self.ring_mode or k < 8 or N.TIMERS["on"] is not None:
+            for _ in range(k):
+                self.iterate()
+                if on_iter is not None:
+                    on_iter()
+            return
+        # eager until the parameter view has settled (raw 1 -> 2 / 0, two iterations) and the step is even (the graph
+        # holds an even + an odd iteration: ring rows and the d / d_next ping-pong return to their roles)
+        while k > 0 and (self.step < 2 or (self.step & 1)):
+            self.iterate()
+            k -= 1
+        if self._graph is None and k >= 2:
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            l0, c0, step0 = N.LAUNCHES["kernels"], N.LAUNCHES["count"], self.step
+            with torch.cuda.graph(g, capture_error_mode="relaxed"):
+                self.iterate()
+                self.iterate()
+            self._graph_kernels = N.LAUNCHES["kernels"] - l0
+            N.LAUNCHES["kernels"], N.LAUNCHES["count"] = l0, c0      # capture records, it does not execute
+            self.step = step0
+            self._graph = g      # cached: later run() calls on this engine replay it without re-capturing
+        for _ in range(k // 2 if self._graph is not None else 0):
+            self._graph.replay()
+            self.step += 2
+            N.LAUNCHES["kernels"] += self._graph_kernels
+            k -= 2
+        for _ in range(k):
+            self.iterate()
 
     def _project(self, t):
         """projection + bisection (topology_attack.py:338-347, 397-412) without a host round trip."""
         st = N.stream_ptr()
         n, tr0, tr1 = self.n, self.tr0, self.tr1
-        acc_next = self.acc_hist[t + 1].data_ptr()
+        acc_next = self._acc_row(t + 1).data_ptr()
         self.cand.zero_()
         call("mcgra_bisect_init", acc_next, ptr(self.minmax), self.budget, ptr(self.bstate), ptr(self.mu), st)
         for _ in range(8):               # 8 passes x 3 halvings covers brackets up to 167 wide at eps = 1e-5
@@ -405,9 +467,9 @@ class PGDEngine:
                 loss = loss + sgn * c2v
             GA, GM = torch.autograd.grad(loss, [A_hat, M1], allow_unused=True)
         if c1v is not None:
-            self.acc_hist[t, ACC["C1D"]] += c1v.detach().double()
+            self._acc_row(t)[ACC["C1D"]] += c1v.detach().double()
         if c2v is not None:
-            self.acc_hist[t, ACC["C2D"]] += c2v.detach().double()
+            self._acc_row(t)[ACC["C2D"]] += c2v.detach().double()
         EA = (GA + GA.t()).contiguous()
         call("mcgra_dense_to_tiles", ptr(EA), n, n, self.tr0, self.tr1, 0, ptr(self.Ft), ptr(self.Fdiag), st)
         if self.world > 1:       # every rank wrote only the diagonal entries of its own tile rows
@@ -431,12 +493,12 @@ class PGDEngine:
             if self.w9 != 0.0:
                 c9 = self.w9 * calc(self.HA[idx], em[idx])
                 loss = loss + c9
-                self.acc_hist[t, ACC["C9"]] += c9.detach().double()
+                self._acc_row(t)[ACC["C9"]] += c9.detach().double()
             if self.w10 != 0.0:
                 p2 = torch.softmax(F.log_softmax(em @ self.Wl.t() + self.bl, dim=1), dim=1)
                 c10 = self.w10 * calc(self.YA[idx], p2[idx])
                 loss = loss + c10
-                self.acc_hist[t, ACC["C10"]] += c10.detach().double()
+                self._acc_row(t)[ACC["C10"]] += c10.detach().double()
             (g,) = torch.autograd.grad(loss, [em])
         self.demd.add_(g)
 

@@ -176,10 +176,9 @@ class PGDAttack(BaseAttack):
         _mark("engine_setup")
         self._trace = []
         self._timing = timing
-        for _ in range(int(epochs)):
-            eng.iterate()
-            if kwargs.get("_trace"):             # test hook: parameter after every iteration's projection
-                self._trace.append(eng.packed_parameter())
+        # test hook `_trace`: parameter after every iteration's projection; `_graph`: True / False force or forbid CUDA-graph replay (default: auto)
+        on_iter = (lambda: self._trace.append(eng.packed_parameter())) if kwargs.get("_trace") else None
+        eng.run(int(epochs), on_iter=on_iter, use_graph=kwargs.get("_graph", "auto"))
         if kwargs.get("_skip_finalize"):         # bench hook: engine is driven by the caller
             return 0, 0, 0, 0
         if int(epochs) == 0:

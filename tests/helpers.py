@@ -46,7 +46,7 @@ def make_args(d):
     return a
 
 
-def run_native_case(d, device="cuda:0", epochs=None, trace=True):
+def run_native_case(d, device="cuda:0", epochs=None, trace=True, graph=True):
     """Drive mcgra_b200.topology_attack.PGDAttack.attack exactly like main.objective does (main.py:298-307)."""
     from mcgra_b200.topology_attack import PGDAttack
     dev = torch.device(device)
@@ -68,7 +68,7 @@ def run_native_case(d, device="cuda:0", epochs=None, trace=True):
             model.attack(args, None, 10 ** float(d["lr_exp"]), 0, float(d["weight_sup"]), tuple(d["weights"]),
                          feature_adj, 0, 0, 0, None, None, np.arange(min(8, n)), adj, d["X"],
                          np.zeros((n, n), np.float32), d["labels"], d["idx_attack"], int(d["num_edges"]), 0,
-                         epochs=epochs, _trace=trace)
+                         epochs=epochs, _trace=trace, _graph=graph)
         finally:
             os.chdir(cwd)
     torch.cuda.synchronize()

@@ -142,3 +142,17 @@ def test_two_gpu_sharded_attack_matches_golden():
                           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "mgpu_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("case,epochs", [("mse_all_n150", 13), ("mse_budget_n150", 12)])
+def test_cuda_graph_replay_matches_eager(case, epochs):
+    """Small graphs replay two iterations per CUDA graph (engine.run: ring accumulator rows, device-side Adam step);
+    the trajectory must be the eager one (up to the order of the fp32 atomics)."""
+    d = np.load(os.path.join(GOLDEN, f"attack_{case}.npz"))
+    a = run_native_case(d, epochs=epochs, trace=False, graph=False)
+    b = run_native_case(d, epochs=epochs, trace=False, graph=True)
+    assert b["model"].engine.ring_mode and b["model"].engine._graph is not None and a["model"].engine._graph is None
+    assert len(a["loss"]) == epochs and len(b["loss"]) == epochs
+    np.testing.assert_allclose(b["loss"], a["loss"], rtol=2e-6)
+    assert np.max(np.abs(a["x_final"] - b["x_final"])) < 1e-5
+    np.testing.assert_allclose(b["modified_adj"], a["modified_adj"], rtol=1e-4, atol=1e-5)
