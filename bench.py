@@ -38,7 +38,7 @@ PROFILES = {"A": dict(w=PROFILE_A, measure="MSELoss", lr=-2.0,
             "B": dict(w=PROFILE_B, measure="HSIC", lr=-2.5,
                       flags="Profile B: README Polblogs HSIC w1=.01 w2=.01 w6=1e4 w7=100 w9=.001 w10=1000 lr=10^-2.5 "
                             "(n x n HSIC stage on library GEMMs, DESIGN.md 1)")}
-SAMPLE_N = 3072           # CPU baseline sample size (reference algorithm is O(n^3) per iteration)
+SAMPLE_N = int(os.environ.get("MCGRA_BENCH_SAMPLE_N", "3072"))   # CPU baseline sample size (the reference algorithm is O(n^3) per iteration)
 
 
 class Args:
