@@ -9,8 +9,10 @@
 //   g = mask * [ U_i.V_j + V_i.U_j  +  r_i r_j (e'_ij + e'_ji)  +  rho_i + rho_j ]  +  0.001 w_sup x / ||x||
 // with U = [r dZ1 | r dZ2 | dQ1 | dQ2], V = [r S1 | r S2 | S1 | T2] (rank-64 factors built by the node kernels),
 // e' the element-wise loss derivatives at A_hat_ij and rho the degree gradient.
-// One CTA per 128x128 tile: rank product as an fp32 register-tiled GEMM (K = 128), then a streaming epilogue
-// that reads x', m, v (and feature_adj) once and writes x', m, v once:  24 (+4) bytes per entry.
+// One CTA per 128x128 tile: rank-128 product (k_fold_adam: fp32 register-tiled FFMA; k_fold_mma: mma.sync 3xTF32;
+// k_fold_tc [default]: tcgen05 kind::tf32 with N = 256 [W_hi | W_lo] operands pre-formatted by k_prep_w, CTAs in an
+// L2-friendly blocked tile order), then a streaming epilogue that reads x', m, v (and feature_adj) once and writes
+// x', m, v once:  24 (+4) bytes per entry.
 #include "common.cuh"
 #include "tc_common.cuh"
 

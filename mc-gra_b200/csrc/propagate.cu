@@ -10,8 +10,15 @@
 // n x n matrices are never materialised: the D^-1/2 scaling lives in the B operand (prologue, node kernels) and in
 // the consumers of Y (epilogue, node kernels).
 //
-// v1 engine: fp32 FFMA with a 2 x K register tile per thread (exact fp32 accumulate).  HBM traffic = one read of
-// the tile shard (4 bytes per stored entry) + O(n K).
+// Engines (mcgra_set_engine(0, v)), all with HBM traffic = one read of the tile shard (4 bytes per stored
+// entry) + O(n K):
+//   v0 k_propagate        fp32 FFMA, 2 x K register tile per thread (exact fp32; the reference of the agreement tests)
+//   v1 k_propagate_mma    mma.sync m16n8k8 3xTF32, both products
+//   v2 k_propagate_tc     direct product on tcgen05 (SS operands, D in TMEM), mirrored product on mma.sync
+//   v4 k_propagate_tc2    both products on tcgen05 kind::tf32; T^T written to tensor memory (tcgen05.st), TS-mode MMAs
+//   v5 k_propagate_h      both products on tcgen05 kind::f16 from ONE fp16x2 image per tile (K-major for the direct,
+//                         MN-major for the mirrored product); DEFAULT
+// plus k_elem_stats (the element-wise terms as a stand-alone streaming pass), k_degree, k_row_sumexp.
 #include <cuda_fp16.h>
 #include <type_traits>
 
