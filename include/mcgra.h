@@ -65,7 +65,8 @@ int mcgra_version(void);
  * hybrid, 3: hybrid for the plain 32-wide passes only, 4: both products on tcgen05 kind::tf32 with the transposed
  * operand in tensor memory, 5: both products on tcgen05 kind::f16 from one fp16x2 image per tile [default]; values
  * >= 100 set developer timing bits and are not for production use); which 1 = fold (0 FFMA, 1 mma.sync, 2 tcgen05 [default]);
- * which 2 = pairs (0 FFMA, 1 mma.sync [default]).  Returns 0, or -1 for an unknown selector.          */
+ * which 2 = pairs (0 FFMA, 1 mma.sync [default]); which 3 = dense contraction mcgra_gemm_nt (1 = cta_group::1, 128 x 128
+ * tiles; 2 = cta_group::2 CTA pairs, 256 x 256 tiles [default]).  Returns 0, or -1 for an unknown selector.          */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */
 
@@ -274,6 +275,126 @@ int mcgra_pair_dense(const float* X, int d, int64_t m1, const float* Z, int64_t 
  * [sum w x (dx) | sum w y (dy) | sum w x y^T (dx*dy) | sum w y y^T (dy*dy)]; linear HSIC/CKA in O(n d d')     */
 int mcgra_cross_moments(const float* X, int dx, const float* Y, int dy, const float* w, int64_t n,
                         double* out, void* stream);
+
+/* ---- dense n x n contractions of the HSIC / CKA / DP measures on two n x n operands (K6) ----
+ * (CudaCKA.centering / linear_HSIC / linear_CKA, utils.py:1060-1091; PGDAttack.dot_product, topology_attack.py:480-481;
+ *  call sites topology_attack.py:190-229.)  The reference evaluates linear_HSIC(X, Y) with six n^3 GEMMs through dense
+ *  centring matrices; here every measure is a short sequence of mcgra_gemm_nt calls with closed-form gradients:
+ *     c1  HSIC(F, A) = sum (Kf A) o A,           Kf = H F F^T H  (constant),         d/dA = 2 Kf A
+ *     c2  HSIC(A, M) = || T ||_F^2,  T = A Hc M = A M - (A 1)(M 1 / n)^T,            d/dA = 2 (Hc M) T^T, d/dM = 2 (Hc A) T
+ *  (A, M symmetric; Hc = H for HSIC / CKA, I for DP; CKA adds the self terms S = A Hc A, d/dA = 4 Hc A S.)
+ *
+ * An IMAGE is the tensor-core operand form of an fp32 matrix: two fp16 planes hi = fp16(s_i x), lo = fp16(s_i x - hi)
+ * per row i with a power-of-two row scale s_i (max_j |s_i x_ij| <= 2^14), 4 bytes per element like fp32, ~2^-23 of the
+ * row maximum.  ld (in halves) must be a multiple of 8 and the planes 16-byte aligned (TMA).                         */
+typedef struct {
+  void* hi;                 /* fp16 [rows x ld]                                                        */
+  void* lo;                 /* fp16 [rows x ld]                                                        */
+  float* inv_scale;         /* [rows] 1 / s_i                                                          */
+  int64_t rows, cols, ld;
+} mcgra_image;
+
+typedef struct {
+  float* C;                 /* [M x ldc] fp32 output or NULL (reductions only)                         */
+  int64_t ldc;
+  float alpha, beta;        /* C = beta * C + alpha * (A B^T - coef * u_i v_j)                          */
+  const float* alpha_dev;   /* optional device scalars that multiply alpha / beta                      */
+  const float* beta_dev;
+  const float* u;           /* [M] or NULL (= 1); ignored when v is NULL                               */
+  const float* v;           /* [N] or NULL (no rank-1 correction)                                      */
+  float coef;
+  double* sumsq;            /* device: += sum (A B^T - coef u v^T)^2 over the computed rows, or NULL    */
+  double* dot;              /* device: += sum (A B^T - coef u v^T) o E, E = dot_with (M x N image)      */
+  const mcgra_image* dot_with;
+  int64_t row0, row1;       /* row panel [row0, row1) of C computed by this call (row1 <= row0: all)    */
+} mcgra_gemm_epilogue;
+
+/* C[M x N] = A[M x K] * B[N x K]^T on tcgen05 (kind::f16, three MMAs per K step, TMEM accumulators, TMA-fed,
+ * cta_group::2); M = A->rows, N = B->rows, K = A->cols = B->cols.                                                  */
+int mcgra_gemm_nt(const mcgra_image* A, const mcgra_image* B, const mcgra_gemm_epilogue* e, void* stream);
+
+/* image of a dense fp32 matrix src[rows x cols] (leading dimension ld); transpose != 0 builds the image of src^T
+ * (cols x rows).  ws: device scratch of max(rows, cols) uint32.                                                      */
+int mcgra_image_from_dense(const float* src, int64_t rows, int64_t cols, int64_t ld, int transpose,
+                           const mcgra_image* out, void* ws, void* stream);
+/* image of A_hat = D^-1/2 (M + I) D^-1/2 (utils.py:211-230) from the FULL tiled triangle (tile rows [0, T)) and
+ * r = d^-1/2; rowsum[i] (device double, zero on entry) += sum_j A_hat_ij.                                            */
+int mcgra_image_ahat(const float* tiles, int64_t n, const float* mu, int raw, const float* r, const mcgra_image* out,
+                     double* rowsum, void* stream);
+/* image of M1 = relu(zhat zhat^T) with zero diagonal (dot_product_decode + get_modified_adj_after, :381-395, 414-419);
+ * rowsum as above.                                                                                                   */
+int mcgra_image_m1(const float* zhat, int64_t n, const mcgra_image* out, double* rowsum, void* stream);
+/* X <- H X H (CudaCKA.centering, utils.py:1060-1065) in place on a dense symmetric fp32 matrix; ws: n doubles + 1     */
+int mcgra_center_dense(float* X, int64_t n, int64_t ld, double* ws, void* stream);
+/* out[j] += scale * sum_k w[k] X[k][j] (transpose == 0) or scale * sum_k X[j][k] w[k] (transpose != 0); X is
+ * rows x cols fp32; w, out device double (caller zero-fills out).                                                    */
+int mcgra_dense_gemv(const float* X, int64_t rows, int64_t cols, int64_t ld, const double* w, double scale,
+                     int transpose, double* out, void* stream);
+/* out[0] += sum X_ij^2 (device double)                                                                               */
+int mcgra_dense_sumsq(const float* X, int64_t rows, int64_t cols, int64_t ld, double* out, void* stream);
+/* tiles of (G_ij + G_ji) * scale (* *scale_dev) for the tile rows [tr0, tr1) and, when diag != NULL, diag[i] =
+ * G_ii * scale for ALL i (every rank holds the full G).                                                              */
+int mcgra_sym_to_tiles(const float* G, int64_t ld, int64_t n, int tr0, int tr1, float scale, const float* scale_dev,
+                       float* tiles, float* diag, void* stream);
+/* scalars of the dense measures: in = device double[8] {S1, hAM, hAA, hMM, hFF, -, -, -}; writes the loss values
+ * c1, c2 (fully scaled, sign NOT applied) to acc[MCGRA_ACC_C1D], acc[MCGRA_ACC_C2D] (+=) and the gradient scales
+ * alpha[8] (device float): {a1: G1 -> dL/dA, a2: (Hc M) T^T -> dL/dA, a3: (Hc A) S_A -> dL/dA, a4: (Hc A) T -> dL/dM,
+ * a5: (Hc M) S_M -> dL/dM}; sign = -1 for HSIC (topology_attack.py:215-229).                                           */
+int mcgra_dense_scalars(int measure, const double* in, double k1c, double k2c, double sign, double* acc, float* alpha,
+                        void* stream);
+/* out[i] = (float)(in[i] * scale)                                                                                    */
+int mcgra_d2f(const double* in, int64_t count, double scale, float* out, void* stream);
+
+/* ---- KL measure on two n x n operands (PGDAttack.calc_kl, topology_attack.py:483-487; c1 / c2 at :212-229) as
+ * three passes over the tiled triangle (csrc/kl2.cu); the gram M1 is regenerated per tile from zhat.  Row statistics
+ * (seA, seM, klrow, c1row: float [n], zero on entry of the pass that accumulates them) are all-reduced across ranks by
+ * the caller between passes.  Pass 2 writes the tiles EAt = dL/dA_ij + dL/dA_ji and Ct = dL/dM1_ij + dL/dM1_ji that
+ * mcgra_pairs / mcgra_fold_adam consume as MCGRA_M_PRE.                                                               */
+typedef struct {
+  const float* tiles;       /* x' shard (tile rows [tr0, tr1))                                          */
+  const float* mu;
+  int raw;
+  int tr0, tr1;
+  int64_t n;
+  const float* Ftiles;      /* tiled feature_adj (same shard) or NULL when c1 is off                    */
+  const float* Fdiag_feat;  /* [n] diagonal of feature_adj                                              */
+  const float* lseF;        /* [n] row log-sum-exp of feature_adj                                       */
+  const float* zhat;        /* [n x 16]                                                                 */
+  const float* r;           /* [n]                                                                      */
+  float *seA, *seM;         /* [n] pass 0 accumulators                                                  */
+  float *lseA, *lseM;       /* [n] written by node stage 0                                              */
+  float *klrow, *c1row;     /* [n] pass 1 accumulators                                                  */
+  float *EAt, *Ct;          /* pass 2 outputs (shard tiles)                                             */
+  double k1c, k2c;          /* fully scaled term weights (w1 * 1000 * 100, w2 * 100 * 1000); 0 = off    */
+} mcgra_kl2_args;
+int mcgra_kl2_pass(int pass, const mcgra_kl2_args* k, void* stream);
+/* stage 0: lseA / lseM from the exp sums; stage 1: KL_i, loss values into acc[C1D], acc[C2D], Fdiag = dL/dA_ii        */
+int mcgra_kl2_node(int stage, const mcgra_kl2_args* k, float* Fdiag, double* acc, void* stream);
+
+/* ---- the n x d prior terms c9 / c10 under HSIC / CKA / DP (topology_attack.py:237-272), forward and backward from
+ * weighted second moments in O(n d d') (csrc/ndmeasure.cu).  Adds the gradient w.r.t. the raw-branch embedding to
+ * demd and the signed term values to acc[MCGRA_ACC_C9], acc[MCGRA_ACC_C10].                                         */
+typedef struct {
+  int64_t n;
+  int nclass;
+  int measure;              /* MCGRA_M_HSIC / MCGRA_M_CKA / MCGRA_M_DP                                  */
+  const float* em;          /* [n x 16] embedding(X, M) (variable)                                      */
+  const float* HA;          /* [n x 16] target H_A                                                      */
+  const float* YA;          /* [n x c] target Y_A (log-probabilities)                                   */
+  const float* Wl;          /* [c x 16] linear head                                                     */
+  const float* bl;          /* [c]                                                                      */
+  const float* wmult;       /* [n] multiplicity of node i in idx_attack / |idx_attack|                  */
+  double m;                 /* |idx_attack|                                                             */
+  float w9, w10;            /* signed term weights; 0 = off                                             */
+  float* p2;                /* scratch [n x c]                                                          */
+  double* mom;              /* scratch, mcgra_nd_scratch_doubles(c) doubles                             */
+  float* coef;              /* scratch, mcgra_nd_scratch_floats(c) floats                               */
+  float* demd;              /* [n x 16] +=                                                              */
+  double* acc;
+} mcgra_nd_args;
+int64_t mcgra_nd_scratch_doubles(int nclass);
+int64_t mcgra_nd_scratch_floats(int nclass);
+int mcgra_nd_measure(const mcgra_nd_args* a, void* stream);
 
 /* ---- AUC / AP (main.metric_pool, main.py:66-75; gcn_parameterized.py:55-65) ----
  * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU,

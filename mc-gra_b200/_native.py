@@ -52,6 +52,30 @@ class FoldArgs(C.Structure):
                 ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int), ("Wk", c_fp), ("step_ptr", c_fp)]
 
 
+class Image(C.Structure):
+    """mcgra_image: fp16x2 operand image of an fp32 matrix (include/mcgra.h)."""
+    _fields_ = [("hi", c_fp), ("lo", c_fp), ("inv_scale", c_fp), ("rows", i64), ("cols", i64), ("ld", i64)]
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [("C", c_fp), ("ldc", i64), ("alpha", C.c_float), ("beta", C.c_float), ("alpha_dev", c_fp),
+                ("beta_dev", c_fp), ("u", c_fp), ("v", c_fp), ("coef", C.c_float), ("sumsq", c_fp), ("dot", c_fp),
+                ("dot_with", C.POINTER(Image)), ("row0", i64), ("row1", i64)]
+
+
+class Kl2Args(C.Structure):
+    _fields_ = [("tiles", c_fp), ("mu", c_fp), ("raw", C.c_int), ("tr0", C.c_int), ("tr1", C.c_int), ("n", i64),
+                ("Ftiles", c_fp), ("Fdiag_feat", c_fp), ("lseF", c_fp), ("zhat", c_fp), ("r", c_fp),
+                ("seA", c_fp), ("seM", c_fp), ("lseA", c_fp), ("lseM", c_fp), ("klrow", c_fp), ("c1row", c_fp),
+                ("EAt", c_fp), ("Ct", c_fp), ("k1c", C.c_double), ("k2c", C.c_double)]
+
+
+class NdArgs(C.Structure):
+    _fields_ = [("n", i64), ("nclass", C.c_int), ("measure", C.c_int), ("em", c_fp), ("HA", c_fp), ("YA", c_fp),
+                ("Wl", c_fp), ("bl", c_fp), ("wmult", c_fp), ("m", C.c_double), ("w9", C.c_float), ("w10", C.c_float),
+                ("p2", c_fp), ("mom", c_fp), ("coef", c_fp), ("demd", c_fp), ("acc", c_fp)]
+
+
 ENSEMBLE_MAX = 8
 TERM_GRAM, TERM_DENSE, TERM_LABEL = 0, 1, 2
 
@@ -104,6 +128,21 @@ _SIGS = {
     "mcgra_gauss_stats": (C.c_int, [c_fp, C.c_int, c_fp, C.c_int, i64, C.c_float, C.c_float, c_fp, c_fp, c_fp, c_fp]),
     "mcgra_pair_dense": (C.c_int, [c_fp, C.c_int, i64, c_fp, i64, C.c_int, C.c_float, c_fp, c_fp]),
     "mcgra_cross_moments": (C.c_int, [c_fp, C.c_int, c_fp, C.c_int, c_fp, i64, c_fp, c_fp]),
+    "mcgra_gemm_nt": (C.c_int, [C.POINTER(Image), C.POINTER(Image), C.POINTER(GemmEpilogue), c_fp]),
+    "mcgra_image_from_dense": (C.c_int, [c_fp, i64, i64, i64, C.c_int, C.POINTER(Image), c_fp, c_fp]),
+    "mcgra_image_ahat": (C.c_int, [c_fp, i64, c_fp, C.c_int, c_fp, C.POINTER(Image), c_fp, c_fp]),
+    "mcgra_image_m1": (C.c_int, [c_fp, i64, C.POINTER(Image), c_fp, c_fp]),
+    "mcgra_center_dense": (C.c_int, [c_fp, i64, i64, c_fp, c_fp]),
+    "mcgra_dense_gemv": (C.c_int, [c_fp, i64, i64, i64, c_fp, C.c_double, C.c_int, c_fp, c_fp]),
+    "mcgra_dense_sumsq": (C.c_int, [c_fp, i64, i64, i64, c_fp, c_fp]),
+    "mcgra_sym_to_tiles": (C.c_int, [c_fp, i64, i64, C.c_int, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp]),
+    "mcgra_dense_scalars": (C.c_int, [C.c_int, c_fp, C.c_double, C.c_double, C.c_double, c_fp, c_fp, c_fp]),
+    "mcgra_d2f": (C.c_int, [c_fp, i64, C.c_double, c_fp, c_fp]),
+    "mcgra_kl2_pass": (C.c_int, [C.c_int, C.POINTER(Kl2Args), c_fp]),
+    "mcgra_kl2_node": (C.c_int, [C.c_int, C.POINTER(Kl2Args), c_fp, c_fp, c_fp]),
+    "mcgra_nd_scratch_doubles": (i64, [C.c_int]),
+    "mcgra_nd_scratch_floats": (i64, [C.c_int]),
+    "mcgra_nd_measure": (C.c_int, [C.POINTER(NdArgs), c_fp]),
     "mcgra_auc_workspace_bytes": (i64, [i64, i64]),
     "mcgra_auc_ap": (C.c_int, [c_fp, c_fp, i64, i64, c_fp, c_fp, c_fp]),
     "mcgra_sort_workspace_bytes": (i64, [i64]),
@@ -166,7 +205,9 @@ LAUNCHES = {"count": 0, "kernels": 0}
 # scatter) + rank + finish; argsort_desc = make_keys + 4 x 3
 KERNELS_PER_CALL = {"mcgra_propagate": 3, "mcgra_fold_adam": 2, "mcgra_auc_ap": 15, "mcgra_argsort_desc": 13,
                     "mcgra_version": 0, "mcgra_set_engine": 0, "mcgra_tiles_in_rows": 0, "mcgra_propagate_ws_bytes": 0,
-                    "mcgra_fold_ws_bytes": 0, "mcgra_auc_workspace_bytes": 0, "mcgra_sort_workspace_bytes": 0}
+                    "mcgra_fold_ws_bytes": 0, "mcgra_auc_workspace_bytes": 0, "mcgra_sort_workspace_bytes": 0,
+                    "mcgra_nd_scratch_doubles": 0, "mcgra_nd_scratch_floats": 0, "mcgra_nd_measure": 5,
+                    "mcgra_image_from_dense": 2, "mcgra_center_dense": 2, "mcgra_sym_to_tiles": 2}
 
 
 TIMERS = {"on": None}     # when a dict: name -> list of (start, end) CUDA events around each call

@@ -779,7 +779,8 @@ __global__ void k_bisect_update(double budget, float epsilon, float* state, doub
     }
     if (!done && !((b - a) >= epsilon)) done = true;
     state[0] = a; state[1] = b; state[2] = miu;
-    if (done) { state[3] = 1.f; *mu = miu; }
+    *mu = miu;               // always the last visited midpoint: an unfinished search still projects (never mu = 0)
+    if (done) state[3] = 1.f;
   }
   for (int q = 0; q < 7; ++q) cand_sums[q] = 0.0;
 }

@@ -1654,7 +1654,9 @@ extern "C" {
 
 int mcgra_set_fold_engine_(int value);
 int mcgra_set_pairs_engine_(int value);
+int mcgra_set_gemm_engine_(int value);
 int mcgra_set_engine(int which, int value) {
+  if (which == 3) return mcgra_set_gemm_engine_(value);
   if (which == 0 && value >= 100) { g_prop_dbg = value - 100; return 0; }
   if (which == 0) { g_prop_engine = value; return 0; }
   if (which == 1) return mcgra_set_fold_engine_(value);

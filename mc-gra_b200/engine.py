@@ -28,6 +28,7 @@ ALIGN = {"c1": 100, "c2": 1000, "c6": 10, "c7": 10, "c9": 1, "c10": 1}      # MC
 
 
 # largest n for which the iteration is replayed as a CUDA graph (0 disables); env override for A/B runs
+BISECT_PASSES = 10
 GRAPH_MAX_N = int(os.environ.get("MCGRA_GRAPH_MAX_N", "8192"))
 
 
@@ -92,15 +93,10 @@ class PGDEngine:
         nn2 = float(n) * float(n)
         sgn = -1.0 if measure == "HSIC" else 1.0
         self.c1_active = False
-        self.Ft = self.Fdiag = self.lseF = self.Ct = self.F_dense = None
+        self.Ft = self.Fdiag = self.lseF = self.Ct = None
         self.k1 = self.k2 = 0.0
         self.meas_nn = N.M_NONE       # measure code used by the element-wise n x n kernels
         self.idx = idx
-        # Which engine evaluates the n x n terms c1 / c2:
-        #   "native": fused element-wise kernels (MSELoss; KL when only c1 is on)
-        #   "dense" : HSIC / CKA / DP (n^3 contractions) and KL's c2 -- evaluated upstream on dense n x n tensors with
-        #             library GEMMs + autograd (stop-gap for the tcgen05 contraction K6) and handed to the
-        #             native kernels as pre-computed gradient tiles (MCGRA_M_PRE)
         fa = None
         if w1 != 0 and feature_adj is not None:
             fa = feature_adj.to(dev)
@@ -109,13 +105,21 @@ class PGDEngine:
                 self.c1_active = True
                 fa = fa.to(torch.float32).contiguous()
         native_nn = (self.measure == N.M_MSE) or (self.measure == N.M_KL and w2 == 0)
-        self.nn_mode = "native" if native_nn else "dense"
+        # Which engine evaluates the n x n terms c1 / c2:
+        #   "native": fused element-wise kernels (MSELoss; KL when only c1 is on)
+        #   "kl2"   : KL with c2 on -- row-softmax statistics of A_hat AND of the decode gram M1: three tile passes
+        #             (csrc/kl2.cu) that hand the element-wise gradient tiles to the pipeline (MCGRA_M_PRE)
+        #   "dense" : HSIC / CKA / DP -- n^3 contractions on tcgen05 (dense_measure.DenseMeasure, csrc/gemm.cu), gradient
+        #             tiles handed over the same way
+        self.nn_mode = "native" if native_nn else ("kl2" if self.measure == N.M_KL else "dense")
         if not (self.c1_active or w2 != 0):
             self.nn_mode = "off"
         self.w1, self.w2 = w1, w2
+        self.dense = None
+        ntl = max(self.ntiles, 1) * TILE * TILE
         if self.nn_mode == "native":
             if self.c1_active:
-                self.Ft = torch.zeros(max(self.ntiles, 1) * TILE * TILE, **f32)
+                self.Ft = torch.zeros(ntl, **f32)
                 self.Fdiag = torch.zeros(n, **f32)
                 call("mcgra_dense_to_tiles", ptr(fa), n, n, self.tr0, self.tr1, 1, ptr(self.Ft), ptr(self.Fdiag),
                      N.stream_ptr())
@@ -130,13 +134,35 @@ class PGDEngine:
                     self.lseF = self.lseF64.float().contiguous()
             if w2 != 0:
                 self.k2 = w2 * 100 * ALIGN["c2"] / nn2
-        elif self.nn_mode == "dense":
-            self.F_dense = fa if self.c1_active else None
-            self.Ft = torch.zeros(max(self.ntiles, 1) * TILE * TILE, **f32)      # dL/dA_ij + dL/dA_ji
-            self.Ct = torch.zeros(max(self.ntiles, 1) * TILE * TILE, **f32)      # dL/dM1_ij + dL/dM1_ji
-            self.Fdiag = torch.zeros(n, **f32)
+        elif self.nn_mode in ("kl2", "dense"):
+            self.Ft = torch.zeros(ntl, **f32)      # dL/dA_ij + dL/dA_ji
+            self.Ct = torch.zeros(ntl, **f32)      # dL/dM1_ij + dL/dM1_ji
+            self.Fdiag = torch.zeros(n, **f32)     # dL/dA_ii
             self.meas_nn = N.M_PRE
             self.sgn = sgn
+            k1c = w1 * 1000 * ALIGN["c1"] if self.c1_active else 0.0
+            k2c = w2 * 100 * ALIGN["c2"]
+            if self.nn_mode == "dense":
+                from .dense_measure import DenseMeasure
+                self.dense = DenseMeasure(self, fa if self.c1_active else None, self.measure, k1c, k2c, sgn)
+            else:
+                self.kl2 = k = N.Kl2Args()
+                self._kl2_keep = keep = {}
+                for name in ("seA", "seM", "lseA", "lseM", "klrow", "c1row"):
+                    keep[name] = torch.zeros(n, **f32)
+                    setattr(k, name, ptr(keep[name]))
+                if self.c1_active:
+                    keep["Ffeat"] = torch.zeros(ntl, **f32)
+                    keep["Fdiag_feat"] = torch.zeros(n, **f32)
+                    call("mcgra_dense_to_tiles", ptr(fa), n, n, self.tr0, self.tr1, 1, ptr(keep["Ffeat"]),
+                         ptr(keep["Fdiag_feat"]), N.stream_ptr())
+                    if world > 1:
+                        self._allreduce(keep["Fdiag_feat"])
+                    keep["lseF"] = torch.logsumexp(fa.double(), dim=1).float().contiguous()
+                    k.Ftiles, k.Fdiag_feat, k.lseF = ptr(keep["Ffeat"]), ptr(keep["Fdiag_feat"]), ptr(keep["lseF"])
+                k.tr0, k.tr1, k.n = self.tr0, self.tr1, n
+                k.EAt, k.Ct = ptr(self.Ft), ptr(self.Ct)
+                k.k1c, k.k2c = k1c, k2c
         del fa
         self.k6 = -w6 * 100 * ALIGN["c6"] / nn2
         self.k7 = -w7 * ALIGN["c7"] / nn2
@@ -190,6 +216,11 @@ class PGDEngine:
         self.lseA = z(n) if kl_native else None
         self.dlse = z(n) if kl_native else None
 
+        if not self.nd_native and (self.w9 != 0.0 or self.w10 != 0.0):
+            self.nd_p2 = z(n, self.nclass)
+            self.nd_mom = torch.zeros(int(N.lib().mcgra_nd_scratch_doubles(self.nclass)), dtype=torch.float64, device=dev)
+            self.nd_coef = z(int(N.lib().mcgra_nd_scratch_floats(self.nclass)))
+            self.nd_m = float(idx.numel())
         self.split_elem = True     # element-wise c1/c6 terms as a separate streaming pass (faster than fused, see DESIGN)
         self.set_parameter(x0)
 
@@ -303,9 +334,11 @@ class PGDEngine:
         n, tr0, tr1, mu, raw = self.n, self.tr0, self.tr1, ptr(self.mu), self.raw
         a = self.forward_stages(t)
         ap = C.byref(a)
-        dense = self.nn_mode == "dense"
-        if dense:
-            self._dense_stage(t)
+        dense = self.nn_mode in ("dense", "kl2")             # gradient tiles handed over as MCGRA_M_PRE
+        if self.nn_mode == "dense":
+            self.dense.step(t)
+        elif self.nn_mode == "kl2":
+            self._kl2_stage(t)
         if not self.nd_native and (self.w9 != 0.0 or self.w10 != 0.0):
             self._nd_stage(t)
         if self.k7 != 0.0 or self.k2 != 0.0 or dense:
@@ -404,7 +437,7 @@ class PGDEngine:
         acc_next = self._acc_row(t + 1).data_ptr()
         self.cand.zero_()
         call("mcgra_bisect_init", acc_next, ptr(self.minmax), self.budget, ptr(self.bstate), ptr(self.mu), st)
-        for _ in range(8):               # 8 passes x 3 halvings covers brackets up to 167 wide at eps = 1e-5
+        for _ in range(BISECT_PASSES):   # 10 passes x 3 halvings: brackets up to ~10^4 wide at eps = 1e-5; finished passes read nothing
             call("mcgra_bisect_pass", ptr(self.xt), n, tr0, tr1, 1e-5, ptr(self.bstate), ptr(self.cand), st)
             self._allreduce(self.cand)
             call("mcgra_bisect_update", self.budget, 1e-5, ptr(self.bstate), ptr(self.cand), ptr(self.mu), st)
@@ -413,94 +446,45 @@ class PGDEngine:
         # (with world > 1 the reset writes d_next = 1 on every rank; keep rank 0's only)
         if self.world > 1 and self.rank != 0:
             self.d_next.sub_(self.bstate[4])
+        if self.world > 1:
+            # bisect_finish re-accumulated SUMSQ from this rank's shard only (when the projection was active): the
+            # slot was all-reduced BEFORE the projection, so reduce the re-accumulated partial again.  bstate[4] = active.
+            ssq = self._acc_row(t + 1)[ACC["SUMSQ"]:ACC["SUMSQ"] + 1]
+            part = torch.where(self.bstate[4] != 0, ssq, ssq / self.world)
+            self._allreduce(part)
+            ssq.copy_(part)
 
     # ------------------------------------------------------------------------------------------------
-    @staticmethod
-    def _measure_fn(name):
-        """Algebraically equal, O(n^3)-minimal forms of the reference measures (topology_attack.py:190-208):
-        linear_HSIC(X,Y) = sum (H XX^T H) o (H YY^T H) = ||(HX)^T (HY)||_F^2 (utils.py:1060-1084)."""
-        import torch.nn.functional as F
-
-        def hsic(X, Y):
-            Xc = X - X.mean(0, keepdim=True)
-            Yc = Y - Y.mean(0, keepdim=True)
-            return ((Xc.t() @ Yc) ** 2).sum()
-        if name == "HSIC":
-            return hsic
-        if name == "CKA":
-            return lambda X, Y: hsic(X, Y) / (torch.sqrt(hsic(X, X)) * torch.sqrt(hsic(Y, Y)))
-        if name == "DP":
-            return lambda X, Y: torch.norm(Y.t() @ X, p=2)
-        if name == "KL":
-            return lambda X, Y: F.kl_div(F.log_softmax(Y, dim=1), F.softmax(X, dim=1), reduction="batchmean")
-        if name == "MSELoss":
-            return lambda X, Y: F.mse_loss(X, Y)
-        raise NotImplementedError(name)
-
-    def _dense_stage(self, t):
-        """c1 / c2 for measures that contract two n x n operands (HSIC, CKA, DP) or need row statistics of both
-        (KL's c2): dense tensors + library GEMMs + autograd, results handed to the native kernels as tiles of
-        dL/dA_ij + dL/dA_ji (self.Ft), dL/dA_ii (self.Fdiag) and dL/dM1_ij + dL/dM1_ji (self.Ct)."""
-        n, st = self.n, N.stream_ptr()
-        calc = self._measure_fn(self.measure_name)
-        sgn = self.sgn
-        Md = torch.zeros(n, n, dtype=torch.float32, device=self.dev)
-        call("mcgra_tiles_to_dense", ptr(self.xt), n, self.tr0, self.tr1, ptr(self.mu), self.raw, ptr(Md), n, st)
-        self._allreduce(Md)
-        if self.raw:
-            Md.clamp_(0, 1)
-        r = self.r
-        Md.diagonal().add_(1.0)
-        A_hat = ((r[:, None] * Md) * r[None, :]).requires_grad_(True)
-        del Md
-        M1 = torch.relu(self.zhat @ self.zhat.t())
-        M1.fill_diagonal_(0.0)
-        M1.requires_grad_(True)
-        with torch.enable_grad():
-            loss = 0.0
-            c1v = c2v = None
-            if self.c1_active:
-                c1v = self.w1 * calc(self.F_dense, A_hat) * 1000 * ALIGN["c1"]
-                loss = loss + sgn * c1v
-            if self.w2 != 0:
-                c2v = self.w2 * calc(A_hat, M1) * 100 * ALIGN["c2"]
-                loss = loss + sgn * c2v
-            GA, GM = torch.autograd.grad(loss, [A_hat, M1], allow_unused=True)
-        if c1v is not None:
-            self._acc_row(t)[ACC["C1D"]] += c1v.detach().double()
-        if c2v is not None:
-            self._acc_row(t)[ACC["C2D"]] += c2v.detach().double()
-        EA = (GA + GA.t()).contiguous()
-        call("mcgra_dense_to_tiles", ptr(EA), n, n, self.tr0, self.tr1, 0, ptr(self.Ft), ptr(self.Fdiag), st)
-        if self.world > 1:       # every rank wrote only the diagonal entries of its own tile rows
-            self._allreduce(self.Fdiag)
-        self.Fdiag.mul_(0.5)
-        if GM is not None:
-            Cm = (GM + GM.t()).contiguous()
-            call("mcgra_dense_to_tiles", ptr(Cm), n, n, self.tr0, self.tr1, 0, ptr(self.Ct), None, st)
-        else:
-            self.Ct.zero_()
+    def _kl2_stage(self, t):
+        """c1 / c2 under --measure KL with c2 on (topology_attack.py:212-229, 483-487): three tile passes, row
+        statistics all-reduced across ranks in between (csrc/kl2.cu)."""
+        st = N.stream_ptr()
+        k, keep = self.kl2, self._kl2_keep
+        k.tiles, k.mu, k.raw = ptr(self.xt), ptr(self.mu), self.raw
+        k.zhat, k.r = ptr(self.zhat), ptr(self.r)
+        kp = C.byref(k)
+        for name in ("seA", "seM", "klrow", "c1row"):
+            keep[name].zero_()
+        call("mcgra_kl2_pass", 0, kp, st)
+        self._allreduce(keep["seA"])
+        self._allreduce(keep["seM"])
+        call("mcgra_kl2_node", 0, kp, None, None, st)
+        call("mcgra_kl2_pass", 1, kp, st)
+        self._allreduce(keep["klrow"])
+        self._allreduce(keep["c1row"])
+        call("mcgra_kl2_node", 1, kp, ptr(self.Fdiag), self._acc_row(t).data_ptr(), st)
+        call("mcgra_kl2_pass", 2, kp, st)
 
     def _nd_stage(self, t):
-        """c9 / c10 under HSIC / CKA / DP (n x 16 and n x c operands, O(n d^2)): small library ops + autograd on the
-        embedding produced by node_head; the gradient is added to the node-level dem buffer."""
-        import torch.nn.functional as F
-        calc = self._measure_fn(self.measure_name)
-        em = self.em.detach().clone().requires_grad_(True)
-        idx = self.idx
-        with torch.enable_grad():
-            loss = 0.0
-            if self.w9 != 0.0:
-                c9 = self.w9 * calc(self.HA[idx], em[idx])
-                loss = loss + c9
-                self._acc_row(t)[ACC["C9"]] += c9.detach().double()
-            if self.w10 != 0.0:
-                p2 = torch.softmax(F.log_softmax(em @ self.Wl.t() + self.bl, dim=1), dim=1)
-                c10 = self.w10 * calc(self.YA[idx], p2[idx])
-                loss = loss + c10
-                self._acc_row(t)[ACC["C10"]] += c10.detach().double()
-            (g,) = torch.autograd.grad(loss, [em])
-        self.demd.add_(g)
+        """c9 / c10 under HSIC / CKA / DP (n x 16 and n x c operands): weighted second moments + closed-form gradient,
+        O(n d^2) (csrc/ndmeasure.cu); the gradient is added to the node-level demd buffer."""
+        a = N.NdArgs()
+        a.n, a.nclass, a.measure = self.n, self.nclass, self.measure
+        a.em, a.HA, a.YA, a.Wl, a.bl, a.wmult = (ptr(x) for x in (self.em, self.HA, self.YA, self.Wl, self.bl, self.wmult))
+        a.m, a.w9, a.w10 = self.nd_m, self.w9, self.w10
+        a.p2, a.mom, a.coef, a.demd = ptr(self.nd_p2), ptr(self.nd_mom), ptr(self.nd_coef), ptr(self.demd)
+        a.acc = self._acc_row(t).data_ptr()
+        call("mcgra_nd_measure", C.byref(a), N.stream_ptr())
 
     # ------------------------------------------------------------------------------------------------
     def losses(self):

@@ -359,7 +359,7 @@ class PGDAttack(BaseAttack):
         mu = torch.zeros(1, dtype=torch.float32, device=dev)
         cand = torch.zeros(8, dtype=torch.float64, device=dev)
         call("mcgra_bisect_init", ptr(acc), ptr(minmax), float(num_edges), ptr(state), ptr(mu), st)
-        for _ in range(8):
+        for _ in range(10):
             call("mcgra_bisect_pass", ptr(tiles), n, 0, T, 1e-5, ptr(state), ptr(cand), st)
             call("mcgra_bisect_update", float(num_edges), 1e-5, ptr(state), ptr(cand), ptr(mu), st)
         out = torch.empty_like(x)
