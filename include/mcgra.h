@@ -396,6 +396,13 @@ int64_t mcgra_nd_scratch_doubles(int nclass);
 int64_t mcgra_nd_scratch_floats(int nclass);
 int mcgra_nd_measure(const mcgra_nd_args* a, void* stream);
 
+/* ---- stand-alone helpers of the class surface ----
+ * M <- clamp(M + eps * noise, 0, 1) (PGDAttack.adding_noise, topology_attack.py:474-478; noise = the caller's N(0,1) draw) */
+int mcgra_noise_clamp(float* M, const float* noise, float eps, int64_t count, void* stream);
+/* out[0] += sum_rows KL(softmax(X_i) || softmax(Y_i)) (PGDAttack.calc_kl, :483-487; divide by rows for batchmean)      */
+int mcgra_row_kl(const float* X, const float* Y, int64_t rows, int64_t cols, int64_t ldx, int64_t ldy, double* out,
+                 void* stream);
+
 /* ---- AUC / AP (main.metric_pool, main.py:66-75; gcn_parameterized.py:55-65) ----
  * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU,
  * every negative is ranked against them; exact integer counts => sklearn's trapezoid AUC with ties, and

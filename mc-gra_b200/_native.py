@@ -143,6 +143,8 @@ _SIGS = {
     "mcgra_nd_scratch_doubles": (i64, [C.c_int]),
     "mcgra_nd_scratch_floats": (i64, [C.c_int]),
     "mcgra_nd_measure": (C.c_int, [C.POINTER(NdArgs), c_fp]),
+    "mcgra_noise_clamp": (C.c_int, [c_fp, c_fp, C.c_float, i64, c_fp]),
+    "mcgra_row_kl": (C.c_int, [c_fp, c_fp, i64, i64, i64, i64, c_fp, c_fp]),
     "mcgra_auc_workspace_bytes": (i64, [i64, i64]),
     "mcgra_auc_ap": (C.c_int, [c_fp, c_fp, i64, i64, c_fp, c_fp, c_fp]),
     "mcgra_sort_workspace_bytes": (i64, [i64]),

@@ -86,7 +86,8 @@ def test_gemm_nt(cg, shape):
         assert err < 2e-6, f"cg={cg} shape={shape}: max scaled err {err:.3e}"
         assert torch.all(Cbuf[:, Nn:] == 7.0), "padding columns must stay untouched"
         ssq = float(red[0])
-        assert abs(ssq - float((ref ** 2).sum())) <= 2e-6 * float((ref ** 2).sum())
+        # (tensor-core fp32 accumulation truncates: a small systematic bias, see test_gemm_large_k)
+        assert abs(ssq - float((ref ** 2).sum())) <= 2e-5 * float((ref ** 2).sum())
         # row panel: only rows [row0, row1) are written
         C2 = torch.zeros(M, ldc, dtype=torch.float32, device=dev)
         e2 = N.GemmEpilogue()
@@ -101,6 +102,27 @@ def test_gemm_nt(cg, shape):
         assert torch.all(C2[:r0] == 0) and torch.all(C2[r1:] == 0)
     finally:
         N.lib().mcgra_set_engine(3, 2)
+
+
+@pytest.mark.parametrize("K", [16384, 65536])
+def test_gemm_large_k(K):
+    """All-positive operands (the A_hat M1 product: no cancellation) at the K of the large configurations: the relative
+    error of every entry, dominated by the accumulator's truncation bias, must stay far below the 1e-4 loss budget."""
+    N = _N()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(K)
+    A = (torch.rand(384, K, generator=g) * 1e-3).to(dev)
+    B = torch.rand(256, K, generator=g).to(dev)
+    ia, ib = _image_of(N, A), _image_of(N, B)
+    Cbuf = torch.zeros(384, 256, dtype=torch.float32, device=dev)
+    e = N.GemmEpilogue()
+    e.C, e.ldc, e.alpha = N.ptr(Cbuf), 256, 1.0
+    N.call("mcgra_gemm_nt", ia.ref, ib.ref, C.byref(e), N.stream_ptr())
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    rel = (Cbuf.double() - ref) / ref
+    print(f"K={K}: mean rel err {float(rel.mean()):.3e}, max |rel err| {float(rel.abs().max()):.3e}")
+    assert float(rel.abs().max()) < 1e-5
 
 
 def test_gemm_dot_epilogue():
