@@ -181,6 +181,209 @@ def make_attack(prob, device):
     return atk, adj
 
 
+def w_active(w, k):
+    return w[k] != 0
+
+
+def large_parity(a, prob, args, PROFILE_W, num_edges, device, world, iters=5, rows=64):
+    """Untimed precision evidence AT THE BENCH SIZE (the reference cannot run there): (1) the exact fp32 FFMA engines
+    (mcgra_set_engine(*, 0)) against the default tensor-core engines for `iters` iterations from the same start: relative
+    loss difference and max |dx|; (2) an fp64 evaluation of `rows` sampled rows of the first propagation
+    Y = M [r*S1 | S1] against the tcgen05 result.  Collective at N > 1 (every rank runs it)."""
+    import torch
+    from mcgra_b200 import _native as N
+    out = {}
+    runs = {}
+    try:
+        for name, engines in (("exact", {0: 0, 1: 0, 2: 0}), ("default", {0: 5, 1: 2, 2: 1})):
+            for w, v in engines.items():
+                N.lib().mcgra_set_engine(w, v)
+            atk, adj = make_attack(prob, device)
+            n = prob["n"]
+            atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_W, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
+                       prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=0,
+                       _engine_epochs=iters + 2, _skip_finalize=True)
+            eng = atk.engine
+            if name == "default":       # fp64 check of sampled rows of the first propagation (before any update: x = 0
+                eng.iterate()           # gives M = 0, so check after one iteration)
+                rs = np.random.RandomState(0)
+                ii = torch.from_numpy(rs.randint(0, n, rows)).to(device)
+                xp = eng.packed_parameter()
+                keep_row = eng._acc_row(eng.step).clone()
+                eng.forward_stages(eng.step)             # re-runnable (node kernels re-zero their outputs) ...
+                eng._acc_row(eng.step).copy_(keep_row)   # ... except for the loss accumulators of this iteration
+                Y1 = eng.Y1[ii].double()
+                B1 = eng.B1.double()
+                jj = torch.arange(n, device=device)
+                errs = []
+                for q in range(rows):
+                    i = int(ii[q])
+                    lo = (i * (i - 1)) // 2 + jj[:i]
+                    hi = (jj[i + 1:] * (jj[i + 1:] - 1)) // 2 + i
+                    row = torch.zeros(n, dtype=torch.float64, device=device)
+                    row[:i] = xp[lo].double().clamp(0, 1)
+                    row[i + 1:] = xp[hi].double().clamp(0, 1)
+                    y = row @ B1
+                    errs.append(float(((Y1[q] - y).abs() / (row @ B1.abs() + 1e-30)).max()))
+                out["fp64_rows_checked"] = rows
+                out["propagate_max_rel_err_vs_fp64"] = max(errs)
+                del xp
+                for _ in range(iters - 1):
+                    eng.iterate()
+            else:
+                for _ in range(iters):
+                    eng.iterate()
+            runs[name] = (eng.losses()["loss"], eng.packed_parameter())
+            del eng, atk
+            torch.cuda.empty_cache()
+    finally:
+        for w, v in {0: 5, 1: 2, 2: 1}.items():
+            N.lib().mcgra_set_engine(w, v)
+    le, xe = runs["exact"]
+    ld, xd = runs["default"]
+    out["iters"] = iters
+    out["rel_loss"] = float(np.max(np.abs(le - ld) / np.abs(le)))
+    out["max_dx"] = float((xe - xd).abs().max())
+    out["what"] = ("exact fp32 FFMA engines vs default tcgen05 engines, same start, %d iterations at the bench size; "
+                   "fp64 check of %d sampled rows of the first propagation" % (iters, rows))
+    return out
+
+
+def same_config_baseline(a, device, n=2708, f=1433, c=7, iters=3):
+    """The SAME configuration on every arm, in the same run, at a size the reference's dense algorithm can run:
+    synthetic Cora shape (BASELINE configs[0]), Profile A, `iters` iterations each -- native (device-resident),
+    the oracle port on the host cores, and the oracle port on this GPU (fp32, allow_tf32=False: the reference's own
+    PyTorch-GPU path).  At N = 1 only."""
+    import torch
+    res = {"n": n, "f": f, "c": c, "profile": "A", "iters": iters}
+    wl = dict(n=n, f=f, c=c, name="same-config")
+    prob = build_problem(wl, device)
+    args = make_args("A")
+    atk, adj = make_attack(prob, device)
+    atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_A, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
+               prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], 10 ** 12, 0, epochs=0,
+               _engine_epochs=iters + 8, _skip_finalize=True)
+    eng = atk.engine
+    for _ in range(3):
+        eng.iterate()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        eng.iterate()
+    e1.record()
+    torch.cuda.synchronize()
+    res["native_it_s"] = iters / (e0.elapsed_time(e1) * 1e-3)
+    native_loss = eng.losses()["loss"][:iters]
+    del eng, atk
+    O, cprob, cfg = cpu_problem(n, f, c)
+    torch.set_num_threads(os.cpu_count())
+    O.attack(cprob, cfg, 1, bookkeeping=True)
+    t0 = time.perf_counter()
+    r = O.attack(cprob, cfg, iters, bookkeeping=True)
+    res["oracle_cpu_it_s"] = iters / (time.perf_counter() - t0)
+    res["oracle_cpu_cores"] = os.cpu_count()
+    res["max_rel_loss_native_vs_oracle"] = float(np.max(np.abs(np.asarray(r["loss"]) - native_loss) / np.abs(np.asarray(r["loss"]))))
+    res["oracle_cuda"] = oracle_on_cuda(O, cprob, cfg, device, iters)
+    return res
+
+
+def oracle_on_cuda(O, cprob, cfg, device, iters):
+    """The reference's dense PyTorch algorithm (oracle port) on the GPU in fp32 with TF32 off."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        gprob = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in cprob.items()}
+        gprob["W"] = {k: v.to(device) for k, v in cprob["W"].items()}
+        with torch.device(device):
+            O.attack(gprob, cfg, 1, bookkeeping=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            O.attack(gprob, cfg, iters, bookkeeping=True)
+            torch.cuda.synchronize()
+        return {"it_s": iters / (time.perf_counter() - t0), "dtype": "fp32, allow_tf32=False", "n": cprob["n"]}
+    except Exception as e:          # the oracle is CPU test infrastructure; report instead of failing the bench
+        return {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def roofline_report(kt, kcount, n, P, world, a, peaks, extra):
+    """`roofline` of the DOMINANT kernel of the step (largest share of the iteration) + per-kernel fractions.
+    Algorithmic bytes per launch: one read of the rank's shard of every streamed tile array + the node
+    arrays; flops of the dense contraction: 2 n^3 / world per GEMM (row panel), issued = 3x (three kind::f16 MMAs)."""
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    bf16 = float(peaks.get("bf16_tflops", 1650.0))
+    src = "MEASURED_PEAKS.json (measured)" if peaks else "fallback (B200_PROFILING.md)"
+    w = PROFILES[a.profile]["w"]
+    c1 = w[0] != 0
+    Pw = P / world
+    alg = {"elem_stats": (8.0 if c1 else 4.0) * Pw, "propagate32": 4.0 * Pw + 3 * n * 32 * 4, "propagate32_elem": 8.0 * Pw,
+           "propagate16": 4.0 * Pw + 3 * n * 16 * 4, "mcgra_fold_adam": (28.0 if (c1 or a.profile == "B") else 24.0) * Pw,
+           "mcgra_pairs": (12.0 * Pw if a.profile == "B" else 0.0), "mcgra_bisect_pass": 4.0 * Pw,
+           "mcgra_bisect_finish": 4.0 * Pw, "mcgra_sym_to_tiles": 4.0 * n * n / world + 4.0 * Pw,
+           "mcgra_image_ahat": 4.0 * P + 4.0 * n * n, "mcgra_image_m1": 4.0 * n * n,
+           "mcgra_image_from_dense": 12.0 * n * n}
+    flops = {k: 2.0 * n ** 3 / world for k in ("gemm_c1", "gemm_c2_T", "gemm_grad", "gemm_self")}
+    per = []
+    for k, ms in kt.items():
+        cnt = kcount.get(k, 1.0)
+        row = {"kernel": k, "ms": ms, "launches_per_step": cnt, "ms_per_step": ms * cnt}
+        if k in flops:
+            row.update(bound="tensor", useful_tflops=flops[k] / (ms * 1e-3) / 1e12,
+                       issued_tflops=3 * flops[k] / (ms * 1e-3) / 1e12, frac=3 * flops[k] / (ms * 1e-3) / 1e12 / bf16)
+        elif alg.get(k, 0.0) > 0:
+            row.update(bound="hbm", alg_bytes=alg[k], gbs=alg[k] / (ms * 1e-3) / 1e9, frac=alg[k] / (ms * 1e-3) / 1e9 / hbm)
+        per.append(row)
+    per.sort(key=lambda r: -r["ms_per_step"])
+    dom = next((r for r in per if "frac" in r), None)
+    if dom is None:
+        return None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = None
+    if world == 1 and os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{a.workload}_{a.profile}", {}).get(dom["kernel"])
+    if dom["bound"] == "tensor":
+        roof = {"bound": "tensor", "kernel": dom["kernel"] + " (mcgra_gemm_nt / k_gemm3<2>: TMA-fed tcgen05 kind::f16 x3 from fp16x2 "
+                "operand images, cta_group::2, fp32 accumulators in TMEM)",
+                "achieved": dom["issued_tflops"], "peak": bf16, "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic,
+                "peak_source": src + ": bf16_tflops (the kernel issues kind::f16 MMAs)",
+                "useful_tflops": dom["useful_tflops"], "tf32_peak_measured": extra.get("tf32_tflops"),
+                "useful_over_tf32_peak": (dom["useful_tflops"] / extra["tf32_tflops"]) if extra.get("tf32_tflops") else None,
+                "note": "useful = 2 n^3 / t (TF32-equivalent work of the reference's fp32 GEMM); a 3xTF32 kernel cannot exceed "
+                        "1/3 of the TF32 peak in useful flops, the fp16x2 split reaches the same precision class at the "
+                        "kind::f16 rate"}
+    else:
+        roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": traffic, "peak_source": src + ": hbm_gbs",
+                "launch_ms": dom["ms"], "algorithmic_bytes_per_launch": dom["alg_bytes"]}
+    roof["share_of_step"] = dom["ms_per_step"] / max(1e-9, sum(r["ms_per_step"] for r in per))
+    roof["per_kernel"] = per
+    return roof
+
+
+def measure_tf32_peak(device):
+    """TF32 tensor peak measured the way MEASURED_PEAKS.json measures bf16 (torch.matmul 8192^3, best of 10), untimed setup."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        x = torch.randn(8192, 8192, device=device)
+        y = torch.randn(8192, 8192, device=device)
+        best = 1e9
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            x @ y
+            e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def run_native(a):
     import torch
     import torch.distributed as dist
@@ -197,6 +400,9 @@ def run_native(a):
     wl = WORKLOADS[a.workload]
     n = wl["n"]
     P = n * (n - 1) // 2
+    extra = {}
+    if rank == 0:
+        extra["tf32_tflops"] = measure_tf32_peak(device)
     prob = build_problem(wl, device, host_feature_adj=(world == 1))
     args = make_args(a.profile)
     PROFILE_W = PROFILES[a.profile]["w"]
@@ -227,6 +433,7 @@ def run_native(a):
             eng.iterate()
         torch.cuda.synchronize()
         kt = {k: float(np.mean([s.elapsed_time(e) for s, e in v])) for k, v in N.TIMERS['on'].items()}
+        kcount = {k: len(v) / 3.0 for k, v in N.TIMERS['on'].items()}
         N.TIMERS['on'] = None
         eng.run(8, use_graph=True)  # captures the graph (one-off, cached on the engine) outside the timed region
         torch.cuda.synchronize()
@@ -249,6 +456,7 @@ def run_native(a):
     ms = ev0.elapsed_time(ev1)
     if not graphed:
         kt = {k: float(np.mean([s.elapsed_time(e) for s, e in v])) for k, v in N.TIMERS['on'].items()}
+        kcount = {k: len(v) / float(K) for k, v in N.TIMERS['on'].items()}
         N.TIMERS['on'] = None
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
@@ -258,6 +466,9 @@ def run_native(a):
     losses = eng.losses()["loss"]
     del eng, atk
     torch.cuda.empty_cache()
+    parity_large = None
+    if not a.no_parity:
+        parity_large = large_parity(a, prob, args, PROFILE_W, num_edges, device, world)
 
     # ------------------------------------------------------------------ end to end through the public API
     e2e = None
@@ -302,23 +513,7 @@ def run_native(a):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm = float(peaks.get("hbm_gbs", 6650.0))
-    prop_ms = kt.get("propagate32")
-    prop_bytes = 4.0 * P / world + 3 * n * 32 * 4          # one read of the shard + B, Y (read-modify-write)
-    roof = None
-    if prop_ms:
-        ach = prop_bytes / (prop_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
-        # workload (profiles/ncu_traffic.json, written by profiles/ncu_summary.py); null when no capture is committed
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if world == 1 and os.path.exists(tp):
-            traffic = json.load(open(tp)).get(a.workload, {}).get("k_propagate_h<32>")
-        roof = {"bound": "hbm", "kernel": "k_propagate_h<32> (Y += M*B over the tiled triangle; both products on tcgen05 "
-                                          "kind::f16 from one fp16x2 image per tile, fp32 accumulators in TMEM)",
-                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "launch_ms": prop_ms, "algorithmic_bytes_per_launch": prop_bytes,
-                "per_kernel_ms": kt}
+    roof = roofline_report(kt, kcount, n, P, world, a, peaks, extra)
     clocks = summarise_clocks(samples)
     out = {"metric": "PGD attack iterations/s (fwd+bwd+prior losses+Adam+projection)", "value": K / (ms * 1e-3),
            "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
@@ -330,9 +525,13 @@ def run_native(a):
                       "cuda_graph": graphed},
            "roofline": roof, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
            "iter_bytes_algorithmic": 52.0 * P, "hbm_frac_whole_iter": 52.0 * P / world / (ms / K * 1e-3) / 1e9 / hbm,
-           "loss_first_last": [float(losses[0]), float(losses[-1])]}
+           "loss_first_last": [float(losses[0]), float(losses[-1])], "parity_large": parity_large,
+           "tf32_tflops_measured": extra.get("tf32_tflops")}
+    if a.profile == "B":
+        out["dense_flops_per_iter_useful"] = (8.0 if w_active(PROFILE_W, 0) else 6.0) * float(n) ** 3
     if world == 1 and not a.no_cpu:
         out["cpu_baseline"] = cpu_baseline(a, threads=os.cpu_count())
+        out["same_config_baseline"] = same_config_baseline(a, device)
     print(json.dumps(out))
 
 
@@ -398,7 +597,10 @@ def run_reference(a):
            "unit": "iterations/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": min(a.warmup, 1),
            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": wl["name"], "sample_n": n},
+           "config": {"workload": f"bounded sample n={n} of: " + wl["name"], "n": n, "sample_n": n,
+                      "same_config_as_native_arm": n == wl["n"],
+                      "note": "the reference's dense algorithm is O(n^3) time / >0.9 TB at n=65536; the native arm reports a "
+                              "same-size comparison in `same_config_baseline` (n=2708, all three arms in one run)"},
            "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -415,6 +617,7 @@ def main():
     ap.add_argument("--density", type=float, default=1e7, help="main.py --density (1e7: budget never binds; 1: it does)")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the untimed large-size precision check")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

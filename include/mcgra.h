@@ -65,7 +65,7 @@ int mcgra_version(void);
  * hybrid, 3: hybrid for the plain 32-wide passes only, 4: both products on tcgen05 kind::tf32 with the transposed
  * operand in tensor memory, 5: both products on tcgen05 kind::f16 from one fp16x2 image per tile [default]; values
  * >= 100 set developer timing bits and are not for production use); which 1 = fold (0 FFMA, 1 mma.sync, 2 tcgen05 [default]);
- * which 2 = pairs (0 FFMA, 1 mma.sync [default]); which 3 = dense contraction mcgra_gemm_nt (1 = cta_group::1, 128 x 128
+ * which 2 = pairs (0 FFMA, 1 mma.sync, 2 tcgen05 for the entropy-only configuration + mma.sync otherwise [default]); which 3 = dense contraction mcgra_gemm_nt (1 = cta_group::1, 128 x 128
  * tiles; 2 = cta_group::2 CTA pairs, 256 x 256 tiles [default]).  Returns 0, or -1 for an unknown selector.          */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */
@@ -170,9 +170,13 @@ int mcgra_node_rho(const mcgra_node_args* a, void* stream);    /* after pass 4: 
  *      gradient w.r.t. zhat (dzhat, caller zero-fills) and c2's eps_row contribution.              */
 /* Optional precomputed inputs (MCGRA_M_PRE measures): EAt = tiles of dL/dA_ij + dL/dA_ji (their eps_row
  * contribution is accumulated here), Ct = tiles of dL/dM1_ij + dL/dM1_ji (added to the coefficient tile).     */
+/* ws (may be NULL): device scratch of mcgra_pairs_ws_bytes(n) bytes; with it the entropy-only configuration (k7 != 0,
+ * k2 == 0, no upstream tiles) runs entirely on tcgen05 (pairs_tc.cu: gram, coefficient planes and both skinny products
+ * on chip, no HBM stream).                                                                                       */
+int64_t mcgra_pairs_ws_bytes(int64_t n);
 int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw,
                 const float* zhat, const float* r, float k7, float k2, const float* EAt, const float* Ct,
-                float* dzhat, float* eps_row, double* acc, void* stream);
+                float* dzhat, float* eps_row, double* acc, void* ws, void* stream);
 
 /* ---- gradient fold + Adam + box clamp (loss.backward()+optimizer.step()+clamp, :274-283) ---- */
 typedef struct {
@@ -197,6 +201,10 @@ typedef struct {
   void* Wk;               /* scratch of mcgra_fold_ws_bytes(n) bytes for the tcgen05 engine (NULL: mma.sync)   */
   const int* step_ptr;    /* optional: device counter of completed iterations; Adam step = *step_ptr + 1 (overrides
                              `step`) so that the launch carries no per-iteration host scalar (CUDA-graph replay) */
+  int plain_gd;           /* != 0: x <- x - lr * g instead of Adam (MC-GPB/topology_attack.py:66-70: adj_changes +=
+                             lr * (-grad), lr = 0.1); m, v are carried through unchanged                          */
+  const float* Gtiles;    /* optional tiles of dL/dM_ij + dL/dM_ji computed upstream (feature smoothing of the GraphMI
+                             attack, MC-GPB/topology_attack.py:57-61), added to the gradient as is; NULL = none      */
 } mcgra_fold_args;
 int64_t mcgra_fold_ws_bytes(int64_t n);
 /* minmax: device float[2] = {min x', max x'} (bisection bracket, :340-341); reset by mcgra_node_rho          */

@@ -49,7 +49,8 @@ class FoldArgs(C.Structure):
                 ("lseA", c_fp), ("lseF", c_fp), ("zhat", c_fp), ("measure", C.c_int),
                 ("k1", C.c_float), ("k6", C.c_float), ("k2", C.c_float), ("norm_coef", C.c_float),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
-                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int), ("Wk", c_fp), ("step_ptr", c_fp)]
+                ("step", C.c_int), ("acc_prev", c_fp), ("acc_next", c_fp), ("d_next", c_fp), ("store_clamped", C.c_int), ("Wk", c_fp), ("step_ptr", c_fp),
+                ("plain_gd", C.c_int), ("Gtiles", c_fp)]
 
 
 class Image(C.Structure):
@@ -109,8 +110,9 @@ _SIGS = {
     "mcgra_node_bwd2": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
     "mcgra_node_bwd1": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
     "mcgra_node_rho": (C.c_int, [C.POINTER(NodeArgs), c_fp]),
+    "mcgra_pairs_ws_bytes": (i64, [i64]),
     "mcgra_pairs": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp, C.c_float, C.c_float,
-                              c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+                              c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "mcgra_fold_ws_bytes": (i64, [i64]),
     "mcgra_fold_adam": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp, C.c_int, C.POINTER(FoldArgs), c_fp,
                                   c_fp]),
@@ -208,7 +210,7 @@ LAUNCHES = {"count": 0, "kernels": 0}
 KERNELS_PER_CALL = {"mcgra_propagate": 3, "mcgra_fold_adam": 2, "mcgra_auc_ap": 15, "mcgra_argsort_desc": 13,
                     "mcgra_version": 0, "mcgra_set_engine": 0, "mcgra_tiles_in_rows": 0, "mcgra_propagate_ws_bytes": 0,
                     "mcgra_fold_ws_bytes": 0, "mcgra_auc_workspace_bytes": 0, "mcgra_sort_workspace_bytes": 0,
-                    "mcgra_nd_scratch_doubles": 0, "mcgra_nd_scratch_floats": 0, "mcgra_nd_measure": 5,
+                    "mcgra_pairs_ws_bytes": 0, "mcgra_nd_scratch_doubles": 0, "mcgra_nd_scratch_floats": 0, "mcgra_nd_measure": 5,
                     "mcgra_image_from_dense": 2, "mcgra_center_dense": 2, "mcgra_sym_to_tiles": 2}
 
 

@@ -268,6 +268,7 @@ __device__ __forceinline__ void fold_stream(SM& sm, const mcgra_fold_args& fa, c
   float* mt = mbuf + tix * TILE_ELEMS;
   float* vt = vbuf + tix * TILE_ELEMS;
   const float* ft = fa.Ftiles ? fa.Ftiles + tix * TILE_ELEMS : nullptr;
+  const float* gt_up = fa.Gtiles ? fa.Gtiles + tix * TILE_ELEMS : nullptr;
   const bool interior = (J < I) && (i0 + TILE <= n);
   const int b0 = lane * 4;
   const int meas = FAST ? MEAS : fa.measure;
@@ -331,6 +332,7 @@ __device__ __forceinline__ void fold_stream(SM& sm, const mcgra_fold_args& fa, c
         if (ENT && fa.k6 != 0.f && ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(2.f * fa.k6, __log2f(ah) + INV_LN2, esym);
         if (!FAST && fa.k2 != 0.f) esym = fmaf(4.f * fa.k2, ah - fmaxf(sdot[k], 0.f), esym);
         float gg = fmaf(ri * rj, esym, rhoi + rhoj4[k] + gs[k]);
+        if (!FAST && gt_up != nullptr) gg += gt_up[off + k];
         if (!FAST) gg *= pv.mask(xs[k]);
         gg = fmaf(ec.norm_scale, p_, gg);
         const float mn = fmaf(ec.omb1, gg - ms[k], ms[k]);                 // beta1*m + (1-beta1)*g
@@ -338,7 +340,7 @@ __device__ __forceinline__ void fold_stream(SM& sm, const mcgra_fold_args& fa, c
         // Adam: p - step * m / (sqrt(v)/sqrt(bc2) + eps); sqrt via rsqrt (1 MUFU), divide via rcp (1 MUFU)
         const float sq = vn > 0.f ? vn * rsqrtf(vn) : 0.f;
         const float denom = fmaf(sq, ec.inv_sqrt_bc2, fa.adam_eps);
-        const float xn = fmaf(-ec.step_size, __fdividef(mn, denom), p_);
+        const float xn = (!FAST && fa.plain_gd) ? fmaf(-fa.lr, gg, p_) : fmaf(-ec.step_size, __fdividef(mn, denom), p_);
         const float c = fminf(fmaxf(xn, 0.f), 1.f);
         xo[k] = valid ? (fa.store_clamped ? c : xn) : 0.f;
         mo[k] = valid ? mn : 0.f;
@@ -479,7 +481,7 @@ k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restric
   float s_clamp = 0.f, s_sq = 0.f, xmin = INFINITY, xmax = -INFINITY;
   float colp[4] = {0.f, 0.f, 0.f, 0.f};
   // specialise the hot combinations (uniform per CTA): plain parameter view + interior tile + MSE/none + no c2
-  const bool fastview = (pv.raw == 2) && interior && fa.k2 == 0.f && fa.measure != MCGRA_M_KL;
+  const bool fastview = (pv.raw == 2) && interior && fa.k2 == 0.f && fa.measure != MCGRA_M_KL && !fa.plain_gd && fa.Gtiles == nullptr;
   if (fastview) {
     if (fa.measure == MCGRA_M_MSE) {
       if (fa.k6 != 0.f) fold_stream<true, MCGRA_M_MSE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
@@ -669,7 +671,7 @@ k_fold_tc(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
   const bool interior = (J < I) && (i0 + TILE <= n);
   float s_clamp = 0.f, s_sq = 0.f, xmin = INFINITY, xmax = -INFINITY;
   float colp[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool fastview = (pv.raw == 2) && interior && fa.k2 == 0.f && fa.measure != MCGRA_M_KL;
+  const bool fastview = (pv.raw == 2) && interior && fa.k2 == 0.f && fa.measure != MCGRA_M_KL && !fa.plain_gd && fa.Gtiles == nullptr;
   if (fastview) {
     if (fa.measure == MCGRA_M_MSE) {
       if (fa.k6 != 0.f) fold_stream<true, MCGRA_M_MSE, true>(sm, fa, pv, ec, tix, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);

@@ -650,12 +650,18 @@ extern "C" {
 
 int mcgra_set_pairs_engine_(int value) { g_pairs_engine = value; return 0; }
 
+int mcgra_pairs_tc_(int64_t n, int tr0, int tr1, const float* zhat, float k7, float* dzhat, double* acc, void* ws,
+                    cudaStream_t st);
+
 int mcgra_pairs(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* zhat,
                 const float* r, float k7, float k2, const float* EAt, const float* Ct, float* dzhat, float* eps_row,
-                double* acc, void* stream) {
+                double* acc, void* ws, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
-  if (g_pairs_engine == 1) {
+  // engine 2: the entropy-only configuration (README Cora profile) entirely on tcgen05, no HBM stream (pairs_tc.cu)
+  if (g_pairs_engine == 2 && ws != nullptr && k7 != 0.f && k2 == 0.f && EAt == nullptr && Ct == nullptr)
+    return mcgra_pairs_tc_(n, tr0, tr1, zhat, k7, dzhat, acc, ws, (cudaStream_t)stream);
+  if (g_pairs_engine >= 1) {
     const bool f7 = k7 != 0.f, f2 = k2 != 0.f, fd = (EAt != nullptr) || (Ct != nullptr);
 #define MCGRA_PAIRS_CASE(A, B, D)                                                                                  \
     if (f7 == A && f2 == B && fd == D)                                                                             \

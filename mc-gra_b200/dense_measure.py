@@ -68,7 +68,6 @@ class DenseMeasure:
         f32 = dict(dtype=torch.float32, device=dev)
         f64 = dict(dtype=torch.float64, device=dev)
         self.GA = torch.zeros(rows_alloc, self.ld, **f32)
-        self.GM = torch.zeros(rows_alloc, self.ld, **f32) if (self.c2 or self.cka) else None
         self.ws = torch.zeros(n + 8, dtype=torch.int32, device=dev)
         self.scal = torch.zeros(8, **f64)
         self.alpha = torch.zeros(8, **f32)
@@ -76,20 +75,22 @@ class DenseMeasure:
         self.a32, self.abar32, self.m32, self.mbar32 = (torch.zeros(n, **f32) for _ in range(4))
         self.vd = torch.zeros(n, **f64)
         self.v1, self.v2, self.v3, self.v4 = (torch.zeros(n, **f32) for _ in range(4))
+        self.hFF = 0.0
+        self.imgK = None
+        if self.c1:                  # constant kernel image first: its temporaries (F image) are gone before the rest
+            self._build_kernel_image(feature_adj)
+        self.GM = torch.zeros(rows_alloc, self.ld, **f32) if (self.c2 or self.cka) else None
         self.imgA = _Img(n, n, dev)
         self.imgM = _Img(n, n, dev) if self.c2 else None
         self.imgT = _Img(n, n, dev) if self.c2 else None
-        self.imgTt = _Img(n, n, dev) if self.c2 else None
+        # the image of T^T is built after the last use of M1's image (HSIC / DP), so it can live in the same memory
+        self.imgTt = (self.imgM if not self.cka else _Img(n, n, dev)) if self.c2 else None
         self.imgSA = _Img(n, n, dev) if self.cka else None
         self.imgSM = _Img(n, n, dev) if (self.cka and self.c2) else None
         self.tiles_full = None
         if world > 1:
             T = eng.T
             self.tiles_full = torch.zeros((T * (T + 1) // 2) * TILE * TILE, **f32)
-        self.hFF = 0.0
-        self.imgK = None
-        if self.c1:
-            self._build_kernel_image(feature_adj)
 
     # ------------------------------------------------------------------------------------------------
     def _gemm(self, A, B, Cbuf=None, alpha=1.0, beta=0.0, alpha_dev=None, beta_dev=None, u=None, v=None, coef=0.0,
@@ -184,7 +185,8 @@ class DenseMeasure:
             self._gemm(self.imgA, self.imgM, self.GM, u=self.a32, v=self.mbar32 if cen else None, sumsq=self._sptr(1),
                        tag="gemm_c2_T", **rank1)
             self._image(self.GM, self.imgT)
-            self._image(self.GM, self.imgTt, transpose=1)
+            if self.cka:
+                self._image(self.GM, self.imgTt, transpose=1)
             self._gemv(self.GM, self.rsM, 1, self.v1)            # T mbar
             self._gemv(self.GM, self.rsA, 0, self.v2)            # abar^T T
             if self.cka:  # S_M = M Hc M
@@ -216,6 +218,8 @@ class DenseMeasure:
             acc_into_ga(self.imgA, self.imgSA, 2, self.v3)       # (Hc A) S_A
         gm = False
         if self.c2:
+            if not self.cka:         # M1's image is dead now: T^T takes its place (T is still in the GM buffer)
+                self._image(self.GM, self.imgTt, transpose=1)
             self._gemm(self.imgA, self.imgTt, self.GM, alpha=1.0, alpha_dev=self._aptr(3), v=self.v2 if cen else None,
                        coef=cen, tag="gemm_grad")                # (Hc A) T
             gm = True
@@ -226,3 +230,37 @@ class DenseMeasure:
              self._aptr(0) if ga == "raw" else None, ptr(eng.Ft), ptr(eng.Fdiag), st)
         if gm:
             call("mcgra_sym_to_tiles", ptr(self.GM), self.ld, n, eng.tr0, eng.tr1, 1.0, None, ptr(eng.Ct), None, st)
+
+
+def cross_frobenius(X, Y, center):
+    """|| Xc^T Yc ||_F^2 (center=True: linear_HSIC, utils.py:1080-1084) or || Y^T X ||_F^2 (center=False: dot_product,
+    topology_attack.py:480-481) of two m-row operands, on the device.  Narrow operands: weighted second moments
+    (mcgra_cross_moments); wide ones: one tcgen05 contraction X^T Y on transposed operand images with the centring as a
+    rank-1 correction and the Frobenius norm as the fused epilogue reduction."""
+    X = X.detach().to(torch.float32).contiguous()
+    Y = Y.detach().to(torch.float32).contiguous()
+    if not X.is_cuda:
+        raise N.NativeError("needs CUDA tensors (no CPU fallback)")
+    m, dx, dy = X.shape[0], X.shape[1], Y.shape[1]
+    dev, st = X.device, N.stream_ptr()
+    if dx <= 64 and dy <= 64:
+        out = torch.zeros(dx + dy + dx * dy + dy * dy, dtype=torch.float64, device=dev)
+        call("mcgra_cross_moments", ptr(X), dx, ptr(Y), dy, None, m, ptr(out), st)
+        G = out[dx + dy:dx + dy + dx * dy].view(dx, dy)
+        if center:
+            G = G - torch.outer(out[:dx], out[dx:dx + dy]) / m
+        return (G ** 2).sum()
+    ws = torch.zeros(max(m, dx, dy) + 8, dtype=torch.int32, device=dev)
+    ix, iy = _Img(dx, m, dev), _Img(dy, m, dev)
+    call("mcgra_image_from_dense", ptr(X), m, dx, dx, 1, ix.ref, ptr(ws), st)
+    call("mcgra_image_from_dense", ptr(Y), m, dy, dy, 1, iy.ref, ptr(ws), st)
+    red = torch.zeros(1, dtype=torch.float64, device=dev)
+    e = N.GemmEpilogue()
+    e.alpha = 1.0
+    e.sumsq = red.data_ptr()
+    if center:       # Xc^T Yc = X^T Y - m xbar ybar^T
+        u = (X.double().sum(0)).float().contiguous()
+        v = (Y.double().mean(0)).float().contiguous()
+        e.u, e.v, e.coef = ptr(u), ptr(v), 1.0
+    call("mcgra_gemm_nt", ix.ref, iy.ref, C.byref(e), st)
+    return red[0]

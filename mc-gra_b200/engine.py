@@ -52,7 +52,7 @@ def shard_tile_rows(T, world):
 class PGDEngine:
     def __init__(self, n, S1, W2, b1, b2, Wl, bl, labels, idx_attack, HA, YA, feature_adj, measure, weights,
                  lr, weight_sup=1.0, num_edges=None, x0=None, device="cuda", rank=0, world=1, group=None,
-                 max_epochs=1024):
+                 max_epochs=1024, plain_gd=False):
         if not torch.cuda.is_available():
             raise N.NativeError("mcgra_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         N.lib()
@@ -169,6 +169,8 @@ class PGDEngine:
         self.nd_native = self.measure in (N.M_MSE, N.M_KL)
         self.w9 = sgn * w9 * ALIGN["c9"]
         self.w10 = sgn * w10 * ALIGN["c10"]
+        self.plain_gd = bool(plain_gd)
+        self.Gt = None                 # optional upstream dL/dM tiles (feature smoothing, mcgpb_attack)
         self.budget = float(num_edges) if num_edges is not None else float("inf")
         self.proj_possible = self.budget < float(self.P)
 
@@ -211,6 +213,7 @@ class PGDEngine:
         self.Wt = z(128, self.npad)
         self.fold_ws = torch.empty(int(N.lib().mcgra_fold_ws_bytes(n)), dtype=torch.uint8, device=dev)
         self.prop_ws = torch.empty(int(N.lib().mcgra_propagate_ws_bytes(n, 32)), dtype=torch.uint8, device=dev)
+        self.pairs_ws = torch.empty(int(N.lib().mcgra_pairs_ws_bytes(n)), dtype=torch.uint8, device=dev)
         kl_native = self.meas_nn == N.M_KL and self.nn_mode == "native"
         self.sumexp = z(n) if kl_native else None
         self.lseA = z(n) if kl_native else None
@@ -344,7 +347,7 @@ class PGDEngine:
         if self.k7 != 0.0 or self.k2 != 0.0 or dense:
             call("mcgra_pairs", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.zhat), ptr(self.r),
                  self.k7, self.k2, (ptr(self.Ft) if dense else None), (ptr(self.Ct) if dense else None),
-                 ptr(self.dzhat), ptr(self.eps_row), self._acc_row(t).data_ptr(), st)
+                 ptr(self.dzhat), ptr(self.eps_row), self._acc_row(t).data_ptr(), ptr(self.pairs_ws), st)
             self._allreduce(self.dzhat)
         call("mcgra_node_bwd2", ap, st)
         call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, ptr(self.prop_ws), st, tag="propagate32")
@@ -373,6 +376,8 @@ class PGDEngine:
         f.d_next = ptr(self.d_next)
         f.store_clamped = 0 if self.proj_possible else 1
         f.Wk = ptr(self.fold_ws)
+        f.plain_gd = 1 if self.plain_gd else 0
+        f.Gtiles = ptr(self.Gt)
         call("mcgra_fold_adam", ptr(self.xt), ptr(self.mt), ptr(self.vt), tr0, tr1, mu, raw, C.byref(f),
              ptr(self.minmax), st)
         # the buffer now holds the un-projected Adam output x' (mu = 0), or the clamped parameter itself

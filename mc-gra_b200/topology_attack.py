@@ -173,6 +173,9 @@ class PGDAttack(BaseAttack):
                                 x0=x0, device=dev, rank=rank, world=world,
                                 max_epochs=max(int(epochs), int(kwargs.get('_engine_epochs', 1)), 1))
         eng = self.engine
+        fa_on_host = not (torch.is_tensor(feature_adj) and feature_adj.is_cuda)
+        if eng.nn_mode == "dense" and fa_on_host:
+            fa = None          # the contraction stage keeps its own constant image; the dense copy returns for the ensemble
         _mark("engine_setup")
         self._trace = []
         self._timing = timing
@@ -184,6 +187,10 @@ class PGDAttack(BaseAttack):
         if int(epochs) == 0:
             eng.forward_stages(0)
         _mark("iterations")
+        if eng.dense is not None:          # n x n operand images / gradient buffers are not needed past the loop
+            eng.dense = None
+        if fa is None:
+            fa = feature_adj.to(dev) if torch.is_tensor(feature_adj) else _dense(feature_adj, dev)
         self._finalize(eng, args, fa, labels_t, W2, b1, b2, Wl, bl)
         _mark("finalize")
         return 0, 0, 0, 0
@@ -366,7 +373,72 @@ class PGDAttack(BaseAttack):
         call("mcgra_tiles_to_tril", ptr(tiles), n, 0, T, ptr(mu), 0, ptr(out), st)
         self.adj_changes.data.copy_(out)
 
+    def bisection(self, a, b, num_edges, epsilon):
+        """Root of sum(clamp(adj_changes - mu, 0, 1)) = num_edges on [a, b] (topology_attack.py:397-412) on the device
+        bisection kernels (same fp32 midpoints as the scalar loop, three halvings per pass over the parameter)."""
+        dev = torch.device(self.device)
+        n = self.nnodes
+        T = (n + N.TILE - 1) // N.TILE
+        st = N.stream_ptr()
+        x = self.adj_changes.data.detach().to(dev, torch.float32).contiguous()
+        tiles = torch.empty(T * (T + 1) // 2 * N.TILE * N.TILE, dtype=torch.float32, device=dev)
+        call("mcgra_tril_to_tiles", ptr(x), n, 0, T, ptr(tiles), st)
+        a, b = float(a), float(b)
+        state = torch.tensor([a, b, a, 0.0, 1.0, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        mu = torch.full((1,), a, dtype=torch.float32, device=dev)
+        cand = torch.zeros(8, dtype=torch.float64, device=dev)
+        passes = max(1, int(np.ceil(np.log2(max(b - a, epsilon) / epsilon) / 3.0)) + 1)
+        for _ in range(passes):
+            call("mcgra_bisect_pass", ptr(tiles), n, 0, T, float(epsilon), ptr(state), ptr(cand), st)
+            call("mcgra_bisect_update", float(num_edges), float(epsilon), ptr(state), ptr(cand), ptr(mu), st)
+        return mu[0]
+
+    def adding_noise(self, modified_adj, eps=0):
+        """clamp(M + eps * N(0,1), 0, 1) in place on M (topology_attack.py:474-478).  The draw comes from torch's CUDA
+        generator (the reference's stream), the add + clamp is one native streaming pass."""
+        M = modified_adj
+        if not (M.is_cuda and M.dtype == torch.float32 and M.is_contiguous()):
+            raise N.NativeError("adding_noise needs a contiguous fp32 CUDA tensor (no CPU fallback)")
+        noise = torch.randn_like(M)
+        call("mcgra_noise_clamp", ptr(M), ptr(noise), float(eps), M.numel(), N.stream_ptr())
+        return M
+
+    def delete_eye(self, A):
+        """topology_attack.py:469-472 (the reference computes A * (1 - I) and returns None)."""
+        A = A * (torch.ones_like(A) - torch.eye(self.nnodes, device=A.device, dtype=A.dtype))
+
+    def dot_product(self, X, Y):
+        """|| Y^T X ||_F (topology_attack.py:480-481): second moments for narrow operands, the tcgen05 contraction
+        (mcgra_gemm_nt on transposed operand images) for wide ones."""
+        from .dense_measure import cross_frobenius
+        return cross_frobenius(X, Y, center=False).sqrt().float()
+
+    def calc_kl(self, X, Y):
+        """KLDivLoss(batchmean)(log_softmax(Y, 1), softmax(X, 1)) (topology_attack.py:483-487), forward value."""
+        X = X.detach().to(torch.float32).contiguous()
+        Y = Y.detach().to(torch.float32).contiguous()
+        if not X.is_cuda:
+            raise N.NativeError("calc_kl needs CUDA tensors (no CPU fallback)")
+        out = torch.zeros(1, dtype=torch.float64, device=X.device)
+        call("mcgra_row_kl", ptr(X), ptr(Y), X.shape[0], X.shape[1], X.stride(0), Y.stride(0), ptr(out), N.stream_ptr())
+        return (out[0] / X.shape[0]).float()
+
+    def test(self, idx_attack, idx_val, idx_test, adj, features, labels, victim_model):
+        """Accuracy of the victim on the normalised adjacency (topology_attack.py:83-93)."""
+        from . import utils
+        adj, features, labels = utils.to_tensor(adj, features, labels, device=self.device)
+        victim_model.eval()
+        adj_norm = utils.normalize_adj_tensor(adj)
+        output = victim_model(features, adj_norm)
+        return utils.accuracy(output[idx_test], labels[idx_test]).item()
+
     def _loss(self, output, labels):
         if self.loss_type == "CE":
             return F.nll_loss(output, labels)
-        raise NotImplementedError("loss_type 'CW' is not on the reference driver's path")
+        if self.loss_type == "CW":       # topology_attack.py:329-335 (stand-alone helper; the loop uses CE)
+            onehot = torch.eye(int(labels.max()) + 1, device=output.device)[labels]
+            best_second_class = (output - 1000 * onehot).argmax(1)
+            ar = torch.arange(len(output), device=output.device)
+            margin = output[ar, labels] - output[ar, best_second_class]
+            return -torch.clamp(margin, min=0).mean()
+        raise ValueError(self.loss_type)

@@ -101,22 +101,10 @@ class CudaCKA(object):
         return tr.float()
 
     def linear_HSIC(self, X, Y):
-        """sum (H XX^T H) . (H YY^T H) = ||(HX)^T (HY)||_F^2 (utils.py:1080-1084), from weighted moments."""
-        from . import _native as N
-        dx, dy = X.shape[1], Y.shape[1]
-        if dx > 64 or dy > 64:          # wide operands (n x n): centred cross product as a library GEMM
-            Xc = X - X.mean(0, keepdim=True)
-            Yc = Y - Y.mean(0, keepdim=True)
-            return ((Xc.t() @ Yc) ** 2).sum()
-        X = X.detach().to(torch.float32).contiguous()
-        Y = Y.detach().to(torch.float32).contiguous()
-        m = X.shape[0]
-        out = torch.zeros(dx + dy + dx * dy + dy * dy, dtype=torch.float64, device=X.device)
-        N.call("mcgra_cross_moments", N.ptr(X), dx, N.ptr(Y), dy, None, m, N.ptr(out), N.stream_ptr())
-        Sx, Sy = out[:dx], out[dx:dx + dy]
-        Sxy = out[dx + dy:dx + dy + dx * dy].view(dx, dy)
-        G = Sxy - torch.outer(Sx, Sy) / m
-        return (G ** 2).sum().float()
+        """sum (H XX^T H) . (H YY^T H) = ||(HX)^T (HY)||_F^2 (utils.py:1080-1084): weighted moments for narrow operands,
+        the tcgen05 contraction (mcgra_gemm_nt) for wide ones (dense_measure.cross_frobenius)."""
+        from .dense_measure import cross_frobenius
+        return cross_frobenius(X, Y, center=True).float()
 
     def linear_CKA(self, X, Y):
         hsic = self.linear_HSIC(X, Y)

@@ -438,6 +438,47 @@ def attack(prob, cfg, epochs, x0=None, bookkeeping=False, record_terms=False):
 
 
 # ----------------------------------------------------------------------------------------------
+# GraphMI baseline attack (MC-GRA/baseline.py:36-86) and its feature-smoothing helper (:155-169)
+# ----------------------------------------------------------------------------------------------
+def feature_smoothing(adj, X):
+    """baseline.PGDAttack.feature_smoothing (baseline.py:155-169): tr(X^T L~ X) through dense diagonal matmuls."""
+    rowsum = adj.sum(1)
+    r_inv = rowsum.flatten()
+    L = torch.diag(r_inv) - adj
+    r_inv = (r_inv + 1e-3).pow(-1 / 2).flatten()
+    r_inv = torch.where(torch.isinf(r_inv), torch.zeros_like(r_inv), r_inv)
+    R = torch.diag(r_inv)
+    L = (R @ L) @ R
+    return torch.trace((X.t() @ L) @ X)
+
+
+def baseline_attack(prob, cfg, epochs, x0=None):
+    """baseline.PGDAttack.attack: nll + 0.001 ||x|| only, Adam, budget projection, final decode (no ensemble).
+    Returns loss per iteration, x after every projection, final x, modified_adj and the last victim output."""
+    n = prob["n"]
+    X, Wt, labels, idx = prob["X"], prob["W"], prob["labels"], prob["idx_attack"]
+    P = n * (n - 1) // 2
+    x = torch.zeros(P, dtype=X.dtype) if x0 is None else x0.clone().to(X.dtype)
+    m, v = torch.zeros_like(x), torch.zeros_like(x)
+    losses, xs = [], []
+    output = A_hat = None
+    for t in range(epochs):
+        xr = x.clone().requires_grad_(True)
+        A_hat = normalize(expand(xr, n))                               # :53-54 (no clamp in the forward)
+        output = victim(X, A_hat, Wt)                                  # :55
+        loss = F.nll_loss(output[idx], labels[idx]) + torch.norm(xr, p=2) * 0.001      # :57-58
+        loss.backward()
+        losses.append(float(loss.detach().double()))
+        adam_update(x, xr.grad, m, v, t + 1, cfg["lr"])                # :75
+        x = torch.clamp(projection(x, cfg["num_edges"]), 0, 1)         # :77-79
+        xs.append(x.clone())
+    em = embed(X, A_hat.detach(), Wt, 2)                               # :81
+    x_final = decode_tril(em)                                          # :82
+    return {"loss": losses, "x_iters": xs, "x_final": x_final, "modified_adj": expand(x_final, n),
+            "output": output.detach()}
+
+
+# ----------------------------------------------------------------------------------------------
 # AUC / AP with sklearn semantics (main.py:66-75; gcn_parameterized.py:55-65), numpy float64
 # ----------------------------------------------------------------------------------------------
 def roc_auc(labels, scores):

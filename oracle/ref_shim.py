@@ -43,6 +43,6 @@ def load():
     install()
     import importlib
     mods = {}
-    for name in ("utils", "base_attack", "topology_attack", "hsic", "models.gcn", "gcn_parameterized"):
+    for name in ("utils", "base_attack", "topology_attack", "hsic", "models.gcn", "gcn_parameterized", "baseline"):
         mods[name] = importlib.import_module(name)
     return mods

@@ -43,6 +43,7 @@ R_ta = ref["topology_attack"]
 R_gcn = ref["models.gcn"]
 R_hsic = ref["hsic"]
 R_gp = ref["gcn_parameterized"]
+R_base = ref["baseline"]
 
 
 def build_victim(X, W, c):
@@ -169,6 +170,49 @@ def run_attack_case(name, n, f, c, measure, weights, lr_exp, epochs, dataset="co
     np.savez_compressed(os.path.join(HERE, f"attack_{name}.npz"), **out)
     print(f"[golden] attack_{name}: n={n} measure={measure} loss[0..2]={losses[:3]} auc={out['auc']:.5f} "
           f"ap={out['ap']:.5f} budget={num_edges} sum_x={xs[-1].sum():.3f}")
+
+
+def run_baseline_case(name, n, f, c, lr, epochs, density=1.0, seed=15, gain=3.0, mean_deg=12.0):
+    """The UNMODIFIED reference GraphMI baseline (MC-GRA/baseline.py PGDAttack.attack) with a binding edge budget."""
+    g = synth.make_graph(n, f, c, seed=seed, mean_deg=mean_deg)
+    X, labels = g["features"], g["labels"]
+    A = synth.dense_adj(n, g["edges"])
+    W = synth.gcn_weights(f, 16, c, seed=seed, gain=gain)
+    victim, emb = build_victim(X, W, c)
+    random.seed(seed)
+    idx_attack = np.array(random.sample(range(n), n))
+    num_edges = int(0.5 * density * A.sum() / n ** 2 * len(idx_attack) ** 2)
+    model = R_base.PGDAttack(model=victim, embedding=emb, nnodes=n, loss_type="CE", device="cpu")
+    losses, xs = [], []
+    orig_backward = torch.Tensor.backward
+
+    def rec_backward(self, *a, **k):
+        losses.append(float(self.detach().double()))
+        return orig_backward(self, *a, **k)
+
+    orig_proj = model.projection
+
+    def rec_proj(ne):
+        orig_proj(ne)
+        xs.append(torch.clamp(model.adj_changes.detach().clone(), 0, 1).numpy())
+
+    model.projection = rec_proj
+    torch.Tensor.backward = rec_backward
+    try:
+        output = model.attack(None, lr, 0, 1.0, None, None, 0, 0, 0, None, None, None, torch.from_numpy(A), X,
+                              np.zeros((n, n), np.float32), labels, idx_attack, num_edges, 0, epochs=epochs)
+    finally:
+        torch.Tensor.backward = orig_backward
+    Xt = torch.from_numpy(X)
+    smooth = model.feature_smoothing(torch.from_numpy(A), Xt)
+    out = dict(X=X, adj=A.astype(np.uint8), labels=labels, idx_attack=idx_attack.astype(np.int64),
+               num_edges=np.int64(num_edges), epochs=np.int64(epochs), lr=np.float64(lr),
+               loss=np.array(losses, dtype=np.float64), x_iters=np.stack(xs).astype(np.float32),
+               x_final=model.adj_changes.detach().numpy().astype(np.float32),
+               modified_adj=model.modified_adj.numpy().astype(np.float32), output=output.numpy().astype(np.float32),
+               smooth_true_adj=np.float64(float(smooth)), **{k: v for k, v in W.items()})
+    np.savez_compressed(os.path.join(HERE, f"baseline_{name}.npz"), **out)
+    print(f"[golden] baseline_{name}: n={n} loss[0..2]={losses[:3]} budget={num_edges} sum_x={xs[-1].sum():.3f}")
 
 
 def function_goldens():
@@ -319,6 +363,12 @@ def main():
         if a.only and a.only not in cs["name"]:
             continue
         run_attack_case(**cs)
+    base_cases = [dict(name="budget_n150", n=150, f=24, c=4, lr=0.05, epochs=6),
+                  dict(name="free_n90", n=90, f=20, c=3, lr=0.01, epochs=5, density=1e7, mean_deg=4.5)]
+    for cs in base_cases:
+        if a.only and a.only not in ("baseline_" + cs["name"]):
+            continue
+        run_baseline_case(**cs)
 
 
 if __name__ == "__main__":

@@ -16,35 +16,44 @@ SUPPORTED = ["mse_A_n37", "mse_A_n150", "mse_all_n150", "mse_budget_n150", "mse_
              "kl_C_n150", "kl_all_n90", "hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90"]
 
 
+# Cases whose FREE-RUNNING fp32 trajectory is allowed to separate from the reference's by more than 1e-4 in the loss:
+# Adam's first steps move every entry by +-lr according to the SIGN of gradients that sit at the fp32 noise floor of the
+# n x n KL / HSIC / CKA terms, so even the reference's own fp32 and fp64 runs differ by > 1e-4 there.  For exactly these
+# cases the loss of iteration t is checked against the fp64 oracle evaluated AT THE NATIVE PARAMETER of iteration t
+# ("float64 re-evaluation as tie-breaker").  Every other case must meet 1e-4 against the golden loss directly;
+# the branch each case takes is printed (pytest -s / the committed profiles/r02_parity_branches.log).
+TIEBREAK = {"kl_C_n150", "kl_all_n90"}
+# tie-break tolerance: KL over n x n rows is a ~600:1 cancellation (sum_j X_ij (F_ij - A_ij) ~ 0.6 against
+# lseF_i - lseA_i ~ 0.6 for a row KL of ~1e-3): the reference's own fp32 loss is 1.5e-4 from its fp64 evaluation there
+TIEBREAK_RTOL = {"kl_C_n150": 4e-4, "kl_all_n90": 4e-4}
+X_ROBUST = {"kl_C_n150", "kl_all_n90", "hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90"}
+
+
 @pytest.mark.parametrize("case", SUPPORTED)
 def test_attack_matches_reference_golden(case):
     d = np.load(os.path.join(GOLDEN, f"attack_{case}.npz"))
     got = run_native_case(d)
-    try:
-        np.testing.assert_allclose(got["loss"], d["loss"], rtol=1e-4)
-    except AssertionError:
-        # Tie-breaker ("float64 re-evaluation"): when the free-running trajectories separate -- Adam's first
-        # steps move every entry by +-lr according to the SIGN of gradients that sit at the fp32 noise floor of the
-        # n x n KL / HSIC terms, so even the reference's own fp32 and fp64 runs differ by > 1e-4 there -- the native
-        # loss of iteration t must match the fp64 oracle evaluated AT THE NATIVE PARAMETER of iteration t.
+    rel = np.max(np.abs(np.asarray(got["loss"]) - d["loss"]) / np.abs(d["loss"]))
+    direct_ok = rel <= 1e-4
+    branch = "direct" if direct_ok else "fp64-at-native-x"
+    print(f"[parity] {case}: max rel loss err vs reference golden {rel:.3e} -> {branch}")
+    if case not in TIEBREAK:
+        assert direct_ok, f"{case}: loss differs from the reference golden by {rel:.3e} (> 1e-4) and is not a listed tie-break case"
+    elif not direct_ok:
         prob, cfg = O.problem_from_npz(d, dtype=torch.float64)
         xs_prev = [d["x0"]] + got["x_iters"][:-1]
-        forced = []
-        for xp in xs_prev:
-            xt = torch.from_numpy(np.asarray(xp)).double()
-            forced.append(float(O.iteration_terms(xt, prob, cfg)[0]))
-        # KL over n x n rows is a ~600:1 cancellation (sum_j X_ij (F_ij - A_ij) ~ 0.6 against lseF_i - lseA_i ~ 0.6
-        # for a row KL of ~1e-3): fp32 cannot hold 1e-4 on it -- the reference's own fp32 loss is 1.5e-4 from its fp64
-        # evaluation on this fixture -- so the KL tie-break tolerance is 4e-4; every other measure keeps 1e-4
-        np.testing.assert_allclose(got["loss"], np.array(forced), rtol=4e-4 if str(d["measure"]) == "KL" else 1e-4)
+        forced = [float(O.iteration_terms(torch.from_numpy(np.asarray(xp)).double(), prob, cfg)[0]) for xp in xs_prev]
+        np.testing.assert_allclose(got["loss"], np.array(forced), rtol=TIEBREAK_RTOL[case])
     xs = np.stack(got["x_iters"])
     dx = np.abs(xs - d["x_iters"])
-    if str(d["measure"]) == "MSELoss":
+    if case not in X_ROBUST:
         assert np.max(dx) < 2e-4
     else:
         # Adam normalises the step (lr * m / sqrt(v)): entries whose gradient is at the fp32 noise floor of the
         # n x n KL / HSIC / CKA terms move by up to +-lr in EITHER implementation, so x is compared robustly
-        assert np.mean(dx > 2e-4) < 0.01 and np.max(dx) <= 2.5 * 10 ** float(d["lr_exp"]) * int(d["epochs"])
+        frac = float(np.mean(dx > 2e-4))
+        print(f"[parity] {case}: fraction of x entries off by > 2e-4: {frac:.2e}, max |dx| {np.max(dx):.3e}")
+        assert frac < 0.01 and np.max(dx) <= 2.5 * 10 ** float(d["lr_exp"]) * int(d["epochs"])
     np.testing.assert_allclose(got["x_final"], d["x_final"], rtol=1e-3, atol=2e-4)
     np.testing.assert_allclose(got["modified_adj"], d["modified_adj"], rtol=1e-3, atol=1e-3)
     real = d["adj"].reshape(-1).astype(np.float32)
@@ -53,6 +62,29 @@ def test_attack_matches_reference_golden(case):
     tol = max(1e-3, 2.0 / float(real.sum()))
     assert abs(O.roc_auc(real, got["modified_adj"].reshape(-1)) - float(d["auc"])) < tol
     assert abs(O.average_precision(real, got["modified_adj"].reshape(-1)) - float(d["ap"])) < tol
+
+
+@pytest.mark.parametrize("case", ["mse_A_n150", "mse_all_n150", "hsic_B_n150", "kl_C_n150"])
+def test_ranking_of_tie_free_scores(case):
+    """BASELINE.json: "bit-exact recovered-edge ranking indices for tie-free scores".  The native stable descending
+    arg-sort (mcgra_argsort_desc) of the native final scores must give every entry whose score is separated from both
+    neighbours by more than the fp32 noise between the two implementations EXACTLY the rank it has in the reference's
+    stable arg-sort of the reference's scores."""
+    from mcgra_b200 import metrics
+    d = np.load(os.path.join(GOLDEN, f"attack_{case}.npz"))
+    got = run_native_case(d, trace=False)
+    ours = torch.from_numpy(got["modified_adj"]).cuda().reshape(-1).contiguous()
+    order = metrics.argsort_desc(ours).cpu().numpy()
+    ref = d["modified_adj"].reshape(-1)
+    ref_order = np.argsort(-ref, kind="stable")
+    noise = float(np.max(np.abs(got["modified_adj"].reshape(-1) - ref)))
+    s = ref[ref_order]
+    gap_prev = np.r_[np.inf, s[:-1] - s[1:]]
+    gap_next = np.r_[s[:-1] - s[1:], np.inf]
+    tie_free = (gap_prev > 4 * noise) & (gap_next > 4 * noise)
+    assert tie_free.sum() > 0
+    print(f"[ranking] {case}: noise {noise:.2e}, tie-free entries {int(tie_free.sum())} of {s.size}")
+    assert np.array_equal(order[tie_free], ref_order[tie_free])
 
 
 @pytest.mark.parametrize("n,weights,density", [
@@ -89,6 +121,31 @@ def test_engines_agree(which, eng):
         N.lib().mcgra_set_engine(which, DEFAULT_ENGINE[which])
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-6)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
+
+
+@pytest.mark.parametrize("n,f,epochs", [(150, 24, 4), (1300, 40, 2), (4500, 32, 2)])
+def test_pairs_tcgen05_engine_agrees(n, f, epochs):
+    """pairs engine 2 (pairs_tc.cu: gram, coefficient planes and both skinny products on tcgen05, entropy-only
+    configuration = README Cora profile) vs the exact fp32 FFMA engine 0; n = 4500 crosses the 32-tile run boundary."""
+    from helpers import synthetic_case
+    from mcgra_b200 import _native as N
+    if n == 150:
+        d = np.load(os.path.join(GOLDEN, "attack_mse_A_n150.npz"))
+    else:
+        d = synthetic_case(n, f, 5, weights={1: 0.01, 6: 10, 7: 10, 9: 10, 10: 1000}, epochs=epochs, mean_deg=8.0)
+    try:
+        N.lib().mcgra_set_engine(2, 0)
+        a = run_native_case(d, epochs=epochs, trace=(n < 2000))
+        N.lib().mcgra_set_engine(2, 2)
+        b = run_native_case(d, epochs=epochs, trace=(n < 2000))
+    finally:
+        N.lib().mcgra_set_engine(2, DEFAULT_ENGINE[2])
+    c7a, c7b = a["terms"]["c7"], b["terms"]["c7"]
+    np.testing.assert_allclose(c7b, c7a, rtol=2e-6)
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-6)
+    assert np.max(np.abs(a["x_final"] - b["x_final"])) < 2e-5
+    if n < 2000:
+        assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
 
 
 @pytest.mark.parametrize("eng", [2, 4, 5])

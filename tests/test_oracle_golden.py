@@ -116,3 +116,23 @@ def test_attack_loop_matches_reference(case):
     real = d["adj"].reshape(-1).astype(np.float32)
     assert abs(O.roc_auc(real, res["modified_adj"].numpy().reshape(-1)) - float(d["auc"])) < 1e-3
     assert abs(O.average_precision(real, res["modified_adj"].numpy().reshape(-1)) - float(d["ap"])) < 1e-3
+
+
+BASE_CASES = sorted(os.path.basename(p)[9:-4] for p in glob.glob(os.path.join(GOLDEN, "baseline_*.npz")))
+
+
+@pytest.mark.parametrize("case", BASE_CASES)
+def test_baseline_attack_oracle(case):
+    """oracle.baseline_attack against the unmodified reference's GraphMI baseline (MC-GRA/baseline.py:36-86)."""
+    d = np.load(os.path.join(GOLDEN, f"baseline_{case}.npz"))
+    n = int(d["labels"].shape[0])
+    prob = dict(n=n, X=T(d["X"]), labels=T(d["labels"]).long(), idx_attack=T(d["idx_attack"]).long(),
+                W={k: T(d[k]) for k in ("W1", "b1", "W2", "b2", "Wl", "bl")})
+    ref = O.baseline_attack(prob, dict(lr=float(d["lr"]), num_edges=int(d["num_edges"])), int(d["epochs"]))
+    close(ref["loss"], d["loss"], rtol=2e-5)
+    for k in range(int(d["epochs"])):
+        close(ref["x_iters"][k], d["x_iters"][k], rtol=1e-4, atol=2e-5)
+    close(ref["x_final"], d["x_final"], rtol=1e-4, atol=2e-5)
+    close(ref["output"], d["output"], rtol=1e-4, atol=2e-5)
+    A = T(d["adj"].astype(np.float32))
+    close(O.feature_smoothing(A, T(d["X"])), d["smooth_true_adj"], rtol=1e-4)
