@@ -411,6 +411,15 @@ int mcgra_noise_clamp(float* M, const float* noise, float eps, int64_t count, vo
 int mcgra_row_kl(const float* X, const float* Y, int64_t rows, int64_t cols, int64_t ldx, int64_t ldy, double* out,
                  void* stream);
 
+/* ---- feature smoothing of the GraphMI attack (MC-GPB/topology_attack.py:57-61, 163-177): coef * tr(X^T L~ X) ----
+ * Gfeat = tiled X X^T (same shard), gdiag[i] = |x_i|^2, d = the engine's degree (1 + row sum).  mcgra_smooth writes the
+ * element-wise gradient tiles Gt (consumed by mcgra_fold_adam as Gtiles) and the row sums trow (all-reduced by the caller
+ * across ranks); mcgra_smooth_node then adds the degree part to rho and coef * value to *acc_slot.                      */
+int mcgra_smooth(const float* tiles, const float* Gfeat, const float* gdiag, int64_t n, int tr0, int tr1, const float* mu,
+                 int raw, const float* d, float coef, float* rt, float* trow, float* Gt, void* stream);
+int mcgra_smooth_node(int64_t n, const float* d, const float* rt, const float* trow, const float* gdiag, float coef,
+                      float* rho, double* acc_slot, void* stream);
+
 /* ---- AUC / AP (main.metric_pool, main.py:66-75; gcn_parameterized.py:55-65) ----
  * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU,
  * every negative is ranked against them; exact integer counts => sklearn's trapezoid AUC with ties, and

@@ -147,6 +147,9 @@ _SIGS = {
     "mcgra_nd_measure": (C.c_int, [C.POINTER(NdArgs), c_fp]),
     "mcgra_noise_clamp": (C.c_int, [c_fp, c_fp, C.c_float, i64, c_fp]),
     "mcgra_row_kl": (C.c_int, [c_fp, c_fp, i64, i64, i64, i64, c_fp, c_fp]),
+    "mcgra_smooth": (C.c_int, [c_fp, c_fp, c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, C.c_float, c_fp, c_fp, c_fp,
+                               c_fp]),
+    "mcgra_smooth_node": (C.c_int, [i64, c_fp, c_fp, c_fp, c_fp, C.c_float, c_fp, c_fp, c_fp]),
     "mcgra_auc_workspace_bytes": (i64, [i64, i64]),
     "mcgra_auc_ap": (C.c_int, [c_fp, c_fp, i64, i64, c_fp, c_fp, c_fp]),
     "mcgra_sort_workspace_bytes": (i64, [i64]),
@@ -211,7 +214,7 @@ KERNELS_PER_CALL = {"mcgra_propagate": 3, "mcgra_fold_adam": 2, "mcgra_auc_ap": 
                     "mcgra_version": 0, "mcgra_set_engine": 0, "mcgra_tiles_in_rows": 0, "mcgra_propagate_ws_bytes": 0,
                     "mcgra_fold_ws_bytes": 0, "mcgra_auc_workspace_bytes": 0, "mcgra_sort_workspace_bytes": 0,
                     "mcgra_pairs_ws_bytes": 0, "mcgra_nd_scratch_doubles": 0, "mcgra_nd_scratch_floats": 0, "mcgra_nd_measure": 5,
-                    "mcgra_image_from_dense": 2, "mcgra_center_dense": 2, "mcgra_sym_to_tiles": 2}
+                    "mcgra_image_from_dense": 2, "mcgra_smooth": 2, "mcgra_center_dense": 2, "mcgra_sym_to_tiles": 2}
 
 
 TIMERS = {"on": None}     # when a dict: name -> list of (start, end) CUDA events around each call

@@ -171,6 +171,8 @@ class PGDEngine:
         self.w10 = sgn * w10 * ALIGN["c10"]
         self.plain_gd = bool(plain_gd)
         self.Gt = None                 # optional upstream dL/dM tiles (feature smoothing, mcgpb_attack)
+        self.smooth = None
+        self.smooth_on = False
         self.budget = float(num_edges) if num_edges is not None else float("inf")
         self.proj_possible = self.budget < float(self.P)
 
@@ -358,6 +360,8 @@ class PGDEngine:
             self._allreduce(self.Y4)
             self._allreduce(self.eps_row)
         call("mcgra_node_rho", ap, st)
+        if self.smooth is not None and self.smooth_on:
+            self._smooth_stage(t)
 
         f = N.FoldArgs()
         f.n, f.npad, f.Wt, f.r, f.rho = n, self.npad, ptr(self.Wt), ptr(self.r), ptr(self.rho)
@@ -377,7 +381,7 @@ class PGDEngine:
         f.store_clamped = 0 if self.proj_possible else 1
         f.Wk = ptr(self.fold_ws)
         f.plain_gd = 1 if self.plain_gd else 0
-        f.Gtiles = ptr(self.Gt)
+        f.Gtiles = ptr(self.Gt) if (self.smooth is not None and self.smooth_on) else None
         call("mcgra_fold_adam", ptr(self.xt), ptr(self.mt), ptr(self.vt), tr0, tr1, mu, raw, C.byref(f),
              ptr(self.minmax), st)
         # the buffer now holds the un-projected Adam output x' (mu = 0), or the clamped parameter itself
@@ -460,6 +464,31 @@ class PGDEngine:
             ssq.copy_(part)
 
     # ------------------------------------------------------------------------------------------------
+    def enable_smoothing(self, X, coef):
+        """coef * tr(X^T L~ X) (feature_smoothing, MC-GPB/topology_attack.py:163-177) as an extra loss term: G = X X^T is
+        tiled once (constant); toggle per iteration with `smooth_on` (the reference adds the term for t >= 50, :57-61)."""
+        n, dev, st = self.n, self.dev, N.stream_ptr()
+        f32 = dict(dtype=torch.float32, device=dev)
+        X = X.detach().to(dev, torch.float32).contiguous()
+        G = torch.zeros(n, n, **f32)
+        call("mcgra_gram_accumulate", ptr(X), X.shape[1], n, 3, None, ptr(G), n, 0, n, st) if X.shape[1] <= 32 else G.copy_(X @ X.t())
+        ntl = max(self.ntiles, 1) * TILE * TILE
+        Gfeat = torch.zeros(ntl, **f32)
+        gdiag = torch.zeros(n, **f32)
+        call("mcgra_dense_to_tiles", ptr(G), n, n, self.tr0, self.tr1, 1, ptr(Gfeat), ptr(gdiag), st)
+        gdiag.copy_(G.diagonal())
+        del G
+        self.Gt = torch.zeros(ntl, **f32)
+        self.smooth = dict(Gfeat=Gfeat, gdiag=gdiag, rt=torch.zeros(n, **f32), trow=torch.zeros(n, **f32), coef=float(coef))
+
+    def _smooth_stage(self, t):
+        sm, st = self.smooth, N.stream_ptr()
+        call("mcgra_smooth", ptr(self.xt), ptr(sm["Gfeat"]), ptr(sm["gdiag"]), self.n, self.tr0, self.tr1, ptr(self.mu),
+             self.raw, ptr(self.d), sm["coef"], ptr(sm["rt"]), ptr(sm["trow"]), ptr(self.Gt), st)
+        self._allreduce(sm["trow"])
+        call("mcgra_smooth_node", self.n, ptr(self.d), ptr(sm["rt"]), ptr(sm["trow"]), ptr(sm["gdiag"]), sm["coef"],
+             ptr(self.rho), self._acc_row(t).data_ptr() + 8 * ACC["C1D"], st)
+
     def _kl2_stage(self, t):
         """c1 / c2 under --measure KL with c2 on (topology_attack.py:212-229, 483-487): three tile passes, row
         statistics all-reduced across ranks in between (csrc/kl2.cu)."""
