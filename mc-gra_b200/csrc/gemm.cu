@@ -15,9 +15,16 @@
 // M = 256, N = 256, K = 16; each CTA holds 128 rows of A and 128 rows (its half of N) of B per K-block of 64 halves
 // (128-byte rows, SWIZZLE_128B, K-major), hi and lo planes -> 64 KB per stage, ring of 3 stages filled by TMA
 // (cp.async.bulk.tensor.2d.cta_group::2, both CTAs signal the leader's mbarrier); warp 0 = TMA producer, warp 1 = MMA
-// issuer (leader CTA only, one thread) and TMEM owner, warps 2-5 = epilogue (tcgen05.ld -> scale -> rank-1 correction
-// -> reductions -> global).  The accumulator (128 lanes x 256 columns fp32 per CTA) lives in TMEM.  A cta_group::1
-// instantiation (128 x 128 tile, no cluster) is kept for validation (mcgra_set_engine(3, 1)).
+// issuer (leader CTA only, one thread) and TMEM owner, warps 2-9 = epilogue (tcgen05.ld -> scale -> rank-1 correction
+// -> reductions -> global).  A cta_group::1 instantiation (128 x 128 tile, no cluster) is kept for validation
+// (mcgra_set_engine(3, 1)).
+//
+// Accumulation: the tensor core adds every MMA into its fp32 TMEM accumulator with TRUNCATION -- measured here on
+// all-positive operands: a relative bias of -4.2e-8 per MMA, i.e. -1.3e-4 at K = 16 384 and -4.2e-4 at K = 65 536 when one
+// accumulator runs over the whole K (tests/test_gpu_gemm.py::test_gemm_large_k), above the 1e-4 loss budget.  The K loop is
+// therefore cut into CHUNKS of 8 K-blocks (96 MMAs, bias <= 4e-6): the MMA warp alternates between two TMEM accumulators
+// (2 x 256 columns) and the eight epilogue warps drain each finished chunk into fp32 REGISTERS (round-to-nearest adds, 128
+// per thread) while the next chunk is being accumulated; the epilogue proper then runs from the registers.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -31,6 +38,8 @@ constexpr int G_PLANE = 128 * 128;             // bytes of one 128-row x 128-byt
 constexpr int G_STAGE = 4 * G_PLANE;           // A_hi | A_lo | B_hi | B_lo
 constexpr int G_STAGES = 3;
 constexpr int G_SMEM = G_STAGES * G_STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int G_CHUNK = 8;                     // K-blocks per TMEM accumulation chunk (see header)
+constexpr int G_THREADS = 320;                 // producer warp, MMA warp, 8 epilogue warps
 constexpr int G_GROUP = 8;                     // tile rasterisation: sweep groups of 8 tile rows (L2 reuse)
 
 int g_gemm_cg = 2;
@@ -162,21 +171,32 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank, bool remote) {
+  if (remote) {
+    const uint32_t a = mapa_rank(tc::smem_u32(bar), rank);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(a) : "memory");
+  } else {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+  }
+}
+
 template <int CG>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(G_THREADS, 1)
 k_gemm3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
         const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const GemmParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + G_STAGES * G_STAGE);
   uint64_t* empty = full + G_STAGES;
-  uint64_t* accum = empty + G_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(accum + 1);
+  uint64_t* acc_full = empty + G_STAGES;       // [2] chunk accumulator b complete (MMA -> epilogue warps)
+  uint64_t* acc_empty = acc_full + 2;          // [2] chunk accumulator b drained (epilogue warps of the group -> MMA)
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   constexpr int BT = 128 * CG;                 // tile edge of the CTA group
   constexpr uint32_t NCOLS = 128 * CG;         // accumulator columns per CTA
+  constexpr int NPT = (int)NCOLS / 2;          // accumulator columns per epilogue thread
 
   // grouped rasterisation of the group's tile
   const int64_t tid = (int64_t)blockIdx.x / CG;
@@ -190,16 +210,20 @@ k_gemm3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUten
   const int64_t nb_cta = (int64_t)tn * BT + (int64_t)cta_rank * 128;           // B rows this CTA stages
   const int64_t n0 = (int64_t)tn * BT;                                         // first output column of the tile
   const int num_kb = (int)((p.K + G_BK - 1) / G_BK);
+  const int num_ch = (num_kb + G_CHUNK - 1) / G_CHUNK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < G_STAGES; ++s) {
       tc::mbar_init(&full[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
-    tc::mbar_init(accum, 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&acc_empty[b], 8 * CG);    // one arrival per epilogue warp of every CTA of the group
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc_cg<CG>(tmem_slot, NCOLS);
+  if (warp == 1) tmem_alloc_cg<CG>(tmem_slot, 2 * NCOLS);
   tc::fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc::fence_after();
@@ -229,26 +253,52 @@ k_gemm3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUten
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % G_STAGES;
         const uint32_t ph = (uint32_t)(kb / G_STAGES) & 1u;
+        const int ch = kb / G_CHUNK, kc = kb % G_CHUNK, b = ch & 1;
+        if (kc == 0 && ch >= 2) {              // accumulator b was last used by chunk ch - 2: wait until it is drained
+          tc::mbar_wait(&acc_empty[b], (uint32_t)(((ch - 2) >> 1) & 1));
+          tc::fence_after();
+        }
         tc::mbar_wait(&full[s], ph);
         tc::fence_after();
         const uint32_t base = tc::smem_u32(smem + s * G_STAGE);
+        const uint32_t d = tmem + (uint32_t)b * NCOLS;
 #pragma unroll
         for (int k = 0; k < G_BK / 16; ++k) {
           const uint64_t ah = desc_sw128(base + k * 32), al = desc_sw128(base + G_PLANE + k * 32);
           const uint64_t bh = desc_sw128(base + 2 * G_PLANE + k * 32), bl = desc_sw128(base + 3 * G_PLANE + k * 32);
-          mma_f16_cg<CG>(tmem, ah, bh, idesc, (kb | k) ? 1u : 0u);
-          mma_f16_cg<CG>(tmem, ah, bl, idesc, 1u);
-          mma_f16_cg<CG>(tmem, al, bh, idesc, 1u);
+          mma_f16_cg<CG>(d, ah, bh, idesc, (kc | k) ? 1u : 0u);
+          mma_f16_cg<CG>(d, ah, bl, idesc, 1u);
+          mma_f16_cg<CG>(d, al, bh, idesc, 1u);
         }
         mma_commit_cg<CG>(&empty[s]);          // frees the stage in both CTAs once these MMAs have read it
+        if (kc == G_CHUNK - 1 || kb == num_kb - 1) mma_commit_cg<CG>(&acc_full[b]);   // chunk complete -> epilogue warps
       }
-      mma_commit_cg<CG>(accum);                // accumulator complete -> epilogue warps of both CTAs
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
-    tc::mbar_wait(accum, 0);
-    tc::fence_after();
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float acc[NPT];
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NPT);
+    for (int ch = 0; ch < num_ch; ++ch) {
+      const int b = ch & 1;
+      tc::mbar_wait(&acc_full[b], (uint32_t)((ch >> 1) & 1));
+      tc::fence_after();
+#pragma unroll
+      for (int g = 0; g < NPT / 32; ++g) {
+        float a[32];
+        tc::tmem_ld32(tl + (uint32_t)b * NCOLS + (uint32_t)(g * 32), a);
+        if (ch == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[g * 32 + j] = a[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[g * 32 + j] += a[j];
+        }
+      }
+      tc::fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_rank(&acc_empty[b], 0, CG == 2 && cta_rank != 0);
+    }
     const int64_t row = m_cta + q * 32 + lane;
     const bool row_ok = row < p.row0 + p.rows && row < p.M;
     const float isa = row_ok ? p.inv_sa[row] : 0.f;
@@ -258,32 +308,32 @@ k_gemm3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUten
     const float ise = (row_ok && p.dot != nullptr) ? p.inv_se[row] : 0.f;
     double ssq = 0.0, sdot = 0.0;
     float* crow = (p.C != nullptr && row_ok) ? p.C + row * p.ldc : nullptr;
-    for (int c = 0; c < (int)NCOLS; c += 32) {
-      float a[32];
-      tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, a);      // warp-collective
-      const int64_t col0 = n0 + c;
-      if (!row_ok || col0 >= p.N) continue;
-      float fsq = 0.f, fdot = 0.f;
+    const int64_t cbase = n0 + half * NPT;
+    if (row_ok && cbase < p.N) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int64_t col = col0 + j;
-        if (col < p.N) {
-          float val = a[j] * isa * __ldg(p.inv_sb + col);
-          if (p.v != nullptr) val = fmaf(-ui, __ldg(p.v + col), val);
-          fsq = fmaf(val, val, fsq);
-          if (p.dot != nullptr) {
-            const float e = (__half2float(p.Eh[row * p.lde + col]) + __half2float(p.El[row * p.lde + col])) * ise;
-            fdot = fmaf(val, e, fdot);
-          }
-          if (crow != nullptr) {
-            float o = alpha * val;
-            if (beta != 0.f) o = fmaf(beta, crow[col], o);
-            crow[col] = o;
+      for (int g = 0; g < NPT / 32; ++g) {
+        float fsq = 0.f, fdot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int64_t col = cbase + g * 32 + j;
+          if (col < p.N) {
+            float val = acc[g * 32 + j] * isa * __ldg(p.inv_sb + col);
+            if (p.v != nullptr) val = fmaf(-ui, __ldg(p.v + col), val);
+            fsq = fmaf(val, val, fsq);
+            if (p.dot != nullptr) {
+              const float e = (__half2float(p.Eh[row * p.lde + col]) + __half2float(p.El[row * p.lde + col])) * ise;
+              fdot = fmaf(val, e, fdot);
+            }
+            if (crow != nullptr) {
+              float o = alpha * val;
+              if (beta != 0.f) o = fmaf(beta, crow[col], o);
+              crow[col] = o;
+            }
           }
         }
+        ssq += (double)fsq;
+        sdot += (double)fdot;
       }
-      ssq += (double)fsq;
-      sdot += (double)fdot;
     }
     if (p.sumsq != nullptr) {
       ssq = warp_sum_d(ssq);
@@ -297,7 +347,7 @@ k_gemm3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUten
 
   tc::fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 1) tmem_dealloc_cg<CG>(tmem, NCOLS);
+  if (warp == 1) tmem_dealloc_cg<CG>(tmem, 2 * NCOLS);
 }
 
 // ---- host side: tensor maps ------------------------------------------------------------------------------------
@@ -348,7 +398,7 @@ int launch_gemm(const CUtensorMap* maps, GemmParams& p, cudaStream_t st) {
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(G_THREADS);
   cfg.dynamicSmemBytes = G_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[1];

@@ -205,10 +205,12 @@ class PGDEngine:
         z = lambda *s: torch.zeros(*s, **f32)
         self.r = z(n)
         self.B1, self.Y1, self.B2, self.Y2, self.B3, self.Y3 = (z(n, 32) for _ in range(6))
-        self.B4, self.Y4 = z(n, HID), z(n, HID)
+        # Y4 and eps_row are reduced across ranks at the same point of the iteration: one buffer, one collective
+        self.Y4e = z(n * HID + n)
+        self.B4, self.Y4 = z(n, HID), self.Y4e[:n * HID].view(n, HID)
         (self.S2, self.T2, self.H2, self.dZ2, self.dZ1, self.dQ1, self.dQ2, self.demd, self.zhat,
          self.dzhat) = (z(n, HID) for _ in range(10))
-        self.inv_norm, self.eps_row, self.rho = z(n), z(n), z(n)
+        self.inv_norm, self.eps_row, self.rho = z(n), self.Y4e[n * HID:], z(n)
         self.em = z(n, HID)
         self.masks = torch.zeros(n, dtype=torch.int32, device=dev)
         self.masks2 = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -356,9 +358,7 @@ class PGDEngine:
         self._allreduce(self.Y3)
         call("mcgra_node_bwd1", ap, st)
         call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B4), 16, ptr(self.Y4), None, ptr(self.prop_ws), st, tag="propagate16")
-        if self.world > 1:
-            self._allreduce(self.Y4)
-            self._allreduce(self.eps_row)
+        self._allreduce(self.Y4e)          # Y4 and eps_row in one collective
         call("mcgra_node_rho", ap, st)
         if self.smooth is not None and self.smooth_on:
             self._smooth_stage(t)
@@ -390,8 +390,9 @@ class PGDEngine:
         if self.world > 1:
             import torch.distributed as dist
             self._allreduce(self._acc_row(t + 1)[:16])
-            self._allreduce(self.minmax[0:1], dist.ReduceOp.MIN)
-            self._allreduce(self.minmax[1:2], dist.ReduceOp.MAX)
+            if self.proj_possible:         # the bisection bracket is only read when the budget can bind
+                self._allreduce(self.minmax[0:1], dist.ReduceOp.MIN)
+                self._allreduce(self.minmax[1:2], dist.ReduceOp.MAX)
         if self.proj_possible:
             self._project(t)
         self._allreduce(self.d_next)

@@ -107,7 +107,10 @@ def main(argv=None):
     idx_train, idx_val, idx_test = perm[:max(n // 10, 1)], perm[n // 10:n // 5], perm[n // 5:]
     idx_attack = np.array(random.sample(range(n), int(n * args.nlabel)))
     num_edges = int(0.5 * args.density * adj_sp.sum() / n ** 2 * len(idx_attack) ** 2)
-    adj = torch.from_numpy(np.asarray(adj_sp.todense(), dtype=np.float32))
+    # the true adjacency stays sparse (COO on the device): no dense n x n on the host (main.py:162 densifies it there)
+    coo = adj_sp.tocoo()
+    adj = torch.sparse_coo_tensor(torch.from_numpy(np.vstack([coo.row, coo.col]).astype(np.int64)),
+                                  torch.from_numpy(coo.data.astype(np.float32)), (n, n)).coalesce().to(device)
     features = torch.from_numpy(feats)
     labels_t = torch.from_numpy(labels)
     feature_adj = dot_product_decode(features.to(device), args.dataset)

@@ -45,7 +45,14 @@ def metric_pool(ori_adj, inference_adj, idx, index_delete=None, print_cfg=False)
     the AUC in the reference either, main.py:70-72)."""
     dev = inference_adj.device
     idx_t = torch.as_tensor(np.asarray(idx), device=dev).long()
-    real = ori_adj.to(dev)[idx_t][:, idx_t]
+    if torch.is_tensor(ori_adj) and ori_adj.is_sparse:      # label matrix as uint8 on the device, never a dense host n x n
+        a = ori_adj.to(dev).coalesce()
+        lab = torch.zeros(a.shape, dtype=torch.uint8, device=dev)
+        ij = a.indices()
+        lab[ij[0], ij[1]] = (a.values() != 0).to(torch.uint8)
+        real = lab[idx_t][:, idx_t]
+    else:
+        real = ori_adj.to(dev)[idx_t][:, idx_t]
     pred = inference_adj[idx_t][:, idx_t]
     auc, _ = roc_auc_ap(pred, real)
     if print_cfg:

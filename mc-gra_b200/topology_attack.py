@@ -34,6 +34,14 @@ def Info_entropy(prob):
     return -torch.mean(prob * torch.log2(prob))
 
 
+def _ident(t):
+    """Cheap identity of an input for the cross-call constant cache: storage address + in-place version for tensors,
+    object id otherwise."""
+    if torch.is_tensor(t):
+        return (t.data_ptr() if not t.is_sparse else id(t), t._version, tuple(t.shape), str(t.device))
+    return (id(t), getattr(t, "shape", None))
+
+
 def _dense(t, device):
     if sp.issparse(t):
         t = np.asarray(t.todense())
@@ -61,6 +69,7 @@ class PGDAttack(BaseAttack):
         self.Y_A = Y_A
         self._adj_changes_after = None
         self.engine = None
+        self._const_cache = {}
         if attack_structure:
             assert nnodes is not None, 'Please give nnodes='
             self.adj_changes = Parameter(torch.zeros(int(nnodes * (nnodes - 1) / 2)))
@@ -153,12 +162,19 @@ class PGDAttack(BaseAttack):
             w1, w2, w6, w7, w9, w10 = args.w1, args.w2, args.w6, args.w8, args.w9, args.w10
         weights = (w1, w2, 0, 0, 0, w6, w7, w8, w9, w10)
 
-        # iteration-invariant constants (hoisted from :177-182): targets on the TRUE, un-normalised adjacency
-        with torch.no_grad():
-            S1 = X @ W1
-            E1 = torch.relu(self._mm_adj(adj_d, S1) + b1)
-            HA_loop = torch.relu(self._mm_adj(adj_d, E1 @ W2) + b2)
-            YA_loop = F.log_softmax(HA_loop @ Wl.t() + bl, dim=1)
+        # iteration-invariant constants (hoisted from :177-182): targets on the TRUE, un-normalised adjacency.  They are
+        # also invariant ACROSS attack() calls on the same inputs (main.py's search mode calls objective() repeatedly):
+        # cached on the object, keyed by the identity + version of the tensors they are built from.
+        ckey = tuple(_ident(t) for t in (ori_features, adj, W1, b1, W2, b2, Wl, bl))
+        if self._const_cache.get("key") == ckey:
+            S1, HA_loop, YA_loop = self._const_cache["val"]
+        else:
+            with torch.no_grad():
+                S1 = X @ W1
+                E1 = torch.relu(self._mm_adj(adj_d, S1) + b1)
+                HA_loop = torch.relu(self._mm_adj(adj_d, E1 @ W2) + b2)
+                YA_loop = F.log_softmax(HA_loop @ Wl.t() + bl, dim=1)
+            self._const_cache = {"key": ckey, "val": (S1, HA_loop, YA_loop)}
         _mark("inputs_and_constants")
         fa = feature_adj.to(dev) if torch.is_tensor(feature_adj) else _dense(feature_adj, dev)
         _mark("feature_adj_h2d")

@@ -452,6 +452,17 @@ def feature_smoothing(adj, X):
     return torch.trace((X.t() @ L) @ X)
 
 
+def baseline_loss_at(x, prob, smooth_coef=0.0):
+    """Loss of the GraphMI baselines at a given parameter (baseline.py:53-58; MC-GPB/topology_attack.py:51-61)."""
+    n = prob["n"]
+    M = expand(x, n)
+    out = victim(prob["X"], normalize(M), prob["W"])
+    loss = F.nll_loss(out[prob["idx_attack"]], prob["labels"][prob["idx_attack"]]) + torch.norm(x, p=2) * 0.001
+    if smooth_coef:
+        loss = loss + smooth_coef * feature_smoothing(M, prob["X"])
+    return loss
+
+
 def baseline_attack(prob, cfg, epochs, x0=None):
     """baseline.PGDAttack.attack: nll + 0.001 ||x|| only, Adam, budget projection, final decode (no ensemble).
     Returns loss per iteration, x after every projection, final x, modified_adj and the last victim output."""
@@ -476,6 +487,35 @@ def baseline_attack(prob, cfg, epochs, x0=None):
     x_final = decode_tril(em)                                          # :82
     return {"loss": losses, "x_iters": xs, "x_final": x_final, "modified_adj": expand(x_final, n),
             "output": output.detach()}
+
+
+def mcgpb_attack(prob, cfg, epochs, smooth_from=50, lr=0.1):
+    """MC-GPB/topology_attack.py PGDAttack.attack (:36-87): plain gradient descent (lr 0.1), from iteration 50 on the
+    loss adds 1e-4 * feature_smoothing (:57-61); final decode relu(Z Z^T) without normalisation (:247-254)."""
+    n = prob["n"]
+    X, Wt, labels, idx = prob["X"], prob["W"], prob["labels"], prob["idx_attack"]
+    P = n * (n - 1) // 2
+    x = torch.zeros(P, dtype=X.dtype)
+    losses, xs = [], []
+    output = A_hat = None
+    for t in range(epochs):
+        xr = x.clone().requires_grad_(True)
+        M = expand(xr, n)
+        A_hat = normalize(M)
+        output = victim(X, A_hat, Wt)
+        loss = F.nll_loss(output[idx], labels[idx]) + torch.norm(xr, p=2) * 0.001
+        if t >= smooth_from:
+            loss = loss + 1e-4 * feature_smoothing(M, X)
+        losses.append(float(loss.detach().double()))
+        g = torch.autograd.grad(loss, xr)[0]
+        x = x - lr * g                                                 # :66-70
+        x = torch.clamp(projection(x, cfg["num_edges"]), 0, 1)         # :75-77
+        xs.append(x.clone())
+    em = embed(X, A_hat.detach(), Wt, 2)
+    G = torch.relu(em @ em.t())
+    ii = tril_pairs(n)
+    x_final = G[ii[0], ii[1]]
+    return {"loss": losses, "x_iters": xs, "x_final": x_final, "modified_adj": expand(x_final, n), "output": output.detach()}
 
 
 # ----------------------------------------------------------------------------------------------

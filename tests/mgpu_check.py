@@ -29,7 +29,18 @@ def main():
         if rank == 0:
             print(f"[mgpu world={dist.get_world_size()}] {case}: rel loss err {e_loss:.2e} max|dx| {e_x:.2e} "
                   f"max|dadj| {e_adj:.2e}")
-        ok &= e_loss < 1e-4 and e_x < 2e-4 and e_adj < 2e-3
+        ok &= e_loss < 1e-4 and e_x < 5e-5 and e_adj < 2e-3
+    # the dense-contraction measures (row-panel GEMMs + all-gather) and the KL tile passes (row statistics all-reduced):
+    # sharded loss against the single-GPU golden, robust x comparison as in tests/test_gpu_attack.py
+    for case in ["hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90", "kl_all_n90", "kl_C_n150"]:
+        d = np.load(os.path.join(ROOT, "tests", "golden", f"attack_{case}.npz"))
+        got = run_native_case(d, device=f"cuda:{local}")
+        e_loss = float(np.max(np.abs(got["loss"] - d["loss"]) / np.abs(d["loss"])))
+        dx = np.abs(np.stack(got["x_iters"]) - d["x_iters"])
+        frac = float(np.mean(dx > 2e-4))
+        if rank == 0:
+            print(f"[mgpu world={dist.get_world_size()}] {case}: rel loss err {e_loss:.2e} frac|dx|>2e-4 {frac:.2e}")
+        ok &= e_loss < (1e-3 if case.startswith("kl") else 1e-4) and frac < 0.01
     # a multi-tile case with an active budget against the oracle
     d = synthetic_case(900, 40, 5, weights={1: 0.5, 2: 0.3, 6: 2.0, 7: 3.0, 9: 1.5, 10: 50.0}, epochs=3, density=1.0,
                        mean_deg=8.0)
