@@ -420,6 +420,12 @@ int mcgra_smooth(const float* tiles, const float* Gfeat, const float* gdiag, int
 int mcgra_smooth_node(int64_t n, const float* d, const float* rt, const float* trow, const float* gdiag, float coef,
                       float* rho, double* acc_slot, void* stream);
 
+/* backward of mcgra_cross_moments: g = d loss / d out (device double, same layout); writes dX [n x dx] and dY [n x dy]
+ * (either may be NULL).  With it every linear HSIC / CKA / DP penalty on factor grams is differentiable in O(n d d')
+ * (MC-GPB/models/gcn.py:400-417, utils.py:774-797).                                                                 */
+int mcgra_cross_moments_bwd(const float* X, int dx, const float* Y, int dy, const float* w, int64_t n, const double* g,
+                            float* dX, float* dY, void* stream);
+
 /* ---- AUC / AP (main.metric_pool, main.py:66-75; gcn_parameterized.py:55-65) ----
  * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU,
  * every negative is ranked against them; exact integer counts => sklearn's trapezoid AUC with ties, and

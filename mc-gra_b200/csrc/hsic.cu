@@ -148,9 +148,47 @@ k_cross_moments(const float* __restrict__ X, int dx, const float* __restrict__ Y
   }
 }
 
+// backward of k_cross_moments: g = d loss / d out (same layout, fp64);
+//   dX[i] = w_i (g_sx + g_Sxy y_i),   dY[i] = w_i (g_sy + g_Sxy^T x_i + (g_Syy + g_Syy^T) y_i)
+__global__ void k_cross_moments_bwd(const float* __restrict__ X, int dx, const float* __restrict__ Y, int dy,
+                                    const float* __restrict__ w, int64_t n, const double* __restrict__ g,
+                                    float* __restrict__ dX, float* __restrict__ dY) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double wi = w ? (double)w[i] : 1.0;
+  const double* gsx = g;
+  const double* gsy = g + dx;
+  const double* gxy = g + dx + dy;
+  const double* gyy = gxy + dx * dy;
+  if (dX != nullptr) {
+    for (int k = 0; k < dx; ++k) {
+      double s = gsx[k];
+      for (int l = 0; l < dy; ++l) s += gxy[k * dy + l] * (double)Y[i * dy + l];
+      dX[i * dx + k] = (float)(wi * s);
+    }
+  }
+  if (dY != nullptr) {
+    for (int l = 0; l < dy; ++l) {
+      double s = gsy[l];
+      for (int k = 0; k < dx; ++k) s += gxy[k * dy + l] * (double)X[i * dx + k];
+      for (int m = 0; m < dy; ++m) s += (gyy[l * dy + m] + gyy[m * dy + l]) * (double)Y[i * dy + m];
+      dY[i * dy + l] = (float)(wi * s);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int mcgra_cross_moments_bwd(const float* X, int dx, const float* Y, int dy, const float* w, int64_t n, const double* g,
+                            float* dX, float* dY, void* stream) {
+  if (dx < 1 || dy < 1 || dx > 64 || dy > 64) return -1;
+  if (n <= 0) return 0;
+  k_cross_moments_bwd<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(X, dx, Y, dy, w, n, g, dX, dY);
+  MCGRA_LAUNCH_CHECK();
+  return 0;
+}
 
 int mcgra_gauss_stats(const float* X, int dx, const float* Y, int dy, int64_t m, float gx, float gy, float* rowK,
                       float* rowL, double* out, void* stream) {

@@ -424,7 +424,7 @@ k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
   if (k2 != 0.f) block_atomic_add_d((double)v2 * (double)k2, acc + MCGRA_ACC_C2, sm.red);
 }
 
-int g_pairs_engine = 1;
+int g_pairs_engine = 2;     // 0 fp32 FFMA (exact), 1 mma.sync 3xTF32, 2 tcgen05 for the entropy-only configuration (else 1)
 
 // x_final tiles = relu(z_i . z_j), j < i < n  (dot_product_decode of the last embedding, :300-301)
 __global__ void __launch_bounds__(256)

@@ -352,6 +352,8 @@ class PGDEngine:
             call("mcgra_pairs", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.zhat), ptr(self.r),
                  self.k7, self.k2, (ptr(self.Ft) if dense else None), (ptr(self.Ct) if dense else None),
                  ptr(self.dzhat), ptr(self.eps_row), self._acc_row(t).data_ptr(), ptr(self.pairs_ws), st)
+            if self.k7 != 0.0 and self.k2 == 0.0 and not dense:
+                N.LAUNCHES["kernels"] += 2      # tcgen05 engine: operand prep (2 kernels) + k_pairs_tc
             self._allreduce(self.dzhat)
         call("mcgra_node_bwd2", ap, st)
         call("mcgra_propagate", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.B3), 32, ptr(self.Y3), None, ptr(self.prop_ws), st, tag="propagate32")

@@ -131,9 +131,54 @@ def penalty_fixtures():
     print("[golden] mcgpb_penalties.npz", {k: float(v) for k, v in out.items() if k.endswith("_value")})
 
 
+def fit_case(name, n, f, c, MI_type, epochs=3, seed=15):
+    """MC-GPB GCN.fit with the MI constraints (models/gcn.py:184-277, 321-513), dropout 0 so that the run is a
+    deterministic function of the seeded weights and node-pair draws; records the per-epoch losses and the final weights."""
+    g = synth.make_graph(n, f, c, seed=seed, mean_deg=8.0)
+    X, labels = g["features"], g["labels"]
+    A = synth.dense_adj(n, g["edges"])
+    rs = np.random.RandomState(seed)
+    perm = rs.permutation(n)
+    idx_train, idx_val, idx_test = perm[:n // 5], perm[n // 5:2 * n // 5], perm[2 * n // 5:]
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    model = R_gcn.GCN(nfeat=f, nclass=c, nhid=16, nlayer=2, dropout=0.0, weight_decay=5e-4, device="cpu")
+    init = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    beta = {"layer-0": 0.05, "layer-1": 0.02, "layer-2": 0.01, "layer_inter-0": 0.03, "layer_inter-1": 0.01, "plain_acc": 0.7}
+    draws = []
+    orig_choice = np.random.choice
+
+    def rec_choice(*a, **k):
+        r = orig_choice(*a, **k)
+        draws.append(np.asarray(r).copy())
+        return r
+    np.random.choice = rec_choice
+    try:
+        res = model.fit(torch.from_numpy(X), torch.from_numpy(A), torch.from_numpy(labels), idx_train, idx_val, idx_test,
+                        train_iters=epochs, beta=beta, MI_type=MI_type, verbose=False, plain_acc=0.7)
+    finally:
+        np.random.choice = orig_choice
+    final = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    out = dict(X=X, adj=A.astype(np.uint8), labels=labels, idx_train=idx_train, idx_val=idx_val, idx_test=idx_test,
+               MI_type=np.array(MI_type), epochs=np.int64(epochs), pair_draws=np.stack(draws),
+               full_losses=np.array(res["full_losses"], dtype=np.float64), IAZ=res["IAZ"].numpy(), IYZ=res["IYZ"].numpy(),
+               final_layer_aucs=np.array(res["final_layer_aucs"], dtype=np.float64),
+               beta_keys=np.array(list(beta.keys())), beta_vals=np.array(list(beta.values())),
+               **{"init_" + k: v for k, v in init.items()}, **{"final_" + k: v for k, v in final.items()})
+    np.savez_compressed(os.path.join(HERE, f"mcgpb_fit_{name}.npz"), **out)
+    print(f"[golden] mcgpb_fit_{name}: MI_type={MI_type} losses(IYZ,IAZ,inter,mission) per epoch = {np.array(res['full_losses']).T.tolist()} "
+          f"layer AUCs {res['final_layer_aucs']}")
+
+
 if __name__ == "__main__":
     random.seed(15)
     np.random.seed(15)
     torch.manual_seed(15)
-    attack_case("n150", 150, 24, 4, epochs=56)
-    penalty_fixtures()
+    which = sys.argv[1:] or ["attack", "penalties", "fit"]
+    if "attack" in which:
+        attack_case("n150", 150, 24, 4, epochs=56)
+    if "penalties" in which:
+        penalty_fixtures()
+    if "fit" in which:
+        for mi in ("linear_HSIC", "linear_CKA", "DP"):
+            fit_case(f"{mi}_n300", 300, 24, 4, mi)

@@ -183,3 +183,26 @@ def test_fp16x2_image_precision():
     ref = X.astype(np.float64) @ Y.astype(np.float64).T
     scale = np.abs(X).astype(np.float64) @ np.abs(Y).astype(np.float64).T
     assert np.max(np.abs(C - ref) / scale) < 2.0 ** -20
+
+
+@pytest.mark.parametrize("name", ["linear_HSIC", "linear_CKA", "DP"])
+def test_mcgpb_penalties_from_factor_moments(name, monkeypatch):
+    """mcgpb_gcn.{linear_HSIC, linear_CKA, DP}: the MC-GPB penalties IAZ(N N^T, Z) (MC-GPB/utils.py:774-797) as functions
+    of second moments of the factors, value and both gradients against the fixture produced by the unmodified reference
+    (tests/golden/make_golden_mcgpb.py).  The moment kernel is replaced by its torch definition here (CPU)."""
+    from mcgra_b200 import mcgpb_gcn as G
+    d = np.load(os.path.join(ROOT, "tests", "golden", "mcgpb_penalties.npz"))
+
+    def moments(Nf, Z):
+        Nf, Z = Nf.double(), Z.double()
+        return Nf.sum(0), Z.sum(0), Nf.t() @ Z, Z.t() @ Z, Nf.t() @ Nf
+    monkeypatch.setattr(G, "_moments", moments)
+    Z = torch.from_numpy(d["Z"]).double().requires_grad_(True)
+    Zn = torch.from_numpy(d["Znext"]).double().requires_grad_(True)
+    v = getattr(G, name)(Zn, Z)
+    gz, gzn = torch.autograd.grad(v.double(), [Z, Zn])
+    ref = float(d[f"{name}_value"])
+    assert abs(float(v) - ref) <= 2e-4 * abs(ref)          # the fixture itself is an fp32 n^3 evaluation
+    for g, key in ((gz, "gZ"), (gzn, "gZnext")):
+        r = d[f"{name}_{key}"]
+        assert np.max(np.abs(g.numpy() - r)) <= 2e-3 * np.max(np.abs(r))

@@ -104,7 +104,7 @@ def test_multi_tile_matches_oracle(n, weights, density):
     np.testing.assert_allclose(got["modified_adj"], ref["modified_adj"].numpy(), rtol=1e-3, atol=1e-3)
 
 
-DEFAULT_ENGINE = {0: 5, 1: 2, 2: 1}      # propagate: tcgen05 fp16x2 (v5); fold: tcgen05; pairs: mma.sync
+DEFAULT_ENGINE = {0: 5, 1: 2, 2: 2}      # propagate: tcgen05 fp16x2 (v5); fold: tcgen05; pairs: tcgen05 (entropy-only) / mma.sync
 
 
 @pytest.mark.parametrize("which,eng", [(0, 1), (0, 4), (0, 5), (1, 1), (1, 2), (2, 1)])
