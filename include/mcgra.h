@@ -235,7 +235,9 @@ int mcgra_history_push(const double* row, double* hist, int64_t max_rows, int* s
 int mcgra_decode_to_tiles(const float* zhat, int64_t n, int tr0, int tr1, float* tiles, void* stream);
 /* one gram term of the ensemble: out[i,j] (+)= f(Z_i . Z_j) with the dataset's decode2 variant
  * (dot_product_decode2, :421-467): variant 0 sigmoid(relu(g - I)), 1 relu(g - I),
- * 2 relu(g/rownorm_i - I) (rownorm = ||row i of ZZ^T||, given), 3 plain g (gcn_parameterized.py:406-416).  */
+ * 2 relu(g/rownorm_i - I) (rownorm = ||row i of ZZ^T||, given), 3 plain g (gcn_parameterized.py:406-416),
+ * 4 relu(g) with a zero diagonal (the symmetric expansion of dot_product_decode: get_modified_adj, :365-379, 414-419,
+ * used when the row band of an ensemble is computed on a rank that does not hold the mirrored tiles).              */
 int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const float* rownorm,
                           float* out, int64_t ld, int64_t row0, int64_t row1, void* stream);
 /* out[i,j] += (labels[i]==labels[j])                                                                */
@@ -434,6 +436,14 @@ int mcgra_cross_moments_bwd(const float* X, int dx, const float* Y, int dy, cons
 int64_t mcgra_auc_workspace_bytes(int64_t N, int64_t npos_max);
 int mcgra_auc_ap(const float* scores, const uint8_t* labels, int64_t N, int64_t npos_max, void* ws,
                  double* out, void* stream);
+/* the three stages of mcgra_auc_ap, callable separately so that the n^2 pairs can be split over ranks by row bands:
+ * stage 0 compacts the positives' keys of the local pairs (ws: u64 count at byte 0, u32 keys from byte 256); the caller
+ * may replace them by the global positives (all-gather); stage 1 sorts the positives and ranks the local negatives
+ * (ws: u64 sums[2] at byte 8, u64 hist[npos_max + 2] at mcgra_auc_hist_offset(npos_max)); the caller may sum hist / sums
+ * over ranks (all-reduce); stage 2 writes out[4] = {auc, ap, npos, nneg}.                                          */
+int64_t mcgra_auc_hist_offset(int64_t npos_max);
+int mcgra_auc_stage(int stage, const float* scores, const uint8_t* labels, int64_t N, int64_t npos_max, void* ws,
+                    double* out, void* stream);
 /* stable descending arg-sort (LSD radix sort, key = score, payload = index): the recovered-edge ranking */
 int64_t mcgra_sort_workspace_bytes(int64_t N);
 int mcgra_argsort_desc(const float* scores, int64_t N, int64_t* order, void* ws, void* stream);

@@ -297,10 +297,22 @@ int64_t mcgra_auc_workspace_bytes(int64_t N, int64_t npos_max) {
          align256((npos_max + 2) * 8);
 }
 
-int mcgra_auc_ap(const float* scores, const uint8_t* labels, int64_t N, int64_t npos_max, void* ws, double* out,
-                 void* stream) {
+// The three stages of mcgra_auc_ap, callable separately so that the n^2 pairs can be split over ranks by row bands:
+//   stage 0  compact the positives' keys of the local pairs (ws: counter[0] = count, pos[0 .. count))
+//            -- the caller may then replace pos / counter[0] by the GLOBAL positives (all-gather)
+//   stage 1  sort the positives, rank the local negatives against them (ws: hist, sums)
+//            -- the caller may then sum hist / sums over ranks (all-reduce)
+//   stage 2  AUC / AP from the counts.
+// Workspace byte offsets: counter 0, sums 8, pos 256, hist = mcgra_auc_hist_offset(npos_max).
+int64_t mcgra_auc_hist_offset(int64_t npos_max) {
+  const int64_t nb = (npos_max + CHUNK - 1) / CHUNK + 1;
+  return 256 + 2 * align256(npos_max * 4) + align256(nb * 256 * 4) + align256(nb * 256 * 8);
+}
+
+int mcgra_auc_stage(int stage, const float* scores, const uint8_t* labels, int64_t N, int64_t npos_max, void* ws,
+                    double* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (N <= 0 || npos_max <= 0) return -1;
+  if (npos_max <= 0 || stage < 0 || stage > 2) return -1;
   char* p = (char*)ws;
   unsigned long long* counter = (unsigned long long*)p;       // [0] npos, [1..2] sums
   unsigned long long* sums = counter + 1;
@@ -311,19 +323,33 @@ int mcgra_auc_ap(const float* scores, const uint8_t* labels, int64_t N, int64_t 
   uint32_t* hs = (uint32_t*)p; p += align256(nb * 256 * 4);
   int64_t* offs = (int64_t*)p; p += align256(nb * 256 * 8);
   unsigned long long* hist = (unsigned long long*)p;
-  cudaError_t e = cudaMemsetAsync(ws, 0, 256, st);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaMemsetAsync(hist, 0, (npos_max + 2) * 8, st);
-  if (e != cudaSuccess) return (int)e;
-  // keys of unused slots sort to the top and are ignored (counter gives the true count); fill with 0xff
-  e = cudaMemsetAsync(pos, 0xff, npos_max * 4, st);
-  if (e != cudaSuccess) return (int)e;
-  k_compact_pos<<<148 * 8, 256, 0, st>>>(scores, labels, N, pos, npos_max, counter);
-  int rc = radix_sort<uint32_t>(pos, nullptr, pos_tmp, nullptr, npos_max, hs, offs, st);
-  if (rc) return rc;
-  k_rank_negatives<<<148 * 8, 256, 0, st>>>(scores, labels, N, pos, counter, hist, sums);
-  k_ap_finish<<<1, 1024, 0, st>>>(pos, counter, hist, sums, out);
+  if (stage == 0) {
+    cudaError_t e = cudaMemsetAsync(ws, 0, 256, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(hist, 0, (npos_max + 2) * 8, st);
+    if (e != cudaSuccess) return (int)e;
+    // keys of unused slots sort to the top and are ignored (counter gives the true count); fill with 0xff
+    e = cudaMemsetAsync(pos, 0xff, npos_max * 4, st);
+    if (e != cudaSuccess) return (int)e;
+    if (N > 0) k_compact_pos<<<148 * 8, 256, 0, st>>>(scores, labels, N, pos, npos_max, counter);
+  } else if (stage == 1) {
+    int rc = radix_sort<uint32_t>(pos, nullptr, pos_tmp, nullptr, npos_max, hs, offs, st);
+    if (rc) return rc;
+    if (N > 0) k_rank_negatives<<<148 * 8, 256, 0, st>>>(scores, labels, N, pos, counter, hist, sums);
+  } else {
+    k_ap_finish<<<1, 1024, 0, st>>>(pos, counter, hist, sums, out);
+  }
   MCGRA_LAUNCH_CHECK();
+  return 0;
+}
+
+int mcgra_auc_ap(const float* scores, const uint8_t* labels, int64_t N, int64_t npos_max, void* ws, double* out,
+                 void* stream) {
+  if (N <= 0 || npos_max <= 0) return -1;
+  for (int stage = 0; stage < 3; ++stage) {
+    const int rc = mcgra_auc_stage(stage, scores, labels, N, npos_max, ws, out, stream);
+    if (rc) return rc;
+  }
   return 0;
 }
 

@@ -225,7 +225,8 @@ k_gemm3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUten
   }
   if (warp == 1) tmem_alloc_cg<CG>(tmem_slot, 2 * NCOLS);
   tc::fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();                             // CTA-level order for tmem_slot / the barriers (and for racecheck, which
+  if constexpr (CG == 2) cluster_sync_all();   // does not model barrier.cluster); the pair then syncs across CTAs
   tc::fence_after();
   const uint32_t tmem = *tmem_slot;
 

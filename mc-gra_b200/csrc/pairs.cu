@@ -458,7 +458,7 @@ k_decode_to_tiles(const float* __restrict__ z, int64_t n, int64_t t0, float* __r
 // out[i, j] += f(Z_i . Z_j)   for i in [row0,row1), all j; 32x32 output block per CTA, d <= 32
 __global__ void __launch_bounds__(256)
 k_gram_accumulate(const float* __restrict__ Z, int d, int64_t n, int variant, const float* __restrict__ rownorm,
-                  float* __restrict__ out, int64_t ld, int64_t row0) {
+                  float* __restrict__ out, int64_t ld, int64_t row0, int64_t row1) {
   __shared__ float zi[32][33], zj[32][33];
   const int64_t bi = row0 + (int64_t)blockIdx.y * 32, bj = (int64_t)blockIdx.x * 32;
   const int tid = threadIdx.x;
@@ -471,11 +471,12 @@ k_gram_accumulate(const float* __restrict__ Z, int d, int64_t n, int variant, co
   const int tx = tid & 31, ty = tid >> 5;
   for (int rr = ty; rr < 32; rr += 8) {
     const int64_t gi = bi + rr, gj = bj + tx;
-    if (gi >= n || gj >= n) continue;
+    if (gi >= n || gj >= n || gi >= row1) continue;
     float s = 0.f;
     for (int k = 0; k < d; ++k) s = fmaf(zi[rr][k], zj[tx][k], s);
     if (variant == 2) s = s / fmaxf(rownorm[gi], 1e-12f);
     float v = (variant == 3) ? s : fmaxf(s - (gi == gj ? 1.f : 0.f), 0.f);
+    if (variant == 4) v = (gi == gj) ? 0.f : fmaxf(s, 0.f);
     if (variant == 0) v = 1.f / (1.f + expf(-v));
     out[gi * ld + gj] += v;
   }
@@ -489,7 +490,7 @@ k_gram_accumulate(const float* __restrict__ Z, int d, int64_t n, int variant, co
 constexpr int EB = 64;
 __global__ void __launch_bounds__(256)
 k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, float* __restrict__ out, int64_t ld,
-           int64_t row0) {
+           int64_t row0, int64_t row1) {
   __shared__ __align__(16) float buf[2 * 32 * EB + EB];       // M stage: [64][65]; gram stage: ziT[32][64] | zjT[32][64]
   const int64_t bi = row0 + (int64_t)blockIdx.y * EB, bj = (int64_t)blockIdx.x * EB;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -553,6 +554,7 @@ k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, f
           float sv = s[p][q];
           if (T.variant == 2) sv = sv / rn;
           float v = (T.variant == 3) ? sv : fmaxf(sv - (gi == gj ? 1.f : 0.f), 0.f);
+          if (T.variant == 4) v = (gi == gj) ? 0.f : fmaxf(sv, 0.f);
           if (T.variant == 0) v = 1.f / (1.f + expf(-v));
           acc[p][q] += v;
         }
@@ -562,7 +564,7 @@ k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, f
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4;
-        if (gi >= n) continue;
+        if (gi >= n || gi >= row1) continue;
         if ((n & 3) == 0) {                       // rows are 16-byte aligned: one vector load (gj + 3 < n since n % 4 == 0)
           if (gj < n) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(T.dense + gi * n + gj));
@@ -581,7 +583,7 @@ k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, f
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int64_t gi = bi + ty * 4 + p;
-        if (gi >= n) continue;
+        if (gi >= n || gi >= row1) continue;
         const int64_t li = T.labels[gi];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -592,7 +594,7 @@ k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, f
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4;
-    if (gi >= n) continue;
+    if (gi >= n || gi >= row1) continue;
     if ((ld & 3) == 0 && gj + 3 < n && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
       *reinterpret_cast<float4*>(out + gi * ld + gj) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
     } else {
@@ -696,7 +698,7 @@ int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const f
   if (row1 <= row0) return 0;
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((row1 - row0 + 31) / 32));
   if (grid.y > 65535) return -3;
-  k_gram_accumulate<<<grid, 256, 0, (cudaStream_t)stream>>>(Z, d, n, variant, rownorm, out, ld, row0);
+  k_gram_accumulate<<<grid, 256, 0, (cudaStream_t)stream>>>(Z, d, n, variant, rownorm, out, ld, row0, row1);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }
@@ -710,7 +712,7 @@ int mcgra_ensemble(const float* tiles, int64_t n, const mcgra_ensemble_args* arg
   if (row1 <= row0) return 0;
   dim3 grid((unsigned)((n + EB - 1) / EB), (unsigned)((row1 - row0 + EB - 1) / EB));
   if (grid.y > 65535) return -3;
-  k_ensemble<<<grid, 256, 0, (cudaStream_t)stream>>>(tiles, n, *args, out, ld, row0);
+  k_ensemble<<<grid, 256, 0, (cudaStream_t)stream>>>(tiles, n, *args, out, ld, row0, row1);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }

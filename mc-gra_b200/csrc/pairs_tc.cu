@@ -18,6 +18,7 @@
 // the direct product and the MN-major A operand of the mirrored one) and flush the mirrored result of tile k-1.
 // TMEM columns: D1 [0,48) | D2[0] [48,96) | D2[1] [96,144) | S[0] [256,384) | S[1] [384,512).
 #include <cuda_fp16.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -252,7 +253,7 @@ k_pairs_tc(int64_t n, int tr0, const unsigned char* __restrict__ Zb, const unsig
     const uint32_t tlane = tm + ((uint32_t)(q * 32) << 16);
     const bool flusher = ch == 0;
     const int64_t gi = i0 + row;
-    const float k7s2 = 2.f * k7 * sc;
+    const float k7s2 = 2.f * k7 * sc, k7s2_ln = k7s2 * INV_LN2;
     float v7 = 0.f;
     for (int k = 0; k < nt; ++k) {
       const int J = tile_of(k), b = k & 1;
@@ -263,41 +264,53 @@ k_pairs_tc(int64_t n, int tr0, const unsigned char* __restrict__ Zb, const unsig
       tc::fence_after();
       unsigned char* pl0 = sm.tile[b][0] + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
       unsigned char* pl1 = pl0 + P_PLANE;
+      // the element-wise stage is the bound of this kernel (one MUFU log2 + ~12 ALU ops per pair): interior tiles take
+      // the mask-free instantiation, 32-bit indices everywhere
+      auto convert = [&](auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        const int rel = (int)(gi - j0);             // column c of the tile is valid iff c < rel (and the row exists)
+        const bool row_ok = gi < n;
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = ch * 64 + cc * 32;
-        float s[32];
-        tc::tmem_ld32(tlane + COL_S + (uint32_t)b * 128u + (uint32_t)c0, s);
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c0 = ch * 64 + cc * 32;
+          float s[32];
+          tc::tmem_ld32(tlane + COL_S + (uint32_t)b * 128u + (uint32_t)c0, s);
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float co[8];
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float co[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int col = c0 + g8 * 8 + u;
-            const float sv = s[g8 * 8 + u] * (1.f / 1048576.f);
-            const bool valid = interior || ((j0 + col < gi) && (gi < n));
-            const float pm = fmaxf(sv, 0.f);
-            const float qq = fminf(fmaxf(pm, ENT_LO), ENT_HI);
-            const float lg = __log2f(qq);
-            v7 = valid ? fmaf(qq, lg, v7) : v7;
-            co[u] = (valid && pm >= ENT_LO && pm <= ENT_HI) ? k7s2 * (lg + INV_LN2) : 0.f;
+            for (int u = 0; u < 8; ++u) {
+              const float sv = s[g8 * 8 + u] * (1.f / 1048576.f);
+              const float qq = fminf(fmaxf(sv, ENT_LO), ENT_HI);      // = clamp(relu(sv)): ENT_LO > 0
+              const float lg = __log2f(qq);
+              const float dp = fmaf(k7s2, lg, k7s2_ln);               // 2 k7 s_c (log2 q + 1/ln 2)
+              if (INTERIOR) {
+                v7 = fmaf(qq, lg, v7);
+                co[u] = (qq == sv) ? dp : 0.f;                         // inside the clamp interval <=> q == s
+              } else {
+                const bool valid = row_ok && (c0 + g8 * 8 + u < rel);
+                v7 = valid ? fmaf(qq, lg, v7) : v7;
+                co[u] = (valid && qq == sv) ? dp : 0.f;
+              }
+            }
+            const __half2 a01 = __floats2half2_rn(co[0], co[1]), a23 = __floats2half2_rn(co[2], co[3]);
+            const __half2 a45 = __floats2half2_rn(co[4], co[5]), a67 = __floats2half2_rn(co[6], co[7]);
+            const float2 f01 = __half22float2(a01), f23 = __half22float2(a23), f45 = __half22float2(a45), f67 = __half22float2(a67);
+            const __half2 r01 = __floats2half2_rn((co[0] - f01.x) * 2048.f, (co[1] - f01.y) * 2048.f);
+            const __half2 r23 = __floats2half2_rn((co[2] - f23.x) * 2048.f, (co[3] - f23.y) * 2048.f);
+            const __half2 r45 = __floats2half2_rn((co[4] - f45.x) * 2048.f, (co[5] - f45.y) * 2048.f);
+            const __half2 r67 = __floats2half2_rn((co[6] - f67.x) * 2048.f, (co[7] - f67.y) * 2048.f);
+            const uint32_t off = (uint32_t)((c0 >> 3) + g8) * P_SJ;
+            *reinterpret_cast<uint4*>(pl0 + off) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23),
+                           *reinterpret_cast<const uint32_t*>(&a45), *reinterpret_cast<const uint32_t*>(&a67));
+            *reinterpret_cast<uint4*>(pl1 + off) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&r01), *reinterpret_cast<const uint32_t*>(&r23),
+                           *reinterpret_cast<const uint32_t*>(&r45), *reinterpret_cast<const uint32_t*>(&r67));
           }
-          const __half2 a01 = __floats2half2_rn(co[0], co[1]), a23 = __floats2half2_rn(co[2], co[3]);
-          const __half2 a45 = __floats2half2_rn(co[4], co[5]), a67 = __floats2half2_rn(co[6], co[7]);
-          const float2 f01 = __half22float2(a01), f23 = __half22float2(a23), f45 = __half22float2(a45), f67 = __half22float2(a67);
-          const __half2 r01 = __floats2half2_rn((co[0] - f01.x) * 2048.f, (co[1] - f01.y) * 2048.f);
-          const __half2 r23 = __floats2half2_rn((co[2] - f23.x) * 2048.f, (co[3] - f23.y) * 2048.f);
-          const __half2 r45 = __floats2half2_rn((co[4] - f45.x) * 2048.f, (co[5] - f45.y) * 2048.f);
-          const __half2 r67 = __floats2half2_rn((co[6] - f67.x) * 2048.f, (co[7] - f67.y) * 2048.f);
-          const uint32_t off = (uint32_t)((c0 >> 3) + g8) * P_SJ;
-          *reinterpret_cast<uint4*>(pl0 + off) =
-              make_uint4(*reinterpret_cast<const uint32_t*>(&a01), *reinterpret_cast<const uint32_t*>(&a23),
-                         *reinterpret_cast<const uint32_t*>(&a45), *reinterpret_cast<const uint32_t*>(&a67));
-          *reinterpret_cast<uint4*>(pl1 + off) =
-              make_uint4(*reinterpret_cast<const uint32_t*>(&r01), *reinterpret_cast<const uint32_t*>(&r23),
-                         *reinterpret_cast<const uint32_t*>(&r45), *reinterpret_cast<const uint32_t*>(&r67));
         }
-      }
+      };
+      if (interior) convert(std::true_type{}); else convert(std::false_type{});
       tc::fence_before();
       mbar_arrive(&sm.s_free[b]);                   // S[b] has been read
       tc::fence_async_smem();

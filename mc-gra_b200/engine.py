@@ -49,6 +49,30 @@ def shard_tile_rows(T, world):
     return [(bounds[g], bounds[g + 1]) for g in range(world)]
 
 
+class HostBands:
+    """An n x n matrix given by row bands (multi-GPU: every rank holds, and copies host -> device, only the rows it
+    touches).  `bands` maps (r0, r1) -> tensor [r1 - r0, n] (pinned host or device memory)."""
+
+    def __init__(self, n, bands):
+        self.n, self.bands = int(n), dict(bands)
+
+    def rows(self, r0, r1, device):
+        for (b0, b1), t in self.bands.items():
+            if b0 <= r0 and r1 <= b1:
+                return t[r0 - b0:r1 - b0].to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        raise KeyError(f"rows [{r0}, {r1}) are not covered by the bands {sorted(self.bands)}")
+
+    @staticmethod
+    def of(t):
+        return t if isinstance(t, HostBands) else HostBands(t.shape[0], {(0, t.shape[0]): t})
+
+
+def output_band(n, rank, world):
+    """Row band [b0, b1) of the n x n result owned by `rank`: equal 64-aligned bands (mcgra_ensemble's block height)."""
+    rb = ((n + world - 1) // world + 63) // 64 * 64
+    return min(n, rank * rb), min(n, (rank + 1) * rb)
+
+
 class PGDEngine:
     def __init__(self, n, S1, W2, b1, b2, Wl, bl, labels, idx_attack, HA, YA, feature_adj, measure, weights,
                  lr, weight_sup=1.0, num_edges=None, x0=None, device="cuda", rank=0, world=1, group=None,
@@ -98,12 +122,23 @@ class PGDEngine:
         self.meas_nn = N.M_NONE       # measure code used by the element-wise n x n kernels
         self.idx = idx
         fa = None
+        fa_row0 = 0           # first global row held by `fa` (row-band input: only this rank's tile rows are resident)
         if w1 != 0 and feature_adj is not None:
-            fa = feature_adj.to(dev)
-            # topology_attack.py:212: the term is skipped when feature_adj is constant
-            if bool(fa.max() != fa.min()):
-                self.c1_active = True
-                fa = fa.to(torch.float32).contiguous()
+            if isinstance(feature_adj, HostBands):
+                fa_row0 = self.tr0 * TILE
+                fa = feature_adj.rows(fa_row0, min(n, self.tr1 * TILE), dev)
+                mm = torch.stack([fa.max() if fa.numel() else torch.tensor(-math.inf, device=dev),
+                                  -(fa.min() if fa.numel() else torch.tensor(math.inf, device=dev))])
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+                self.c1_active = bool(mm[0] != -mm[1])
+            else:
+                fa = feature_adj.to(dev)
+                # topology_attack.py:212: the term is skipped when feature_adj is constant
+                if bool(fa.max() != fa.min()):
+                    self.c1_active = True
+                    fa = fa.to(torch.float32).contiguous()
         native_nn = (self.measure == N.M_MSE) or (self.measure == N.M_KL and w2 == 0)
         # Which engine evaluates the n x n terms c1 / c2:
         #   "native": fused element-wise kernels (MSELoss; KL when only c1 is on)
@@ -121,8 +156,10 @@ class PGDEngine:
             if self.c1_active:
                 self.Ft = torch.zeros(ntl, **f32)
                 self.Fdiag = torch.zeros(n, **f32)
-                call("mcgra_dense_to_tiles", ptr(fa), n, n, self.tr0, self.tr1, 1, ptr(self.Ft), ptr(self.Fdiag),
-                     N.stream_ptr())
+                # (row-band input: the pointer is shifted so that the kernel's global row index lands in the band; the
+                #  mirrored entries live on other ranks, so the band is taken as is instead of (F_ij + F_ji) / 2)
+                call("mcgra_dense_to_tiles", fa.data_ptr() - fa_row0 * n * 4, n, n, self.tr0, self.tr1,
+                     0 if isinstance(feature_adj, HostBands) else 1, ptr(self.Ft), ptr(self.Fdiag), N.stream_ptr())
                 if world > 1:     # each rank wrote the diagonal of its own tile rows only
                     self._allreduce(self.Fdiag)
                 self.meas_nn = self.measure
@@ -130,11 +167,19 @@ class PGDEngine:
                     self.k1 = w1 * 1000 * ALIGN["c1"] / nn2
                 else:
                     self.k1 = w1 * 1000 * ALIGN["c1"] / float(n)
-                    self.lseF64 = torch.logsumexp(fa.double(), dim=1)
+                    if isinstance(feature_adj, HostBands):
+                        self.lseF64 = torch.zeros(n, dtype=torch.float64, device=dev)
+                        self.lseF64[fa_row0:fa_row0 + fa.shape[0]] = torch.logsumexp(fa.double(), dim=1)
+                        self._allreduce(self.lseF64)
+                    else:
+                        self.lseF64 = torch.logsumexp(fa.double(), dim=1)
                     self.lseF = self.lseF64.float().contiguous()
             if w2 != 0:
                 self.k2 = w2 * 100 * ALIGN["c2"] / nn2
         elif self.nn_mode in ("kl2", "dense"):
+            if isinstance(feature_adj, HostBands):
+                raise NotImplementedError("row-band feature_adj input is implemented for the element-wise measures (MSELoss, "
+                                          "KL with w2 = 0); pass a full tensor for HSIC / CKA / DP / KL-c2")
             self.Ft = torch.zeros(ntl, **f32)      # dL/dA_ij + dL/dA_ji
             self.Ct = torch.zeros(ntl, **f32)      # dL/dM1_ij + dL/dM1_ji
             self.Fdiag = torch.zeros(n, **f32)     # dL/dA_ii

@@ -68,3 +68,51 @@ def argsort_desc(scores):
     order = torch.empty(total, dtype=torch.int64, device=s.device)
     call("mcgra_argsort_desc", ptr(s), total, ptr(order), ptr(ws), N.stream_ptr())
     return order
+
+
+def auc_ap_from_edges_sharded(scores_band, row0, n, edges, group=None):
+    """metric_pool semantics (all n^2 ordered pairs) when every rank holds a ROW BAND of the scores (rows row0 ...): the
+    positives' keys are all-gathered, every rank ranks its own negatives against the global positives (mcgra_auc_stage),
+    the integer counts are all-reduced and every rank finishes with the same AUC / AP."""
+    import torch.distributed as dist
+    dev = scores_band.device
+    rows = scores_band.shape[0]
+    world = dist.get_world_size(group)
+    e = torch.as_tensor(edges, device=dev).long()
+    lab = torch.zeros(rows, n, dtype=torch.uint8, device=dev)
+    for a, b in ((e[:, 0], e[:, 1]), (e[:, 1], e[:, 0])):
+        m = (a >= row0) & (a < row0 + rows)
+        lab[a[m] - row0, b[m]] = 1
+    npos_max = max(2 * int(e.shape[0]), 1)
+    s = scores_band.detach().reshape(-1).to(torch.float32).contiguous()
+    lab = lab.reshape(-1)
+    total = s.numel()
+    ws = torch.zeros(N.lib().mcgra_auc_workspace_bytes(max(total, 1), npos_max), dtype=torch.uint8, device=dev)
+    out = torch.zeros(4, dtype=torch.float64, device=dev)
+    st = N.stream_ptr()
+    call("mcgra_auc_stage", 0, ptr(s), ptr(lab), total, npos_max, ptr(ws), ptr(out), st)
+    counter = ws[:8].view(torch.int64)
+    keys = ws[256:256 + 4 * npos_max].view(torch.int32)
+    cnt = counter.clone()
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    allk = [torch.empty(npos_max, dtype=torch.int32, device=dev) for _ in range(world)]
+    dist.all_gather(allk, keys.clone(), group=group)
+    counts = [int(c.item()) for c in counts]
+    if sum(counts) > npos_max:
+        raise N.NativeError(f"positives {sum(counts)} exceed npos_max {npos_max}")
+    keys.fill_(-1)                       # 0xffffffff: unused slots sort to the top
+    o = 0
+    for c, k in zip(counts, allk):
+        keys[o:o + c] = k[:c]
+        o += c
+    counter.fill_(o)
+    call("mcgra_auc_stage", 1, ptr(s), ptr(lab), total, npos_max, ptr(ws), ptr(out), st)
+    ho = int(N.lib().mcgra_auc_hist_offset(npos_max))
+    hist = ws[ho:ho + 8 * (npos_max + 2)].view(torch.int64)
+    sums = ws[8:24].view(torch.int64)
+    dist.all_reduce(hist, group=group)
+    dist.all_reduce(sums, group=group)
+    call("mcgra_auc_stage", 2, ptr(s), ptr(lab), total, npos_max, ptr(ws), ptr(out), st)
+    r = out.cpu().numpy()
+    return float(r[0]), float(r[1])

@@ -22,7 +22,7 @@ from torch.nn.parameter import Parameter
 from . import _native as N
 from ._native import call, ptr
 from .base_attack import BaseAttack
-from .engine import HID, PGDEngine
+from .engine import HID, HostBands, PGDEngine, output_band
 
 Align_Parameter_Cora = {"c1": 100, "c2": 1000, "c3": 100, "c4": 10, "c5": 10, "c6": 10, "c7": 10, "c8": 0.01,
                         "c9": 1, "c10": 1}
@@ -99,6 +99,8 @@ class PGDAttack(BaseAttack):
             raise NotImplementedError("native path is built for nhid=16 (hard-coded in the reference, main.py:175)")
         if b1 is None or b2 is None or bl is None:
             raise NotImplementedError("with_bias=False victims are not supported")
+        if not getattr(victim, "with_relu", True):
+            raise NotImplementedError("with_relu=False victims are not supported (the native path hard-codes the relu)")
         if emb is not None:
             for k in range(2):   # embedding.gc = deepcopy(victim.gc) in the reference driver (main.py:185-190)
                 if not (torch.equal(emb.gc[k].weight.detach().cpu(), victim.gc[k].weight.detach().cpu())
@@ -176,7 +178,10 @@ class PGDAttack(BaseAttack):
                 YA_loop = F.log_softmax(HA_loop @ Wl.t() + bl, dim=1)
             self._const_cache = {"key": ckey, "val": (S1, HA_loop, YA_loop)}
         _mark("inputs_and_constants")
-        fa = feature_adj.to(dev) if torch.is_tensor(feature_adj) else _dense(feature_adj, dev)
+        if isinstance(feature_adj, HostBands):     # multi-GPU: every rank copies only the row bands it touches
+            fa = feature_adj
+        else:
+            fa = feature_adj.to(dev) if torch.is_tensor(feature_adj) else _dense(feature_adj, dev)
         _mark("feature_adj_h2d")
 
         rank, world = 0, 1
@@ -189,7 +194,7 @@ class PGDAttack(BaseAttack):
                                 x0=x0, device=dev, rank=rank, world=world,
                                 max_epochs=max(int(epochs), int(kwargs.get('_engine_epochs', 1)), 1))
         eng = self.engine
-        fa_on_host = not (torch.is_tensor(feature_adj) and feature_adj.is_cuda)
+        fa_on_host = not isinstance(feature_adj, HostBands) and not (torch.is_tensor(feature_adj) and feature_adj.is_cuda)
         if eng.nn_mode == "dense" and fa_on_host:
             fa = None          # the contraction stage keeps its own constant image; the dense copy returns for the ensemble
         _mark("engine_setup")
@@ -207,7 +212,10 @@ class PGDAttack(BaseAttack):
             eng.dense = None
         if fa is None:
             fa = feature_adj.to(dev) if torch.is_tensor(feature_adj) else _dense(feature_adj, dev)
-        self._finalize(eng, args, fa, labels_t, W2, b1, b2, Wl, bl)
+        if world > 1:
+            self._finalize_sharded(eng, args, fa, labels_t, W2, b1, b2, Wl, bl, gather_x=kwargs.get("_gather_x", True))
+        else:
+            self._finalize(eng, args, fa, labels_t, W2, b1, b2, Wl, bl)
         _mark("finalize")
         return 0, 0, 0, 0
 
@@ -305,8 +313,9 @@ class PGDAttack(BaseAttack):
             gram(self.Y_A.detach().to(dev))
         if args.useY:
             path = "./saved_data/" + args.dataset + ".npy"
-            if os.path.exists(path):                                      # :133-134
-                dense(torch.from_numpy(np.load(path)).to(dev))
+            lab = np.load(path, mmap_mode="r") if os.path.exists(path) else None                # :133-134
+            if lab is not None and lab.shape == (n, n):      # (a stale file of another graph size is ignored)
+                dense(torch.from_numpy(np.ascontiguousarray(lab)).to(dev))
             else:    # same matrix built from the labels (main.prepare, main.py:440-450)
                 t = ea.t[ea.nterms]
                 t.kind, t.labels = N.TERM_LABEL, ptr(labels_t)
@@ -316,6 +325,97 @@ class PGDAttack(BaseAttack):
         call("mcgra_ensemble", ptr(xf), n, _C.byref(ea), ptr(out), n, 0, n, st)
         del xf, keep
         self.modified_adj = out.detach()
+
+    def _finalize_sharded(self, eng, args, fa, labels_t, W2, b1, b2, Wl, bl, gather_x=True):
+        """topology_attack.py:300-322 with world > 1: the decoded parameter stays sharded by tile rows (its two
+        propagations are reduced across ranks like the loop's), and every rank evaluates the ensemble for ITS ROW BAND of
+        the n x n result only (`self.modified_adj` = rows [b0, b1), `self.modified_adj_rows`); `gather_modified_adj()`
+        assembles the full matrix, `metrics.auc_ap_from_edges_sharded` scores the bands in place."""
+        import ctypes as _C
+        import torch.distributed as dist
+        st = N.stream_ptr()
+        n, dev = eng.n, eng.dev
+        zf = torch.empty_like(eng.H2)
+        call("mcgra_row_normalize", ptr(eng.H2), n, HID, 2.0, ptr(zf), st)
+        xf = torch.zeros(max(eng.ntiles, 1) * N.TILE * N.TILE, dtype=torch.float32, device=dev)
+        call("mcgra_decode_to_tiles", ptr(zf), n, eng.tr0, eng.tr1, ptr(xf), st)
+        if gather_x:          # the reference leaves the full packed vector in adj_changes.data (:301)
+            packed = torch.zeros(n * (n - 1) // 2, dtype=torch.float32, device=dev)
+            call("mcgra_tiles_to_tril", ptr(xf), n, eng.tr0, eng.tr1, None, 1, ptr(packed), st)
+            dist.all_reduce(packed, group=eng.group)
+            self.adj_changes.data = packed
+        Y = torch.zeros(n, HID, dtype=torch.float32, device=dev)
+        call("mcgra_propagate", ptr(xf), n, eng.tr0, eng.tr1, None, 1, ptr(eng.S1), HID, ptr(Y), None, None, st)
+        dist.all_reduce(Y, group=eng.group)
+        H1 = torch.relu(Y + b1)
+        T2 = (H1 @ W2).contiguous()
+        Y2 = torch.zeros(n, HID, dtype=torch.float32, device=dev)
+        call("mcgra_propagate", ptr(xf), n, eng.tr0, eng.tr1, None, 1, ptr(T2), HID, ptr(Y2), None, None, st)
+        dist.all_reduce(Y2, group=eng.group)
+        del xf
+        H2 = torch.relu(Y2 + b2)
+        YA2 = F.log_softmax(H2 @ Wl.t() + bl, dim=1)
+        b0, b1_ = output_band(n, eng.rank, eng.world)
+        ea = N.EnsembleArgs()
+        keep = []
+
+        def gram(Z, variant_override=None):
+            if variant_override is None:
+                Zp, variant, rown = self._decode2_spec(Z.to(torch.float32))
+            else:
+                Zp, variant, rown = Z.to(torch.float32).contiguous(), variant_override, None
+            keep.append((Zp, rown))
+            t = ea.t[ea.nterms]
+            t.kind, t.d, t.variant, t.Z, t.rownorm = N.TERM_GRAM, int(Zp.shape[1]), variant, ptr(Zp), ptr(rown)
+            ea.nterms += 1
+
+        gram(zf, 4)                    # modified_adj = symmetric expansion of relu(zf zf^T), zero diagonal (:302)
+        gram(H1)
+        gram(H2)
+        fa_band = HostBands.of(fa).rows(b0, b1_, dev) if b1_ > b0 else torch.zeros(0, n, device=dev)
+        keep.append(fa_band)
+        t = ea.t[ea.nterms]
+        t.kind, t.dense = N.TERM_DENSE, fa_band.data_ptr() - b0 * n * 4        # global row index lands in the band
+        ea.nterms += 1
+        gram(YA2)
+        if args.useH_A:
+            gram(self.H_A.detach().to(dev))
+        if args.useY_A:
+            gram(self.Y_A.detach().to(dev))
+        if args.useY:
+            path = "./saved_data/" + args.dataset + ".npy"
+            lab_dense = None
+            if os.path.exists(path):
+                arr = np.load(path, mmap_mode="r")
+                if arr.shape == (n, n):
+                    lab_dense = torch.from_numpy(np.ascontiguousarray(arr[b0:b1_])).to(dev, torch.float32)
+            t = ea.t[ea.nterms]
+            if lab_dense is not None:
+                keep.append(lab_dense)
+                t.kind, t.dense = N.TERM_DENSE, lab_dense.data_ptr() - b0 * n * 4
+            else:
+                t.kind, t.labels = N.TERM_LABEL, ptr(labels_t)
+            ea.nterms += 1
+        out = torch.empty(max(b1_ - b0, 0), n, dtype=torch.float32, device=dev)
+        if b1_ > b0:
+            call("mcgra_ensemble", None, n, _C.byref(ea), out.data_ptr() - b0 * n * 4, n, b0, b1_, st)
+        torch.cuda.current_stream().synchronize()       # `keep` holds the operands until the launch has consumed them
+        self.modified_adj = out.detach()
+        self.modified_adj_rows = (b0, b1_)
+
+    def gather_modified_adj(self):
+        """Full n x n result on every rank from the row bands of `_finalize_sharded` (world > 1); identity otherwise."""
+        eng = self.engine
+        if eng is None or eng.world == 1:
+            return self.modified_adj
+        import torch.distributed as dist
+        n = eng.n
+        rb = output_band(n, 0, eng.world)[1]
+        mine = torch.zeros(rb, n, dtype=torch.float32, device=eng.dev)
+        mine[:self.modified_adj.shape[0]] = self.modified_adj
+        full = torch.empty(eng.world * rb, n, dtype=torch.float32, device=eng.dev)
+        dist.all_gather_into_tensor(full, mine, group=eng.group)
+        return full[:n]
 
     # ------------------------------------------------------------------------------------------------
     # stand-alone helpers of the reference class, same names and semantics

@@ -74,7 +74,7 @@ def run_native_case(d, device="cuda:0", epochs=None, trace=True, graph=True):
     torch.cuda.synchronize()
     L = model.engine.losses()
     return dict(loss=L["loss"], terms=L, x_iters=[x.cpu().numpy() for x in model._trace],
-                x_final=model.adj_changes.data.cpu().numpy(), modified_adj=model.modified_adj.cpu().numpy(),
+                x_final=model.adj_changes.data.cpu().numpy(), modified_adj=model.gather_modified_adj().cpu().numpy(),
                 model=model)
 
 

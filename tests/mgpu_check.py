@@ -41,6 +41,46 @@ def main():
         if rank == 0:
             print(f"[mgpu world={dist.get_world_size()}] {case}: rel loss err {e_loss:.2e} frac|dx|>2e-4 {frac:.2e}")
         ok &= e_loss < (1e-3 if case.startswith("kl") else 1e-4) and frac < 0.01
+    # row-band input (every rank holds only the rows of feature_adj it touches) + sharded AUC / AP against the
+    # single-process values of the full matrix
+    from mcgra_b200 import metrics
+    from mcgra_b200.engine import HostBands, TILE, output_band, shard_tile_rows
+    import helpers
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "attack_mse_all_n150.npz")))
+    n = int(d["labels"].shape[0])
+    world = dist.get_world_size()
+    T = (n + TILE - 1) // TILE
+    tr0, tr1 = shard_tile_rows(T, world)[rank]
+    fa_full = torch.from_numpy(d["feature_adj"])
+    bands = {}
+    for r0, r1 in {(tr0 * TILE, min(n, tr1 * TILE)), output_band(n, rank, world)}:
+        if r1 > r0:
+            bands[(r0, r1)] = fa_full[r0:r1].clone().pin_memory()
+    orig_from_numpy = torch.from_numpy
+    d_b = dict(d)
+    d_b["feature_adj"] = d["feature_adj"]
+    _rn = helpers.run_native_case
+
+    class _FA:       # run_native_case does torch.from_numpy(d["feature_adj"]): hand it the band object instead
+        pass
+    torch_from = torch.from_numpy
+    hb = HostBands(n, bands)
+    torch.from_numpy = lambda a: hb if a is d_b["feature_adj"] else torch_from(a)
+    try:
+        got = run_native_case(d_b, device=f"cuda:{local}")
+    finally:
+        torch.from_numpy = torch_from
+    e_loss = float(np.max(np.abs(got["loss"] - d["loss"]) / np.abs(d["loss"])))
+    e_adj = float(np.max(np.abs(got["modified_adj"] - d["modified_adj"])))
+    mdl = got["model"]
+    ee = np.argwhere(np.triu(d["adj"], 1) > 0)
+    auc_s, ap_s = metrics.auc_ap_from_edges_sharded(mdl.modified_adj, mdl.modified_adj_rows[0], n, ee)
+    real = d["adj"].reshape(-1).astype(np.float32)
+    auc_f, ap_f = O.roc_auc(real, got["modified_adj"].reshape(-1)), O.average_precision(real, got["modified_adj"].reshape(-1))
+    if rank == 0:
+        print(f"[mgpu] row-band feature_adj: rel loss err {e_loss:.2e} max|dadj| {e_adj:.2e}; sharded AUC {auc_s:.6f} / AP {ap_s:.6f} "
+              f"vs full-matrix {auc_f:.6f} / {ap_f:.6f}")
+    ok &= e_loss < 1e-4 and e_adj < 2e-3 and abs(auc_s - auc_f) < 1e-9 and abs(ap_s - ap_f) < 1e-9
     # a multi-tile case with an active budget against the oracle
     d = synthetic_case(900, 40, 5, weights={1: 0.5, 2: 0.3, 6: 2.0, 7: 3.0, 9: 1.5, 10: 50.0}, epochs=3, density=1.0,
                        mean_deg=8.0)
