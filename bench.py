@@ -193,7 +193,8 @@ def make_attack(prob, device):
         Xd = prob["X"].to(device)
         H_A = emb(Xd, adj)
         Y_A = victim(Xd, adj)
-    atk = PGDAttack(model=victim, embedding=emb, H_A=H_A, Y_A=Y_A, nnodes=n, loss_type="CE", device=device)
+    # .to(device) like the reference driver (main.py:300): adj_changes (P floats) lives on the device
+    atk = PGDAttack(model=victim, embedding=emb, H_A=H_A, Y_A=Y_A, nnodes=n, loss_type="CE", device=device).to(device)
     return atk, adj
 
 
@@ -505,11 +506,16 @@ def run_native(a):
             dist.barrier()
         t0 = time.perf_counter()
         atk.attack(args, None, 10 ** args.lr, 0, 1.0, PROFILE_W, prob["feature_adj"], 0, 0, 0, None, None, None, adj,
-                   prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=K, _gather_x=False)
+                   prob["X"], torch.zeros(1), prob["labels"], prob["idx_attack"], num_edges, 0, epochs=K, _gather_x=False,
+                   _timing=bool(os.environ.get("MCGRA_E2E_TIMING")))
+        t_att = time.perf_counter() - t0
         loss_hist = atk.engine.losses()["loss"]            # D2H of the per-iteration loss history
         auc, ap = score(atk)                               # D2H of two scalars
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if os.environ.get("MCGRA_E2E_TIMING"):
+            sys.stderr.write(f"[e2e rank {rank}] attack {t_att:.3f}s (phases {getattr(atk, '_timing', None)}), "
+                             f"losses+AUC {dt - t_att:.3f}s, total {dt:.3f}s\n")
         if world > 1:
             t = torch.tensor([dt], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

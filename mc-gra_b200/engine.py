@@ -80,6 +80,17 @@ class PGDEngine:
         if not torch.cuda.is_available():
             raise N.NativeError("mcgra_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         N.lib()
+        import time as _t
+        _dbg = bool(os.environ.get("MCGRA_E2E_TIMING"))
+        _t0 = [_t.perf_counter()]
+
+        def _tick(name):
+            if _dbg:
+                torch.cuda.synchronize()
+                now = _t.perf_counter()
+                print(f"[engine-setup rank {rank}] {name}: {now - _t0[0]:.3f}s", flush=True)
+                _t0[0] = now
+        self._tick = _tick
         dev = torch.device(device)
         self.dev, self.n, self.rank, self.world, self.group = dev, int(n), rank, world, group
         n = self.n
@@ -139,6 +150,7 @@ class PGDEngine:
                 if bool(fa.max() != fa.min()):
                     self.c1_active = True
                     fa = fa.to(torch.float32).contiguous()
+        _tick("node constants + feature_adj rows on device")
         native_nn = (self.measure == N.M_MSE) or (self.measure == N.M_KL and w2 == 0)
         # Which engine evaluates the n x n terms c1 / c2:
         #   "native": fused element-wise kernels (MSELoss; KL when only c1 is on)
@@ -209,6 +221,7 @@ class PGDEngine:
                 k.EAt, k.Ct = ptr(self.Ft), ptr(self.Ct)
                 k.k1c, k.k2c = k1c, k2c
         del fa
+        _tick("feature tiles / measure setup")
         self.k6 = -w6 * 100 * ALIGN["c6"] / nn2
         self.k7 = -w7 * ALIGN["c7"] / nn2
         self.nd_native = self.measure in (N.M_MSE, N.M_KL)
@@ -273,8 +286,10 @@ class PGDEngine:
             self.nd_mom = torch.zeros(int(N.lib().mcgra_nd_scratch_doubles(self.nclass)), dtype=torch.float64, device=dev)
             self.nd_coef = z(int(N.lib().mcgra_nd_scratch_floats(self.nclass)))
             self.nd_m = float(idx.numel())
+        _tick("state + node buffers")
         self.split_elem = True     # element-wise c1/c6 terms as a separate streaming pass (faster than fused, see DESIGN)
         self.set_parameter(x0)
+        _tick("set_parameter")
 
     # ------------------------------------------------------------------------------------------------
     def _allreduce(self, t, op=None):

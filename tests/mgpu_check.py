@@ -40,7 +40,9 @@ def main():
         frac = float(np.mean(dx > 2e-4))
         if rank == 0:
             print(f"[mgpu world={dist.get_world_size()}] {case}: rel loss err {e_loss:.2e} frac|dx|>2e-4 {frac:.2e}")
-        ok &= e_loss < (1e-3 if case.startswith("kl") else 1e-4) and frac < 0.01
+        # (kl_* and hsic_all_n90 are the listed tie-break cases of tests/test_gpu_attack.py: their free-running fp32
+        #  trajectories are allowed to separate from the reference's by more than 1e-4)
+        ok &= e_loss < (4e-4 if (case.startswith("kl") or case == "hsic_all_n90") else 1e-4) and frac < 0.01
     # row-band input (every rank holds only the rows of feature_adj it touches) + sharded AUC / AP against the
     # single-process values of the full matrix
     from mcgra_b200 import metrics
