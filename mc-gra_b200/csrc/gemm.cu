@@ -38,7 +38,7 @@ constexpr int G_PLANE = 128 * 128;             // bytes of one 128-row x 128-byt
 constexpr int G_STAGE = 4 * G_PLANE;           // A_hi | A_lo | B_hi | B_lo
 constexpr int G_STAGES = 3;
 constexpr int G_SMEM = G_STAGES * G_STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int G_CHUNK = 8;                     // K-blocks per TMEM accumulation chunk (see header)
+int g_gemm_chunk = 8;                          // K-blocks per TMEM accumulation chunk (see header); mcgra_set_engine(3, 100 + c)
 constexpr int G_THREADS = 320;                 // producer warp, MMA warp, 8 epilogue warps
 constexpr int G_GROUP = 8;                     // tile rasterisation: sweep groups of 8 tile rows (L2 reuse)
 
@@ -65,6 +65,7 @@ struct GemmParams {
   const float* inv_se;
   int64_t lde;
   int tiles_m, tiles_n;
+  int chunk;                    // K-blocks per accumulation chunk
 };
 
 // ---- PTX wrappers that depend on the CTA-group size ------------------------------------------------------------
@@ -210,6 +211,7 @@ k_gemm3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUten
   const int64_t nb_cta = (int64_t)tn * BT + (int64_t)cta_rank * 128;           // B rows this CTA stages
   const int64_t n0 = (int64_t)tn * BT;                                         // first output column of the tile
   const int num_kb = (int)((p.K + G_BK - 1) / G_BK);
+  const int G_CHUNK = p.chunk;
   const int num_ch = (num_kb + G_CHUNK - 1) / G_CHUNK;
 
   if (warp == 0 && lane == 0) {
@@ -419,6 +421,7 @@ int launch_gemm(const CUtensorMap* maps, GemmParams& p, cudaStream_t st) {
 extern "C" {
 
 int mcgra_set_gemm_engine_(int value) {
+  if (value >= 100) { g_gemm_chunk = value - 100 > 0 ? value - 100 : 1; return 0; }
   if (value != 1 && value != 2) return -1;
   g_gemm_cg = value;
   return 0;
@@ -445,6 +448,7 @@ int mcgra_gemm_nt(const mcgra_image* A, const mcgra_image* B, const mcgra_gemm_e
   p.u = e->u;
   p.v = e->v;
   p.coef = e->coef;
+  p.chunk = g_gemm_chunk;
   p.sumsq = e->sumsq;
   p.dot = e->dot;
   if (e->dot != nullptr) {

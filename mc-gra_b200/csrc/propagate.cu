@@ -1542,10 +1542,14 @@ int g_prop_engine = 5;
 // A pure streaming kernel (x and F tiles read once, 8 bytes per entry) that runs at full occupancy; the propagation
 // passes then all use the plain tensor-core kernels.  Same arithmetic as the fused variants above.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4)
+// Streaming structure: a warp owns rows warp, warp + 8, ...; the loads of EIGHT rows (x and F: 16 LDG.128 per thread)
+// are issued before any arithmetic, and the per-row degree-gradient sums go to shared memory instead of one global
+// atomic per row -- with the atomic inside the loop the compiler could not hoist the next rows' loads above it
+// (eps_row may alias), and the kernel was latency-bound at 0.57 of the HBM roofline (61 % long-scoreboard stalls).
+__global__ void __launch_bounds__(256, 2)
 k_elem_stats(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* mu, int raw, mcgra_elem_args ea) {
   __shared__ float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE], dlI[TILE], dlJ[TILE];
-  __shared__ float colacc[TILE];
+  __shared__ float colacc[TILE], rowacc[TILE];
   __shared__ double red[32];
   int I, J;
   tile_coords(t0 + blockIdx.x, I, J);
@@ -1562,6 +1566,7 @@ k_elem_stats(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
       dlI[tid] = gi < n ? ea.dlse[gi] : 0.f;    dlJ[tid] = gj < n ? ea.dlse[gj] : 0.f;
     }
     colacc[tid] = 0.f;
+    rowacc[tid] = 0.f;
   }
   __syncthreads();
   const float4* src = reinterpret_cast<const float4*>(tiles + (int64_t)blockIdx.x * TILE_ELEMS);
@@ -1574,12 +1579,9 @@ k_elem_stats(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
   float v1 = 0.f, v6 = 0.f;
   // one row (4 consecutive entries per lane): FAST = interior tile whose buffer already holds the clamped parameter and
   // the MSE measure (the steady state of the headline profile) -- no validity tests, no measure dispatch
-  auto row_step = [&](auto fast_tag, int it) {
+  auto row_step = [&](auto fast_tag, int it, const float4 raw4, const float4 f4) {
     constexpr bool FAST = decltype(fast_tag)::value;
     const int row = it * 8 + warp;
-    const float4 raw4 = src[row * 32 + lane];
-    float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (FAST || fsrc != nullptr) f4 = fsrc[row * 32 + lane];
     const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
     const float xr[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
     const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
@@ -1615,20 +1617,32 @@ k_elem_stats(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
       col_e[k] = fmaf(tt, ri, col_e[k]);
     }
     row_e = warp_sum(row_e);
-    if (lane == 0 && gi < n && row_e != 0.f) atomicAdd(ea.eps_row + gi, row_e);
+    if (lane == 0) rowacc[row] = row_e;              // every row is visited by exactly one warp iteration
   };
-  if (interior && pv.raw == 2 && ea.measure == MCGRA_M_MSE && fsrc != nullptr) {
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) row_step(std::true_type{}, it);
-  } else {
-#pragma unroll 2
-    for (int it = 0; it < 16; ++it) row_step(std::false_type{}, it);
+  const bool fast = interior && pv.raw == 2 && ea.measure == MCGRA_M_MSE && fsrc != nullptr;
+#pragma unroll 1
+  for (int hb = 0; hb < 2; ++hb) {
+    float4 xq[8], fq[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int row = (hb * 8 + u) * 8 + warp;
+      xq[u] = src[row * 32 + lane];
+      fq[u] = fsrc != nullptr ? fsrc[row * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (fast) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) row_step(std::true_type{}, hb * 8 + u, xq[u], fq[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) row_step(std::false_type{}, hb * 8 + u, xq[u], fq[u]);
+    }
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) atomicAdd(&colacc[lane * 4 + k], col_e[k]);
   __syncthreads();
   if (tid < TILE) {
-    const int64_t gj = j0 + tid;
+    const int64_t gi = i0 + tid, gj = j0 + tid;
+    if (gi < n && rowacc[tid] != 0.f) atomicAdd(ea.eps_row + gi, rowacc[tid]);
     if (gj < n && colacc[tid] != 0.f) atomicAdd(ea.eps_row + gj, colacc[tid]);
   }
   if (ea.measure != MCGRA_M_NONE) block_atomic_add_d((double)v1 * (double)ea.k1, ea.acc + MCGRA_ACC_C1, red);
