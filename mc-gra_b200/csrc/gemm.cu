@@ -22,7 +22,8 @@
 // Accumulation: the tensor core adds every MMA into its fp32 TMEM accumulator with TRUNCATION -- measured here on
 // all-positive operands: a relative bias of -4.2e-8 per MMA, i.e. -1.3e-4 at K = 16 384 and -4.2e-4 at K = 65 536 when one
 // accumulator runs over the whole K (tests/test_gpu_gemm.py::test_gemm_large_k), above the 1e-4 loss budget.  The K loop is
-// therefore cut into CHUNKS of 8 K-blocks (96 MMAs, bias <= 4e-6): the MMA warp alternates between two TMEM accumulators
+// therefore cut into CHUNKS of 16 K-blocks (192 MMAs, bias <= 8e-6; 8 K-blocks cost ~15 % at n = 65 536 because the drains
+// compete with the MMAs for TMEM bandwidth, 32 K-blocks cost nothing): the MMA warp alternates between two TMEM accumulators
 // (2 x 256 columns) and the eight epilogue warps drain each finished chunk into fp32 REGISTERS (round-to-nearest adds, 128
 // per thread) while the next chunk is being accumulated; the epilogue proper then runs from the registers.
 #include <cuda.h>
@@ -38,7 +39,7 @@ constexpr int G_PLANE = 128 * 128;             // bytes of one 128-row x 128-byt
 constexpr int G_STAGE = 4 * G_PLANE;           // A_hi | A_lo | B_hi | B_lo
 constexpr int G_STAGES = 3;
 constexpr int G_SMEM = G_STAGES * G_STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
-int g_gemm_chunk = 8;                          // K-blocks per TMEM accumulation chunk (see header); mcgra_set_engine(3, 100 + c)
+int g_gemm_chunk = 16;                         // K-blocks per TMEM accumulation chunk (see header); mcgra_set_engine(3, 100 + c)
 constexpr int G_THREADS = 320;                 // producer warp, MMA warp, 8 epilogue warps
 constexpr int G_GROUP = 8;                     // tile rasterisation: sweep groups of 8 tile rows (L2 reuse)
 
