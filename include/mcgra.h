@@ -428,6 +428,27 @@ int mcgra_smooth_node(int64_t n, const float* d, const float* rt, const float* t
 int mcgra_cross_moments_bwd(const float* X, int dx, const float* Y, int dy, const float* w, int64_t n, const double* g,
                             float* dX, float* dY, void* stream);
 
+/* ---- --measure KDE: utils.MutualInformation(sigma 0.4, num_bins B) (MC-GRA/utils.py:980-1053; call sites
+ * topology_attack.py:199-201, 212-229, 246-269) from weighted second moments of kernel-value slabs (csrc/kde.cu):
+ * kv = exp(-0.5 ((v - j * bin_step) / 0.32)^2) per column j; moments by mcgra_cross_moments(kvX, kvY, w) with sum w = 1;
+ * mcgra_kde_scalars adds weight * 2 MI / (H1 + H2) to *acc_slot and writes d/d moments (same layout) for
+ * mcgra_cross_moments_bwd; mcgra_kde_chain takes the gradient through the kernel back to the values.  On n x n operands
+ * only the first columns take part (bin_j ~ j, values in [0,1]: the kernel underflows to 0 for j >= 6): the slab helpers
+ * extract the first NB columns of A_hat / M1 and return the gradient as tiles of tile column 0.                        */
+int mcgra_kde_kv(const float* V, int64_t ldv, int d, int64_t m, float bin_step, float* kv, void* stream);
+int mcgra_kde_chain(const float* V, int64_t ldv, const float* kv, const float* gkv, int d, int64_t m, float bin_step,
+                    float* gV, int accumulate, void* stream);
+int mcgra_kde_scalars(const double* mom, int d, double m, double weight, double* acc_slot, double* gmom, void* stream);
+/* slab [n x NB] += first NB columns of A_hat from this rank's tile rows (caller zero-fills; all-reduce across ranks)     */
+int mcgra_slab_ahat(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* r, int NB,
+                    float* slab, void* stream);
+int mcgra_slab_m1(const float* zhat, int64_t n, int NB, float* slab, void* stream);
+/* gradient slab G [n x NB] -> tiles (I, 0), I in [tr0, tr1), of G_ij + G_ji; diag[i] = G_ii for the rows of those tiles */
+int mcgra_slab_to_tiles(const float* G, int64_t n, int tr0, int tr1, int NB, float* tiles, float* diag, void* stream);
+/* p2 = softmax(em Wl^T + bl) and its backward into demd (the second head of c10, topology_attack.py:259-271)           */
+int mcgra_softmax_rows(const float* em, const float* Wl, const float* bl, int64_t n, int c, float* p2, void* stream);
+int mcgra_softmax_chain(const float* gp, const float* p, const float* Wl, int64_t n, int c, float* demd, void* stream);
+
 /* ---- AUC / AP (main.metric_pool, main.py:66-75; gcn_parameterized.py:55-65) ----
  * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU,
  * every negative is ranked against them; exact integer counts => sklearn's trapezoid AUC with ties, and

@@ -151,6 +151,14 @@ _SIGS = {
                                c_fp]),
     "mcgra_smooth_node": (C.c_int, [i64, c_fp, c_fp, c_fp, c_fp, C.c_float, c_fp, c_fp, c_fp]),
     "mcgra_cross_moments_bwd": (C.c_int, [c_fp, C.c_int, c_fp, C.c_int, c_fp, i64, c_fp, c_fp, c_fp, c_fp]),
+    "mcgra_kde_kv": (C.c_int, [c_fp, i64, C.c_int, i64, C.c_float, c_fp, c_fp]),
+    "mcgra_kde_chain": (C.c_int, [c_fp, i64, c_fp, c_fp, C.c_int, i64, C.c_float, c_fp, C.c_int, c_fp]),
+    "mcgra_kde_scalars": (C.c_int, [c_fp, C.c_int, C.c_double, C.c_double, c_fp, c_fp, c_fp]),
+    "mcgra_slab_ahat": (C.c_int, [c_fp, i64, C.c_int, C.c_int, c_fp, C.c_int, c_fp, C.c_int, c_fp, c_fp]),
+    "mcgra_slab_m1": (C.c_int, [c_fp, i64, C.c_int, c_fp, c_fp]),
+    "mcgra_slab_to_tiles": (C.c_int, [c_fp, i64, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp]),
+    "mcgra_softmax_rows": (C.c_int, [c_fp, c_fp, c_fp, i64, C.c_int, c_fp, c_fp]),
+    "mcgra_softmax_chain": (C.c_int, [c_fp, c_fp, c_fp, i64, C.c_int, c_fp, c_fp]),
     "mcgra_auc_workspace_bytes": (i64, [i64, i64]),
     "mcgra_auc_ap": (C.c_int, [c_fp, c_fp, i64, i64, c_fp, c_fp, c_fp]),
     "mcgra_auc_hist_offset": (i64, [i64]),

@@ -57,6 +57,8 @@ class HostBands:
         self.n, self.bands = int(n), dict(bands)
 
     def rows(self, r0, r1, device):
+        if r1 <= r0:                      # a rank without tile rows / without a result band (more ranks than tile rows)
+            return torch.zeros(0, self.n, dtype=torch.float32, device=device)
         for (b0, b1), t in self.bands.items():
             if b0 <= r0 and r1 <= b1:
                 return t[r0 - b0:r1 - b0].to(device=device, dtype=torch.float32, non_blocking=True).contiguous()

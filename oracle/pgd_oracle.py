@@ -267,6 +267,28 @@ def dot_product(X, Y):
     return torch.norm(Y.t() @ X, p=2)
 
 
+def kde_mi(X, Y, num_bins, sigma=0.4):
+    """utils.MutualInformation(sigma, num_bins, normalize=True).forward on 2-D inputs (utils.py:980-1053): the inputs
+    broadcast to [1, m, B] against bins = linspace(0, B, B); returns the scalar the reference indexes with [0]."""
+    eps = 1e-10
+    s = 2 * sigma ** 2
+    bins = torch.linspace(0, num_bins, num_bins, dtype=X.dtype)
+
+    def marginal(v):
+        kv = torch.exp(-0.5 * ((v - bins[None, None, :]) / s).pow(2))          # [1, m, B]
+        pdf = kv.mean(dim=1)
+        return pdf / (pdf.sum(dim=1).unsqueeze(1) + eps), kv
+    p1, k1 = marginal(X)
+    p2, k2 = marginal(Y)
+    joint = torch.matmul(k1.transpose(1, 2), k2)
+    pj = joint / (joint.sum(dim=(1, 2)).view(-1, 1, 1) + eps)
+    H1 = -torch.sum(p1 * torch.log2(p1 + eps), dim=1)
+    H2 = -torch.sum(p2 * torch.log2(p2 + eps), dim=1)
+    H12 = -torch.sum(pj * torch.log2(pj + eps), dim=(1, 2))
+    mi = H1 + H2 - H12
+    return (2 * mi / (H1 + H2))[0]
+
+
 def pick_measure(name):
     if name == "HSIC":
         return linear_hsic
@@ -278,7 +300,9 @@ def pick_measure(name):
         return linear_cka
     if name == "DP":
         return dot_product
-    raise NotImplementedError("measure %s (KDE is a SURVEY 8(f) 'next' row)" % name)
+    if name == "KDE":            # topology_attack.py:199-201: num_bins = feature_adj.shape[0] for the n x n terms
+        return lambda a, b: kde_mi(a, b, a.shape[0])
+    raise NotImplementedError("measure %s" % name)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -356,12 +380,14 @@ def iteration_terms(x, prob, cfg, noise=None):
         loss = loss + c7
         terms["c7"] = c7
     if w9 != 0:                                                        # :237-258 (em_cur == em, H_A_cur == H_A2)
-        c9 = sgn * w9 * calc(H_A2[idx], em[idx]) * ALIGN["c9"]
+        calc9 = (lambda a, b: kde_mi(a, b, H_A2.shape[1])) if measure == "KDE" else calc       # :246-250
+        c9 = sgn * w9 * calc9(H_A2[idx], em[idx]) * ALIGN["c9"]
         loss = loss + c9
         terms["c9"] = c9
     if w10 != 0:                                                       # :259-272
         output2 = F.log_softmax(em @ Wt["Wl"].t() + Wt["bl"], dim=1)   # victim(X, M): its hidden state == em
-        c10 = sgn * w10 * calc(Y_A[idx], torch.softmax(output2[idx], dim=1)) * ALIGN["c10"]
+        calc10 = (lambda a, b: kde_mi(a, b, Y_A.shape[1])) if measure == "KDE" else calc      # :261-265
+        c10 = sgn * w10 * calc10(Y_A[idx], torch.softmax(output2[idx], dim=1)) * ALIGN["c10"]
         loss = loss + c10
         terms["c10"] = c10
     return loss, terms, A_hat

@@ -358,7 +358,19 @@ def main():
              lr_exp=-2, epochs=5, dataset="brazil", x0_scale=0.3),
         dict(name="mse_sub_n90", n=90, f=20, c=3, measure="MSELoss", weights=PROFILE_A, lr_exp=-2, epochs=5, nlabel=0.6,
              dataset="usair", use=(False, False, True)),
+        # --measure KDE (README Cora K={X,Y}: --w1=1000 --w6=0.01 --lr=-3 --useY, plus the other terms): utils.MutualInformation
+        # hard-codes device='cuda:0' for its bins (utils.py:990-991); the shim below drops that keyword on this CPU-only image
+        dict(name="kde_n90", n=90, f=20, c=3, measure="KDE", weights={1: 1000, 2: 500, 6: 0.01, 7: 1.0, 9: 50.0, 10: 20.0},
+             lr_exp=-2, epochs=5, use=(False, False, True), x0_scale=0.3),
+        dict(name="kde_readme_n150", n=150, f=24, c=4, measure="KDE", weights={1: 1000, 6: 0.01}, lr_exp=-3, epochs=5,
+             use=(False, False, True)),
     ]
+    _ls = torch.linspace
+
+    def _linspace_no_device(*a_, **k_):
+        k_.pop("device", None)
+        return _ls(*a_, **k_)
+    torch.linspace = _linspace_no_device
     for cs in cases:
         if a.only and a.only not in cs["name"]:
             continue
