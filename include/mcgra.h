@@ -38,7 +38,8 @@ extern "C" {
 /* measures for the n x n terms c1/c2 and the n x d terms c9/c10 (topology_attack.py:190-208) */
 enum { MCGRA_M_NONE = 0, MCGRA_M_MSE = 1, MCGRA_M_KL = 2, MCGRA_M_HSIC = 3, MCGRA_M_CKA = 4, MCGRA_M_DP = 5,
        MCGRA_M_PRE = 6 /* element-wise gradient of the n x n terms supplied as tiles (Ftiles = dL/dA_ij + dL/dA_ji,
-                          Fdiag = dL/dA_ii): used for measures whose n x n contraction is computed upstream */ };
+                          Fdiag = dL/dA_ii): used for measures whose n x n contraction is computed upstream */,
+       MCGRA_M_KDE = 7 /* host-side tag only (csrc/kde.cu stages hand MCGRA_M_PRE tiles over; the node kernels treat it as NONE) */ };
 
 /* slots of the per-iteration double-precision accumulator block `acc` (32 doubles).
  * Slots 0-15 are accumulated by the tile kernels over one rank's shard (all-reduced across ranks);

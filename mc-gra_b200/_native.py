@@ -13,7 +13,7 @@ TILE = 128
 HID = 16
 MAXC = 32
 ACC_N = 32
-M_NONE, M_MSE, M_KL, M_HSIC, M_CKA, M_DP, M_PRE = 0, 1, 2, 3, 4, 5, 6
+M_NONE, M_MSE, M_KL, M_HSIC, M_CKA, M_DP, M_PRE, M_KDE = 0, 1, 2, 3, 4, 5, 6, 7
 ACC = dict(C1=1, C2=2, C6=3, C7=4, SUMCLAMP=8, SUMSQ=9, NLL=16, C9=17, C10=18, C1D=19, C2D=20, C6D=21, C7D=22)
 
 c_fp = C.c_void_p     # device float* (passed as integer address)

@@ -23,7 +23,8 @@ from ._native import ACC, call, ptr
 
 HID = N.HID
 TILE = N.TILE
-MEASURES = {"MSELoss": N.M_MSE, "KL": N.M_KL, "HSIC": N.M_HSIC, "CKA": N.M_CKA, "DP": N.M_DP}
+MEASURES = {"MSELoss": N.M_MSE, "KL": N.M_KL, "HSIC": N.M_HSIC, "CKA": N.M_CKA, "DP": N.M_DP, "KDE": N.M_KDE}
+KDE_NB = 8      # columns of an n x n operand that reach utils.MutualInformation's kernel (bin_j ~ j, values in [0, 1]; csrc/kde.cu)
 ALIGN = {"c1": 100, "c2": 1000, "c6": 10, "c7": 10, "c9": 1, "c10": 1}      # MC-GRA/utils.py:1100-1111
 
 
@@ -121,7 +122,7 @@ class PGDEngine:
         # ---- flags -> scaled constants (topology_attack.py:151, 211-272) ----
         self.measure_name = measure
         if measure not in MEASURES:
-            raise NotImplementedError(f"measure {measure!r}: KDE is a SURVEY 8(f) 'next' row")
+            raise NotImplementedError(f"measure {measure!r}")
         self.measure = MEASURES[measure]
         w1, w2, _, _, _, w6, w7, _w8, w9, w10 = [float(w) for w in weights]
         self.w = (w1, w2, w6, w7, w9, w10)
@@ -160,7 +161,10 @@ class PGDEngine:
         #             (csrc/kl2.cu) that hand the element-wise gradient tiles to the pipeline (MCGRA_M_PRE)
         #   "dense" : HSIC / CKA / DP -- n^3 contractions on tcgen05 (dense_measure.DenseMeasure, csrc/gemm.cu), gradient
         #             tiles handed over the same way
-        self.nn_mode = "native" if native_nn else ("kl2" if self.measure == N.M_KL else "dense")
+        #   "kde"   : utils.MutualInformation -- kernel-value slabs of the first KDE_NB columns, weighted second moments
+        #             and their closed-form gradient (csrc/kde.cu), gradient tiles handed over the same way
+        self.nn_mode = "native" if native_nn else ("kl2" if self.measure == N.M_KL else
+                                                   "kde" if self.measure == N.M_KDE else "dense")
         if not (self.c1_active or w2 != 0):
             self.nn_mode = "off"
         self.w1, self.w2 = w1, w2
@@ -190,7 +194,7 @@ class PGDEngine:
                     self.lseF = self.lseF64.float().contiguous()
             if w2 != 0:
                 self.k2 = w2 * 100 * ALIGN["c2"] / nn2
-        elif self.nn_mode in ("kl2", "dense"):
+        elif self.nn_mode in ("kl2", "dense", "kde"):
             if isinstance(feature_adj, HostBands):
                 raise NotImplementedError("row-band feature_adj input is implemented for the element-wise measures (MSELoss, "
                                           "KL with w2 = 0); pass a full tensor for HSIC / CKA / DP / KL-c2")
@@ -204,6 +208,22 @@ class PGDEngine:
             if self.nn_mode == "dense":
                 from .dense_measure import DenseMeasure
                 self.dense = DenseMeasure(self, fa if self.c1_active else None, self.measure, k1c, k2c, sgn)
+            elif self.nn_mode == "kde":
+                nb = min(KDE_NB, n)
+                hi = max(float(fa.max()), 1.0) if self.c1_active else 1.0
+                if hi > 3.0:      # column j >= KDE_NB would no longer underflow: exp(-0.5 ((v - j) / 0.32)^2) > fp32 min
+                    raise NotImplementedError("KDE: feature_adj values above 3 reach bins beyond the kept columns")
+                self.kde = kd = dict(nb=nb, k1c=k1c, k2c=k2c, bin=float(n) / float(n - 1),
+                                     w=torch.full((n,), 1.0 / n, **f32),
+                                     slabA=torch.zeros(n, nb, **f32), slabM=torch.zeros(n, nb, **f32),
+                                     kvA=torch.zeros(n, nb, **f32), kvM=torch.zeros(n, nb, **f32),
+                                     gkvA=torch.zeros(n, nb, **f32), gkvM=torch.zeros(n, nb, **f32),
+                                     gA=torch.zeros(n, nb, **f32), gM=torch.zeros(n, nb, **f32),
+                                     mom=torch.zeros(2 * nb + 2 * nb * nb, dtype=torch.float64, device=dev),
+                                     gmom=torch.zeros(2 * nb + 2 * nb * nb, dtype=torch.float64, device=dev))
+                if self.c1_active:
+                    kd["kvF"] = torch.zeros(n, nb, **f32)
+                    call("mcgra_kde_kv", ptr(fa), n, nb, n, kd["bin"], ptr(kd["kvF"]), N.stream_ptr())
             else:
                 self.kl2 = k = N.Kl2Args()
                 self._kl2_keep = keep = {}
@@ -283,7 +303,21 @@ class PGDEngine:
         self.lseA = z(n) if kl_native else None
         self.dlse = z(n) if kl_native else None
 
-        if not self.nd_native and (self.w9 != 0.0 or self.w10 != 0.0):
+        if self.measure == N.M_KDE and (self.w9 != 0.0 or self.w10 != 0.0):
+            c = self.nclass
+            md = max(HID, c)
+            self.kde_nd = nd = dict(kvE=z(n, md), gkv=z(n, md), gV=z(n, md), p2=z(n, c),
+                                    mom=torch.zeros(2 * md + 2 * md * md, dtype=torch.float64, device=dev),
+                                    gmom=torch.zeros(2 * md + 2 * md * md, dtype=torch.float64, device=dev),
+                                    m=float(idx.numel()))
+            if self.w9 != 0.0:        # bins = linspace(0, 16, 16) (topology_attack.py:246-248)
+                nd["kvH"] = z(n, HID)
+                call("mcgra_kde_kv", ptr(self.HA), HID, HID, n, HID / (HID - 1.0), ptr(nd["kvH"]), N.stream_ptr())
+            if self.w10 != 0.0:       # bins = linspace(0, c, c) (:261-263)
+                nd["kvY"] = z(n, c)
+                nd["binc"] = c / (c - 1.0) if c > 1 else 0.0
+                call("mcgra_kde_kv", ptr(self.YA), c, c, n, nd["binc"], ptr(nd["kvY"]), N.stream_ptr())
+        elif not self.nd_native and (self.w9 != 0.0 or self.w10 != 0.0):
             self.nd_p2 = z(n, self.nclass)
             self.nd_mom = torch.zeros(int(N.lib().mcgra_nd_scratch_doubles(self.nclass)), dtype=torch.float64, device=dev)
             self.nd_coef = z(int(N.lib().mcgra_nd_scratch_floats(self.nclass)))
@@ -403,12 +437,17 @@ class PGDEngine:
         n, tr0, tr1, mu, raw = self.n, self.tr0, self.tr1, ptr(self.mu), self.raw
         a = self.forward_stages(t)
         ap = C.byref(a)
-        dense = self.nn_mode in ("dense", "kl2")             # gradient tiles handed over as MCGRA_M_PRE
+        dense = self.nn_mode in ("dense", "kl2", "kde")      # gradient tiles handed over as MCGRA_M_PRE
         if self.nn_mode == "dense":
             self.dense.step(t)
         elif self.nn_mode == "kl2":
             self._kl2_stage(t)
-        if not self.nd_native and (self.w9 != 0.0 or self.w10 != 0.0):
+        elif self.nn_mode == "kde":
+            self._kde_stage(t)
+        if self.measure == N.M_KDE:
+            if self.w9 != 0.0 or self.w10 != 0.0:
+                self._kde_nd_stage(t)
+        elif not self.nd_native and (self.w9 != 0.0 or self.w10 != 0.0):
             self._nd_stage(t)
         if self.k7 != 0.0 or self.k2 != 0.0 or dense:
             call("mcgra_pairs", ptr(self.xt), n, tr0, tr1, mu, raw, ptr(self.zhat), ptr(self.r),
@@ -573,6 +612,70 @@ class PGDEngine:
         self._allreduce(keep["c1row"])
         call("mcgra_kl2_node", 1, kp, ptr(self.Fdiag), self._acc_row(t).data_ptr(), st)
         call("mcgra_kl2_pass", 2, kp, st)
+
+    def _kde_mi(self, X, dx, Y, dy, w, m, weight, slot, mom, gmom, gX, gY):
+        """weight * MutualInformation(X, Y) from the kernel-value matrices X [n x d], Y [n x d] (d = dx = dy): moments,
+        entropies + d/d moments, gradient w.r.t. the kernel values (gX / gY may be None)."""
+        st = N.stream_ptr()
+        n = self.n
+        mom.zero_()
+        call("mcgra_cross_moments", ptr(X), dx, ptr(Y), dy, ptr(w), n, ptr(mom), st)
+        call("mcgra_kde_scalars", ptr(mom), dx, m, weight, slot, ptr(gmom), st)
+        call("mcgra_cross_moments_bwd", ptr(X), dx, ptr(Y), dy, ptr(w), n, ptr(gmom), ptr(gX), ptr(gY), st)
+
+    def _kde_stage(self, t):
+        """c1 / c2 under --measure KDE (topology_attack.py:199-201, 212-229; utils.py:980-1053): only the first KDE_NB
+        columns of A_hat / M1 / feature_adj reach the Gaussian bins, so the n x n x n joint pdf is an NB x NB weighted
+        second moment.  Slabs are assembled from every rank's tile rows (one all-reduce), the scalar work is replicated."""
+        st = N.stream_ptr()
+        kd, n = self.kde, self.n
+        nb, bin_ = kd["nb"], kd["bin"]
+        acc = self._acc_row(t).data_ptr()
+        kd["slabA"].zero_()
+        call("mcgra_slab_ahat", ptr(self.xt), n, self.tr0, self.tr1, ptr(self.mu), self.raw, ptr(self.r), nb,
+             ptr(kd["slabA"]), st)
+        self._allreduce(kd["slabA"])
+        call("mcgra_kde_kv", ptr(kd["slabA"]), nb, nb, n, bin_, ptr(kd["kvA"]), st)
+        first = True
+        if self.c1_active:
+            self._kde_mi(kd["kvF"], nb, kd["kvA"], nb, kd["w"], float(n), kd["k1c"], acc + 8 * ACC["C1D"], kd["mom"],
+                         kd["gmom"], None, kd["gkvA"])
+            call("mcgra_kde_chain", ptr(kd["slabA"]), nb, ptr(kd["kvA"]), ptr(kd["gkvA"]), nb, n, bin_, ptr(kd["gA"]), 0, st)
+            first = False
+        if self.w2 != 0:
+            call("mcgra_slab_m1", ptr(self.zhat), n, nb, ptr(kd["slabM"]), st)
+            call("mcgra_kde_kv", ptr(kd["slabM"]), nb, nb, n, bin_, ptr(kd["kvM"]), st)
+            self._kde_mi(kd["kvA"], nb, kd["kvM"], nb, kd["w"], float(n), kd["k2c"], acc + 8 * ACC["C2D"], kd["mom"],
+                         kd["gmom"], kd["gkvA"], kd["gkvM"])
+            call("mcgra_kde_chain", ptr(kd["slabA"]), nb, ptr(kd["kvA"]), ptr(kd["gkvA"]), nb, n, bin_, ptr(kd["gA"]),
+                 0 if first else 1, st)
+            call("mcgra_kde_chain", ptr(kd["slabM"]), nb, ptr(kd["kvM"]), ptr(kd["gkvM"]), nb, n, bin_, ptr(kd["gM"]), 0, st)
+            call("mcgra_slab_to_tiles", ptr(kd["gM"]), n, self.tr0, self.tr1, nb, ptr(self.Ct), None, st)
+        call("mcgra_slab_to_tiles", ptr(kd["gA"]), n, self.tr0, self.tr1, nb, ptr(self.Ft), None, st)
+        self.Fdiag.zero_()
+        self.Fdiag[:nb].copy_(kd["gA"][:nb, :nb].diagonal())
+
+    def _kde_nd_stage(self, t):
+        """c9 / c10 under --measure KDE (topology_attack.py:246-269): bins = 16 / nclass; gradient added to demd."""
+        st = N.stream_ptr()
+        nd, n, c = self.kde_nd, self.n, self.nclass
+        acc = self._acc_row(t).data_ptr()
+        if self.w9 != 0.0:
+            b16 = HID / (HID - 1.0)
+            kv, gkv, gV = (nd[k].view(-1)[: n * HID].view(n, HID) for k in ("kvE", "gkv", "gV"))
+            call("mcgra_kde_kv", ptr(self.em), HID, HID, n, b16, ptr(kv), st)
+            self._kde_mi(nd["kvH"], HID, kv, HID, self.wmult, nd["m"], self.w9, acc + 8 * ACC["C9"], nd["mom"], nd["gmom"],
+                         None, gkv)
+            call("mcgra_kde_chain", ptr(self.em), HID, ptr(kv), ptr(gkv), HID, n, b16, ptr(gV), 0, st)
+            self.demd.add_(gV)
+        if self.w10 != 0.0:
+            kv, gkv, gV = (nd[k].view(-1)[: n * c].view(n, c) for k in ("kvE", "gkv", "gV"))
+            call("mcgra_softmax_rows", ptr(self.em), ptr(self.Wl), ptr(self.bl), n, c, ptr(nd["p2"]), st)
+            call("mcgra_kde_kv", ptr(nd["p2"]), c, c, n, nd["binc"], ptr(kv), st)
+            self._kde_mi(nd["kvY"], c, kv, c, self.wmult, nd["m"], self.w10, acc + 8 * ACC["C10"], nd["mom"], nd["gmom"],
+                         None, gkv)
+            call("mcgra_kde_chain", ptr(nd["p2"]), c, ptr(kv), ptr(gkv), c, n, nd["binc"], ptr(gV), 0, st)
+            call("mcgra_softmax_chain", ptr(gV), ptr(nd["p2"]), ptr(self.Wl), n, c, ptr(self.demd), st)
 
     def _nd_stage(self, t):
         """c9 / c10 under HSIC / CKA / DP (n x 16 and n x c operands): weighted second moments + closed-form gradient,

@@ -32,7 +32,7 @@ def main():
         ok &= e_loss < 1e-4 and e_x < 5e-5 and e_adj < 2e-3
     # the dense-contraction measures (row-panel GEMMs + all-gather) and the KL tile passes (row statistics all-reduced):
     # sharded loss against the single-GPU golden, robust x comparison as in tests/test_gpu_attack.py
-    for case in ["hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90", "kl_all_n90", "kl_C_n150"]:
+    for case in ["hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90", "kl_all_n90", "kl_C_n150", "kde_n90", "kde_readme_n150"]:
         d = np.load(os.path.join(ROOT, "tests", "golden", f"attack_{case}.npz"))
         got = run_native_case(d, device=f"cuda:{local}")
         e_loss = float(np.max(np.abs(got["loss"] - d["loss"]) / np.abs(d["loss"])))

@@ -206,3 +206,58 @@ def test_mcgpb_penalties_from_factor_moments(name, monkeypatch):
     for g, key in ((gz, "gZ"), (gzn, "gZnext")):
         r = d[f"{name}_{key}"]
         assert np.max(np.abs(g.numpy() - r)) <= 2e-3 * np.max(np.abs(r))
+
+
+def _kde_scalars_mirror(mom, d, m, weight):
+    """Mirror of csrc/kde.cu k_kde_scalars: value and d value / d moments from mom = [s1 | s2 | Sxy | Syy] (weights sum 1)."""
+    eps, ln2 = 1e-10, float(np.log(2.0))
+    s1, s2, Sxy = mom[:d], mom[d:2 * d], mom[2 * d:2 * d + d * d]
+    fp = lambda p: -torch.log2(p + eps) - p / ((p + eps) * ln2)
+    N1, N2, NJ = eps + s1.sum(), eps + s2.sum(), eps + m * Sxy.sum()
+    p, q, pj = s1 / N1, s2 / N2, m * Sxy / NJ
+    H1, H2, H12 = -(p * torch.log2(p + eps)).sum(), -(q * torch.log2(q + eps)).sum(), -(pj * torch.log2(pj + eps)).sum()
+    Hs = H1 + H2
+    value = 2 * (Hs - H12) / Hs
+    cH, cJ = 2 * H12 / Hs ** 2, -2 / Hs
+    g = torch.zeros_like(mom)
+    g[:d] = weight * cH * (fp(p) - (fp(p) * p).sum()) / N1
+    g[d:2 * d] = weight * cH * (fp(q) - (fp(q) * q).sum()) / N2
+    g[2 * d:2 * d + d * d] = weight * cJ * m * (fp(pj) - (fp(pj) * pj).sum()) / NJ
+    return weight * value, g
+
+
+@pytest.mark.parametrize("shape", ["nn", "nd"])
+def test_kde_closed_form(shape):
+    """--measure KDE: the engine keeps the first 8 columns of an n x n operand (the others underflow in the Gaussian
+    kernel) and works from weighted second moments of the kernel values; value and gradient must equal autograd of the
+    oracle's utils.MutualInformation restatement on the full operands."""
+    g = torch.Generator().manual_seed(5)
+    if shape == "nn":
+        A, M1, _ = _operands(n=29, seed=3)
+        X, Y, bins = A.clone().requires_grad_(True), M1.clone().requires_grad_(True), 29
+        nb = 8
+    else:
+        X = torch.rand(40, 16, generator=g).requires_grad_(True)
+        Y = torch.softmax(torch.randn(40, 16, generator=g), 1).requires_grad_(True)
+        bins, nb = 16, 16
+    want = O.kde_mi(X, Y, bins) * 3.0
+    gX, gY = torch.autograd.grad(want, (X, Y))
+    m = X.shape[0]
+    step = bins / (bins - 1.0)
+    cols = torch.arange(nb, dtype=torch.float64) * step
+    xs, ys = X.detach()[:, :nb], Y.detach()[:, :nb]
+    kx, ky = torch.exp(-0.5 * ((xs - cols) / 0.32) ** 2), torch.exp(-0.5 * ((ys - cols) / 0.32) ** 2)
+    mom = torch.cat([kx.mean(0), ky.mean(0), (kx.t() @ ky / m).reshape(-1), torch.zeros(nb * nb)])
+    val, gm = _kde_scalars_mirror(mom, nb, float(m), 3.0)
+    assert abs(float(val) - float(want.detach())) <= 1e-9 * abs(float(want.detach()))
+    gS = gm[2 * nb:2 * nb + nb * nb].view(nb, nb)
+    gkx = (gm[:nb] + ky @ gS.t()) / m             # mcgra_cross_moments_bwd with w = 1/m
+    gky = (gm[nb:2 * nb] + kx @ gS) / m
+    dX = gkx * kx * (-(xs - cols) / 0.32 ** 2)    # mcgra_kde_chain
+    dY = gky * ky * (-(ys - cols) / 0.32 ** 2)
+    scale = float(gX.abs().max())
+    assert float((dX - gX[:, :nb]).abs().max()) <= 1e-8 * scale
+    assert float((dY - gY[:, :nb]).abs().max()) <= 1e-8 * max(float(gY.abs().max()), 1e-30)
+    if shape == "nn":        # the dropped columns carry no gradient
+        assert float(gX[:, nb:].abs().max()) <= 1e-12 * scale
+        assert float(gY[:, nb:].abs().max()) <= 1e-12 * float(gY.abs().max())

@@ -102,6 +102,7 @@ MULTI = [
     ("HSIC", {1: 0.01, 2: 0.01, 6: 10000, 7: 100, 9: 0.001, 10: 1000}, -2.5, "cora"),          # Profile B, c1 active
     ("CKA", {1: 0.01, 2: 0.01, 6: 100, 7: 1.0, 9: 1.0, 10: 1.0}, -2.0, "cora"),
     ("DP", {1: 1e-3, 2: 1e-3, 6: 10, 7: 1.0, 9: 0.1, 10: 1.0}, -2.0, "cora"),
+    ("KDE", {1: 1000, 2: 500, 6: 0.01, 7: 1.0, 9: 50.0, 10: 20.0}, -2.0, "cora"),     # utils.MutualInformation on every term
 ]
 
 
