@@ -13,7 +13,7 @@ from helpers import run_native_case
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SUPPORTED = ["mse_A_n37", "mse_A_n150", "mse_all_n150", "mse_budget_n150", "mse_nosup_n90", "mse_sub_n90",
-             "kl_C_n150", "kl_all_n90", "hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90"]
+             "kl_C_n150", "kl_all_n90", "hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90", "kde_n90", "kde_readme_n150"]
 
 
 # Cases whose FREE-RUNNING fp32 trajectory is allowed to separate from the reference's by more than 1e-4 in the loss:
@@ -22,11 +22,14 @@ SUPPORTED = ["mse_A_n37", "mse_A_n150", "mse_all_n150", "mse_budget_n150", "mse_
 # cases the loss of iteration t is checked against the fp64 oracle evaluated AT THE NATIVE PARAMETER of iteration t
 # ("float64 re-evaluation as tie-breaker").  Every other case must meet 1e-4 against the golden loss directly;
 # the branch each case takes is printed (pytest -s / the committed profiles/r02_parity_branches.log).
-TIEBREAK = {"kl_C_n150", "kl_all_n90", "hsic_all_n90"}
+# kde_*: the reference's fp32 MutualInformation (H1 + H2 - H12 from fp32 log2 sums) is itself 1e-4 .. 1.1e-3 away from
+# its fp64 evaluation at the SAME parameter (tests/test_oracle_golden.py::test_kde_reference_fp32_is_off_its_fp64); the
+# native path forms the entropies in fp64 from fp32 moments, so it is held to 1e-4 against the fp64 oracle instead.
+TIEBREAK = {"kl_C_n150", "kl_all_n90", "hsic_all_n90", "kde_n90", "kde_readme_n150"}
 # tie-break tolerance: KL over n x n rows is a ~600:1 cancellation (sum_j X_ij (F_ij - A_ij) ~ 0.6 against
 # lseF_i - lseA_i ~ 0.6 for a row KL of ~1e-3): the reference's own fp32 loss is 1.5e-4 from its fp64 evaluation there
-TIEBREAK_RTOL = {"kl_C_n150": 4e-4, "kl_all_n90": 4e-4, "hsic_all_n90": 1e-4}
-X_ROBUST = {"kl_C_n150", "kl_all_n90", "hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90"}
+TIEBREAK_RTOL = {"kl_C_n150": 4e-4, "kl_all_n90": 4e-4, "hsic_all_n90": 1e-4, "kde_n90": 1e-4, "kde_readme_n150": 1e-4}
+X_ROBUST = {"kl_C_n150", "kl_all_n90", "hsic_B_n150", "hsic_all_n90", "cka_n90", "dp_n90", "kde_n90", "kde_readme_n150"}
 
 
 @pytest.mark.parametrize("case", SUPPORTED)

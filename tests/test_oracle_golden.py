@@ -183,3 +183,17 @@ def test_polblogs_hsic_reference_is_noise_dominated():
     assert np.all(g64 > 3999) and np.all(g64 < 4001)
     agree = float(np.mean(np.sign(g32) == np.sign(g64)))
     assert agree < 0.8, agree
+
+
+@pytest.mark.parametrize("case", ["kde_n90", "kde_readme_n150"])
+def test_kde_reference_fp32_is_off_its_fp64(case):
+    """Evidence for listing the KDE cases as tie-break cases in tests/test_gpu_attack.py: the reference's own fp32 loss
+    differs from the fp64 evaluation of the same formula AT THE SAME parameter by more than the 1e-4 parity tolerance at
+    some iteration (entropy differences formed from fp32 log2 sums), so 1e-4 against the fp32 fixture is not a
+    meaningful bar for any other fp32 implementation; the GPU test holds the native path to 1e-4 against fp64."""
+    d = np.load(os.path.join(GOLDEN, f"attack_{case}.npz"))
+    prob, cfg = O.problem_from_npz(d, dtype=torch.float64)
+    xs = [d["x0"]] + list(d["x_iters"][:-1])
+    f64 = np.array([float(O.iteration_terms(torch.from_numpy(np.asarray(x)).double(), prob, cfg)[0]) for x in xs])
+    rel = np.abs(f64 - d["loss"]) / np.abs(d["loss"])
+    assert rel.max() > 0.9e-4 and rel.max() < 5e-3
