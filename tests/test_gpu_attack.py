@@ -107,10 +107,10 @@ def test_multi_tile_matches_oracle(n, weights, density):
     np.testing.assert_allclose(got["modified_adj"], ref["modified_adj"].numpy(), rtol=1e-3, atol=1e-3)
 
 
-DEFAULT_ENGINE = {0: 5, 1: 2, 2: 2}      # propagate: tcgen05 fp16x2 (v5); fold: tcgen05; pairs: tcgen05 (entropy-only) / mma.sync
+DEFAULT_ENGINE = {0: 5, 1: 2, 2: 2}      # propagate: tcgen05 fp16x2 (v5); fold: tcgen05 (one tile per CTA); pairs: tcgen05 (entropy-only) / mma.sync
 
 
-@pytest.mark.parametrize("which,eng", [(0, 1), (0, 4), (0, 5), (1, 1), (1, 2), (2, 1)])
+@pytest.mark.parametrize("which,eng", [(0, 1), (0, 4), (0, 5), (1, 1), (1, 2), (1, 3), (1, 4), (2, 1)])
 def test_engines_agree(which, eng):
     """exact-fp32 FFMA engine (v1) vs the tensor-core engines (mma.sync 3xTF32, tcgen05 3xTF32) of propagate (0) /
     fold (1) / pairs (2) on the same inputs."""
@@ -125,6 +125,32 @@ def test_engines_agree(which, eng):
         N.lib().mcgra_set_engine(which, DEFAULT_ENGINE[which])
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=2e-6)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
+
+
+@pytest.mark.parametrize("eng", [3, 4])
+@pytest.mark.parametrize("density,grid", [(1e7, 5), (1e7, 0), (1.0, 7)])
+def test_fold_persistent_engine_multi_tile(eng, density, grid):
+    """fold engines 3 / 4 (persistent, warp-specialised: bulk-copy operand ring, MMA of tile k + 1 under the stream of
+    tile k, rolling prefetch across tiles) against engine 2 (one tile per CTA) with several tiles per CTA: n = 1500
+    (78 tiles) on a grid capped to 5 / 7 CTAs and n = 1500 uncapped; density 1e7 = fast path from the second
+    iteration (clamped store), density 1 = budget binds (generic path, lazy projection)."""
+    from helpers import synthetic_case
+    from mcgra_b200 import _native as N
+    d = synthetic_case(1500, 40, 5, weights={1: 0.01, 6: 10.0, 7: 10.0, 9: 10.0, 10: 1000.0}, epochs=4, density=density,
+                       mean_deg=8.0)
+    try:
+        N.lib().mcgra_set_engine(1, 2)
+        a = run_native_case(d)
+        N.lib().mcgra_set_engine(1, eng)
+        N.lib().mcgra_set_engine(1, 100 + grid)
+        b = run_native_case(d)
+    finally:
+        N.lib().mcgra_set_engine(1, 100)
+        N.lib().mcgra_set_engine(1, DEFAULT_ENGINE[1])
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)
+    # (not bit-equal: the degree row sums and the norm term are accumulated with float / double atomics in tile order)
+    assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-6
+    np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-5, atol=5e-6)
 
 
 @pytest.mark.parametrize("n,f,epochs", [(150, 24, 4), (1300, 40, 2), (4500, 32, 2)])
