@@ -351,63 +351,6 @@ __device__ __forceinline__ float sqrt_approx(float v) {
 __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4_stream(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 
-template <int MEAS, bool ENT, int NR, bool CS, typename SM>
-__device__ __forceinline__ void fold_rows_fast(SM& sm, const FastConst& fc, float* __restrict__ xt, float* __restrict__ mt,
-                                               float* __restrict__ vt, const int* a, int b0, const float4* x4,
-                                               const float4* m4, const float4* v4, const float4* f4, const float* rj4,
-                                               const float* rhoj4, float& s_sq, float* colp, float* rowpart_lane) {
-  // NR rows at once: 4 NR independent element chains in one basic block (ALU / MUFU latencies overlap)
-  float ri[NR], rhoi[NR];
-  float4 g4[NR];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    ri[r] = sm.rI[a[r]];
-    rhoi[r] = sm.rhoI[a[r]];
-    g4[r] = ld4(&sm.u.gt[a[r]][b0]);
-  }
-  float xo[NR][4], mo[NR][4], vo[NR][4];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const float xs[4] = {x4[r].x, x4[r].y, x4[r].z, x4[r].w};
-    const float ms[4] = {m4[r].x, m4[r].y, m4[r].z, m4[r].w};
-    const float vs[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
-    const float fs[4] = {f4[r].x, f4[r].y, f4[r].z, f4[r].w};
-    const float gs[4] = {g4[r].x, g4[r].y, g4[r].z, g4[r].w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float rirj = ri[r] * rj4[k];
-      const float ah = rirj * xs[k];
-      float esym = 0.f;
-      if (MEAS == MCGRA_M_MSE) esym = fc.k1x4 * (ah - fs[k]);
-      else if (MEAS == MCGRA_M_PRE) esym = fs[k];
-      if (ENT && ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(fc.k6x2, __log2f(ah) + INV_LN2, esym);
-      float gg = fmaf(rirj, esym, rhoi[r] + rhoj4[k] + gs[k]);
-      gg = fmaf(fc.norm_scale, xs[k], gg);
-      const float mn = fmaf(fc.omb1, gg - ms[k], ms[k]);
-      const float vn = fmaf(fc.omb2, gg * gg - vs[k], vs[k]);
-      const float denom = fmaf(sqrt_approx(vn), fc.inv_sqrt_bc2, fc.adam_eps);
-      const float c = __saturatef(fmaf(fc.neg_step, __fdividef(mn, denom), xs[k]));
-      xo[r][k] = c; mo[r][k] = mn; vo[r][k] = vn;
-      s_sq = fmaf(c, c, s_sq);
-      colp[k] += c;
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const int off = a[r] * TILE + b0;
-    if (CS) {
-      st4_stream(xt + off, make_float4(xo[r][0], xo[r][1], xo[r][2], xo[r][3]));
-      st4_stream(mt + off, make_float4(mo[r][0], mo[r][1], mo[r][2], mo[r][3]));
-      st4_stream(vt + off, make_float4(vo[r][0], vo[r][1], vo[r][2], vo[r][3]));
-    } else {
-      *reinterpret_cast<float4*>(xt + off) = make_float4(xo[r][0], xo[r][1], xo[r][2], xo[r][3]);
-      *reinterpret_cast<float4*>(mt + off) = make_float4(mo[r][0], mo[r][1], mo[r][2], mo[r][3]);
-      *reinterpret_cast<float4*>(vt + off) = make_float4(vo[r][0], vo[r][1], vo[r][2], vo[r][3]);
-    }
-    rowpart_lane[a[r] * 33] = (xo[r][0] + xo[r][1]) + (xo[r][2] + xo[r][3]);
-  }
-}
-
 // Streaming epilogue of a one-tile-per-CTA engine: 8 warps, UNR rows in flight per warp.
 template <bool FAST, int MEAS, bool ENT, typename SM>
 __device__ __forceinline__ void fold_stream(SM& sm, const mcgra_fold_args& fa, const ParamView& pv,
@@ -791,28 +734,35 @@ k_fold_tc(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// v4 engine (default): persistent + warp-specialised.  One CTA per SM walks the blocked tile order with stride gridDim.x.
-//   warp 0      operand producer: two cp.async.bulk copies per K-quarter (the pre-formatted factor blocks are contiguous)
-//               into a 2-stage shared-memory ring, completion on mbarriers
-//   warp 1      tcgen05.mma issuer: the rank-128 product of tile k+1 goes into the second TMEM accumulator (2 x 256
-//               columns) while tile k streams
-//   warps 2-17  drain the accumulator to shared memory (coalescing transpose), then stream x', m, v, F rows through
-//               fold_row with a rolling register prefetch (WS_UNR rows per warp always in flight) that crosses tile
-//               boundaries, so that neither the operand staging nor the tile switch interrupts the HBM stream
+// v4 engine: persistent, warp-specialised, row-run schedule.  What bounds the one-tile-per-CTA engine is not HBM but the
+// factor-operand traffic from L2 (2 x 131 KB per 64 KB tile; tools/stream7.cu: the same stream runs at 6.5 TB/s without it
+// and at 4.9 TB/s with it), so this engine halves it and takes the staging off the streaming warps:
+//   * every CTA walks a contiguous run of tiles in storage (row-major) order; the A operand (factor rows of tile row I,
+//     [hi | lo] tf32 planes) stays RESIDENT IN TENSOR MEMORY (2 x 128 columns) for the whole run of that row, only the
+//     B block of tile column J is staged per tile (cp.async.bulk, 2-stage ring of K-quarters)
+//   * x', m, v, F reach the streaming warps through a 5-stage cp.async.bulk ring in shared memory (8 tile rows per
+//     stage), so no registers are spent on prefetch and 16 streaming warps fit; results go back with coalesced stores
+//   * the product of tile k + 1 is formed while tile k streams (single accumulator: it is free once drained)
+//   warp 0 stream producer | warp 1 B producer | warp 2 MMA issuer + TMEM owner | warp 3 idle | warps 4-19 consumers
+// Taken when the launch is "fast" (buffer holds the clamped parameter, clamped store, MSE / precomputed / no c1 term);
+// everything else runs on k_fold_tc.
 // ---------------------------------------------------------------------------------------------------------
-// template parameters: CW = consumer (streaming) warps (8 or 16), UNR = rows per warp in flight
+constexpr int RS_S = 5;                        // stream ring stages
+constexpr int RS_R = 8;                        // tile rows per stage
+constexpr int RS_CH = RS_R * TILE;             // floats per array per stage
+constexpr int RS_CW = 16;                      // consumer warps: warp cw -> row cw / 2 of a stage, column half cw % 2
+constexpr int RS_THREADS = 128 + RS_CW * 32;   // 640
+constexpr uint32_t RS_COL_AH = 256, RS_COL_AL = 384;   // TMEM columns: D [0, 256), A_hi [256, 384), A_lo [384, 512)
 
-struct FoldWsSmem {
-  struct { unsigned char a[8 * WSLAB]; unsigned char b[8 * WSLAB]; } op[2];
-  struct { float gt[TILE][G_LD]; } u;
-  float zI[TILE][HID + 1];
-  float zJt[HID][TILE + 4];
+struct FoldRsSmem {
+  float ring[RS_S][4][RS_CH];                  // x', m, v, F
+  struct { float gt[TILE][G_LD]; } u;          // product tile (rank part of the gradient)
+  unsigned char bop[2][8 * WSLAB];             // B operand ring: one K-quarter (8 slabs) per stage
   float rI[TILE], rJ[TILE], rhoI[TILE], rhoJ[TILE];
-  float lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE];
-  float nxt[4][TILE];                      // r_I, r_J, rho_I, rho_J of the next tile (prefetched during the stream)
-  float colacc[TILE];
-  double dsum[2];                          // CTA totals: sum clamp(x), sum clamp(x)^2
-  uint64_t full[2], empty[2], dfull, dempty;
+  float nxt[4][TILE];                          // the same four vectors of the next tile
+  float rowacc[TILE], colacc[TILE];
+  double dsum[2];
+  uint64_t sfull[RS_S], sempty[RS_S], bfull[2], bempty[2], dfull, dempty;
   uint32_t tmem_base;
 };
 
@@ -840,345 +790,314 @@ __device__ __forceinline__ void ws_wait_backoff(uint64_t* bar, uint32_t parity) 
         : "r"(tc::smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(128);
+    __nanosleep(64);
   }
 }
-__device__ __forceinline__ void ws_bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          tc::smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-template <int NT>
-__device__ __forceinline__ void ws_cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+__device__ __forceinline__ void rs_cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RS_CW * 32) : "memory"); }
 
-// MODE: 0 = MSE + entropy, 1 = MSE, 2 = precomputed tiles (M_PRE), 3 = no c1 term -- interior tiles take the matching
-// fold_row<true, ...> with the rolling prefetch; every other tile (and MODE 4: parameter views other than raw == 2, KL,
-// c2, plain GD, upstream tiles) takes the generic fold_row with plain loads
-template <int MODE, int WS_CW, int WS_UNR, int PAIR, bool CS>
-__global__ void __launch_bounds__(64 + WS_CW * 32, 1)
-k_fold_ws(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int tr0, int tr1, int ntiles,
-          const float* mu, int raw, const __grid_constant__ mcgra_fold_args fa, float* __restrict__ minmax,
-          const unsigned char* __restrict__ Wk, int dbg) {
+// tile run iterator: storage (row-major triangle) order inside the shard of tile rows [tr0, tr1)
+struct RunIter {
+  int I, J;
+  __device__ __forceinline__ void init(int tr0, int64_t tix) { tile_coords(tri((int64_t)tr0) + tix, I, J); }
+  __device__ __forceinline__ void next() {
+    if (++J > I) { ++I; J = 0; }
+  }
+};
+
+// MEAS: MCGRA_M_MSE / MCGRA_M_PRE / MCGRA_M_NONE; ENT: entropy term on
+template <int MEAS, bool ENT>
+__global__ void __launch_bounds__(RS_THREADS, 1)
+k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int tr0, int64_t ntiles,
+          const __grid_constant__ mcgra_fold_args fa, const unsigned char* __restrict__ Wk) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  FoldWsSmem& sm = *reinterpret_cast<FoldWsSmem*>(smem_raw);
-  constexpr int WS_NIT = TILE / (WS_CW * WS_UNR);
-#define LD4S(p) (CS ? ld4_stream(p) : ld4(p))
+  FoldRsSmem& sm = *reinterpret_cast<FoldRsSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b = blockIdx.x + k gridDim.x
+  const int64_t t_begin = (int64_t)blockIdx.x * ntiles / gridDim.x;
+  const int64_t t_end = (int64_t)(blockIdx.x + 1) * ntiles / gridDim.x;
+  const int my_tiles = (int)(t_end - t_begin);
+  constexpr bool USE_F = MEAS != MCGRA_M_NONE;
+  constexpr uint32_t STAGE_BYTES = (USE_F ? 4u : 3u) * RS_CH * 4u;
 
   if (tid == 0) {
+    for (int s = 0; s < RS_S; ++s) {
+      tc::mbar_init(&sm.sfull[s], 1);
+      tc::mbar_init(&sm.sempty[s], RS_CW);
+    }
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&sm.full[s], 1);
-      tc::mbar_init(&sm.empty[s], 1);
+      tc::mbar_init(&sm.bfull[s], 1);
+      tc::mbar_init(&sm.bempty[s], 1);
     }
     tc::mbar_init(&sm.dfull, 1);
-    tc::mbar_init(&sm.dempty, WS_CW);
+    tc::mbar_init(&sm.dempty, RS_CW);
     sm.dsum[0] = 0.0;
     sm.dsum[1] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tc::tmem_alloc(&sm.tmem_base, 256);
-  if (tid < TILE) sm.colacc[tid] = 0.f;
+  if (warp == 2) tc::tmem_alloc(&sm.tmem_base, 512);
+  if (tid < TILE) { sm.colacc[tid] = 0.f; sm.rowacc[tid] = 0.f; }
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
   const uint32_t tm = sm.tmem_base;
 
   if (warp == 0) {
-    // ================= operand producer =================
+    // ================= stream producer: x', m, v, F rows of every tile of the run, 8 rows per stage =================
     if (lane == 0) {
-      const uint64_t keep = tc::l2_policy_evict_last();     // the factor blocks are re-read by every CTA of a tile row / column
-      uint32_t cnt = 0;
+      uint32_t s = 0, ph = 0;
       for (int k = 0; k < my_tiles; ++k) {
-        int I, J;
-        int64_t tix;
-        tile_coords_blocked((int64_t)blockIdx.x + (int64_t)k * gridDim.x, tr0, tr1, 8, I, J, tix);
-        const unsigned char* blkA = Wk + (int64_t)I * WBLOCK;
-        const unsigned char* blkB = Wk + (int64_t)J * WBLOCK;
+        const int64_t base = (t_begin + k) * (int64_t)TILE_ELEMS;
 #pragma unroll 1
-        for (int qd = 0; qd < 4; ++qd, ++cnt) {
-          const uint32_t s = cnt & 1u;
-          if (dbg & 4) tc::mbar_wait(&sm.empty[s], ((cnt >> 1) & 1u) ^ 1u);
-          else ws_wait_backoff(&sm.empty[s], ((cnt >> 1) & 1u) ^ 1u);
-          ws_expect_tx(&sm.full[s], 2u * 8u * WSLAB);
-          if (dbg & 2) {
-            ws_bulk_g2s(sm.op[s].a, blkA + (uint32_t)(8 * qd) * WSLAB, 8u * WSLAB, &sm.full[s]);
-            ws_bulk_g2s(sm.op[s].b, blkB + (uint32_t)((8 * qd + 16) & 31) * WSLAB, 8u * WSLAB, &sm.full[s]);
-          } else {
-            ws_bulk_g2s_hint(sm.op[s].a, blkA + (uint32_t)(8 * qd) * WSLAB, 8u * WSLAB, &sm.full[s], keep);
-            ws_bulk_g2s_hint(sm.op[s].b, blkB + (uint32_t)((8 * qd + 16) & 31) * WSLAB, 8u * WSLAB, &sm.full[s], keep);
-          }
+        for (int ch = 0; ch < TILE / RS_R; ++ch) {
+          ws_wait_backoff(&sm.sempty[s], ph ^ 1u);
+          const int64_t o = base + (int64_t)ch * RS_CH;
+          ws_expect_tx(&sm.sfull[s], STAGE_BYTES);
+          ws_bulk_g2s(sm.ring[s][0], tiles + o, RS_CH * 4u, &sm.sfull[s]);
+          ws_bulk_g2s(sm.ring[s][1], mbuf + o, RS_CH * 4u, &sm.sfull[s]);
+          ws_bulk_g2s(sm.ring[s][2], vbuf + o, RS_CH * 4u, &sm.sfull[s]);
+          if (USE_F) ws_bulk_g2s(sm.ring[s][3], fa.Ftiles + o, RS_CH * 4u, &sm.sfull[s]);
+          if (++s == RS_S) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
+    // ================= B operand producer: factor block of tile column J, V|U order, one K-quarter per stage =========
+    if (lane == 0) {
+      RunIter it;
+      it.init(tr0, t_begin);
+      uint32_t cnt = 0;
+      for (int k = 0; k < my_tiles; ++k, it.next()) {
+        const unsigned char* blkB = Wk + (int64_t)it.J * WBLOCK;
+#pragma unroll 1
+        for (int qd = 0; qd < 4; ++qd, ++cnt) {
+          const uint32_t s = cnt & 1u;
+          ws_wait_backoff(&sm.bempty[s], ((cnt >> 1) & 1u) ^ 1u);
+          ws_expect_tx(&sm.bfull[s], 8u * WSLAB);
+          ws_bulk_g2s(sm.bop[s], blkB + (uint32_t)((8 * qd + 16) & 31) * WSLAB, 8u * WSLAB, &sm.bfull[s]);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= MMA issuer: D = A (TMEM-resident factor rows of tile row I) x B^T =================
     if (lane == 0) {
       const uint32_t id_cat = tc::make_idesc_tf32(128, 256, 0, 0);
       const uint32_t id_lo = tc::make_idesc_tf32(128, 128, 0, 0);
       uint32_t cnt = 0;
       for (int k = 0; k < my_tiles; ++k) {
-        // the accumulator is free as soon as the consumers have drained tile k - 1 (at the START of its stream phase), so
-        // the product of tile k is formed while tile k - 1 streams
-        if (dbg & 4) tc::mbar_wait(&sm.dempty, (uint32_t)(k & 1) ^ 1u);
-        else ws_wait_backoff(&sm.dempty, (uint32_t)(k & 1) ^ 1u);
+        // phase k of dempty: the consumers have drained tile k - 1 and (re)loaded A when the tile row changed
+        ws_wait_backoff(&sm.dempty, (uint32_t)(k & 1));
         tc::fence_after();
 #pragma unroll 1
         for (int qd = 0; qd < 4; ++qd, ++cnt) {
           const uint32_t s = cnt & 1u;
-          if (dbg & 4) tc::mbar_wait(&sm.full[s], (cnt >> 1) & 1u);
-          else ws_wait_backoff(&sm.full[s], (cnt >> 1) & 1u);
+          ws_wait_backoff(&sm.bfull[s], (cnt >> 1) & 1u);
           tc::fence_after();
-          const uint32_t as = tc::smem_u32(sm.op[s].a), bs = tc::smem_u32(sm.op[s].b);
+          const uint32_t bs = tc::smem_u32(sm.bop[s]);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t a_hi = tc::make_desc(as + (uint32_t)ks * 2u * WSLAB, WSLAB, 128u);
-            const uint64_t a_lo = tc::make_desc(as + (uint32_t)ks * 2u * WSLAB + 2048u, WSLAB, 128u);
+            const uint32_t kk = (uint32_t)(qd * 4 + ks);
             const uint64_t bd = tc::make_desc(bs + (uint32_t)ks * 2u * WSLAB, WSLAB, 128u);
-            tc::mma_tf32(tm, a_hi, bd, id_cat, (qd > 0 || ks > 0) ? 1u : 0u);
-            tc::mma_tf32(tm, a_lo, bd, id_lo, 1u);
+            tc::mma_tf32_ts(tm, tm + RS_COL_AH + kk * 8u, bd, id_cat, kk > 0 ? 1u : 0u);
+            tc::mma_tf32_ts(tm, tm + RS_COL_AL + kk * 8u, bd, id_lo, 1u);
           }
-          tc::mma_commit(&sm.empty[s]);                 // operand stage free once these MMAs have read it
+          tc::mma_commit(&sm.bempty[s]);
         }
-        tc::mma_commit(&sm.dfull);                      // accumulator of tile k complete
+        tc::mma_commit(&sm.dfull);
       }
     }
-  } else {
-    // ================= consumers: drain + stream =================
-    const int cw = warp - 2, ct = tid - 64;             // consumer warp / thread index
-    const int64_t n = fa.n;
-    const ParamView pv = load_view(mu, raw);
-    EpiConst ec;
+  } else if (warp >= 4) {
+    // ================= consumers =================
+    const int cw = warp - 4, ct = tid - 128;
+    const int64_t n = fa.n, np = fa.npad;
+    FastConst fc;
     {
       const double sumsq_prev = fa.acc_prev[MCGRA_ACC_SUMSQ];
       const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
       const int adam_step = fa.step_ptr != nullptr ? (*fa.step_ptr + 1) : fa.step;
       const double bc1 = 1.0 - pow((double)fa.beta1, (double)adam_step);
       const double bc2 = 1.0 - pow((double)fa.beta2, (double)adam_step);
-      ec.step_size = (float)((double)fa.lr / bc1);
-      ec.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-      ec.omb1 = 1.f - fa.beta1;
-      ec.omb2 = 1.f - fa.beta2;
-      ec.norm_scale = fa.norm_coef * inv_norm;
+      fc.neg_step = -(float)((double)fa.lr / bc1);
+      fc.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+      fc.omb1 = 1.f - fa.beta1;
+      fc.omb2 = 1.f - fa.beta2;
+      fc.norm_scale = fa.norm_coef * inv_norm;
+      fc.k1x4 = 4.f * fa.k1;
+      fc.k6x2 = 2.f * fa.k6;
+      fc.adam_eps = fa.adam_eps;
     }
-    FastConst fc;
-    fc.k1x4 = 4.f * fa.k1; fc.k6x2 = 2.f * fa.k6; fc.norm_scale = ec.norm_scale; fc.omb1 = ec.omb1; fc.omb2 = ec.omb2;
-    fc.inv_sqrt_bc2 = ec.inv_sqrt_bc2; fc.adam_eps = fa.adam_eps; fc.neg_step = -ec.step_size;
-    const bool use_f = fa.Ftiles != nullptr && fa.measure != MCGRA_M_NONE;
-    const int b0 = lane * 4;
-    const int lofs = cw * TILE + b0;                    // this lane's offset inside a group of WS_CW rows
-    // per-lane row sums of a fast tile (k2 == 0 on that path: the z buffers are free); rowpart[a][lane], row stride 33
-    static_assert(sizeof(sm.zI) + sizeof(sm.zJt) >= TILE * 33 * sizeof(float), "rowpart alias");
-    float* rowpart = &sm.zI[0][0];
-    float* rowpart_lane = rowpart + lane;
+    const int qq = cw & 3;                               // TMEM lane quarter of this warp (= warp % 4)
+    const int rw = cw >> 1, b0 = (cw & 1) * 64 + lane * 2;   // stage row / first column of this lane
+    RunIter cur;
+    cur.init(tr0, t_begin);
 
-    float xmin = INFINITY, xmax = -INFINITY;
-    int I, J, tix;
-    {
-      int64_t t64;
-      tile_coords_blocked(blockIdx.x, tr0, tr1, 8, I, J, t64);
-      tix = (int)t64;
-    }
-    if (ct < TILE) {                                    // node constants of the first tile
-      const int64_t gi = (int64_t)I * TILE + ct, gj = (int64_t)J * TILE + ct;
-      sm.nxt[0][ct] = gi < n ? fa.r[gi] : 0.f;
-      sm.nxt[1][ct] = gj < n ? fa.r[gj] : 0.f;
-      sm.nxt[2][ct] = gi < n ? fa.rho[gi] : 0.f;
-      sm.nxt[3][ct] = gj < n ? fa.rho[gj] : 0.f;
-    }
-    // rolling prefetch buffers: slot uu holds row (it * WS_UNR + uu) * WS_CW + cw of the tile being streamed
-    float4 bx[WS_UNR], bm[WS_UNR], bv[WS_UNR], bf[WS_UNR];
-#pragma unroll
-    for (int uu = 0; uu < WS_UNR; ++uu) {
-      const int64_t o = (int64_t)tix * TILE_ELEMS + uu * WS_CW * TILE + lofs;
-      bx[uu] = LD4S(tiles + o);
-      bm[uu] = LD4S(mbuf + o);
-      bv[uu] = LD4S(vbuf + o);
-      bf[uu] = use_f ? LD4S(fa.Ftiles + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    int Jprev = 0, Iprev = 0;
-    bool prev_fast = false;
+    // factor rows of tile row I -> TMEM [hi | lo] (lane = node, column = factor index); 4 warps per lane quarter split K
+    auto load_A = [&](int I) {
+      const int row = qq * 32 + lane;
+      const float* src = fa.Wt + (int64_t)I * TILE + row;
 #pragma unroll 1
-    for (int k = 0; k < my_tiles; ++k) {
-      const bool has_next = k + 1 < my_tiles;
-      int In = 0, Jn = 0, tixn = 0;
-      if (has_next) {
-        int64_t t64;
-        tile_coords_blocked((int64_t)blockIdx.x + (int64_t)(k + 1) * gridDim.x, tr0, tr1, 8, In, Jn, t64);
-        tixn = (int)t64;
+      for (int half = 0; half < 2; ++half) {
+        const int k0 = (cw >> 2) * 32 + half * 16;
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float v = src[(int64_t)(k0 + j) * np];
+          const uint32_t hb = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;      // same split as k_prep_w
+          h[j] = hb;
+          l[j] = __float_as_uint(v - __uint_as_float(hb));
+        }
+        const uint32_t ta = tm + ((uint32_t)(qq * 32) << 16);
+        tc::tmem_st16(ta + RS_COL_AH + (uint32_t)k0, h);
+        tc::tmem_st16(ta + RS_COL_AL + (uint32_t)k0, l);
       }
-      const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
-      tc::mbar_wait(&sm.dfull, (uint32_t)(k & 1));
-      tc::fence_after();
-      ws_cons_sync<WS_CW * 32>();                                   // A: every consumer finished streaming tile k - 1
+      tc::tmem_st_wait();
+    };
+    auto load_consts = [&](const RunIter& t) {           // node vectors of a tile -> nxt (threads < 128)
       if (ct < TILE) {
-        if (k > 0) {                                    // row / column sums of the previous tile -> next iteration's degrees
-          const int64_t gj = (int64_t)Jprev * TILE + ct;
-          const float cs = sm.colacc[ct];
-          if (gj < n && cs != 0.f) atomicAdd(fa.d_next + gj, cs);
-          sm.colacc[ct] = 0.f;
-          if (prev_fast) {
-            float rs = 0.f;
-#pragma unroll 8
-            for (int l = 0; l < 32; ++l) rs += rowpart[ct * 33 + l];
-            if (rs != 0.f) atomicAdd(fa.d_next + (int64_t)Iprev * TILE + ct, rs);
-          }
-        }
-        sm.rI[ct] = sm.nxt[0][ct]; sm.rJ[ct] = sm.nxt[1][ct]; sm.rhoI[ct] = sm.nxt[2][ct]; sm.rhoJ[ct] = sm.nxt[3][ct];
-        if (fa.measure == MCGRA_M_KL) {
-          const int64_t gi = i0 + ct, gj = j0 + ct;
-          sm.lseAI[ct] = gi < n ? fa.lseA[gi] : 0.f;
-          sm.lseAJ[ct] = gj < n ? fa.lseA[gj] : 0.f;
-          sm.lseFI[ct] = gi < n ? fa.lseF[gi] : 0.f;
-          sm.lseFJ[ct] = gj < n ? fa.lseF[gj] : 0.f;
-        }
-      }
-      if (fa.k2 != 0.f) {
-        for (int e = ct; e < TILE * HID; e += WS_CW * 32) {
-          const int a = e >> 4, q = e & 15;
-          sm.zI[a][q] = (i0 + a < n) ? fa.zhat[(i0 + a) * HID + q] : 0.f;
-          sm.zJt[q][a] = (j0 + a < n) ? fa.zhat[(j0 + a) * HID + q] : 0.f;
-        }
-      }
-      {  // drain: warp -> TMEM lane quarter (warp index % 4), column group cw / 4;  hi + lo, 16 columns at a time
-        constexpr int CPW = TILE / (WS_CW / 4);         // columns per warp
-        const int qq = warp & 3, cg = cw >> 2;
-        const int row = qq * 32 + lane;
-        const uint32_t taddr = tm + ((uint32_t)(qq * 32) << 16) + (uint32_t)(cg * CPW);
-#pragma unroll 1
-        for (int c = 0; c < CPW / 16; ++c) {
-          float hi[16], lo[16];
-          tc::tmem_ld16(taddr + c * 16, hi);
-          tc::tmem_ld16(taddr + 128 + c * 16, lo);
-#pragma unroll
-          for (int u4 = 0; u4 < 4; ++u4)
-            *reinterpret_cast<float4*>(&sm.u.gt[row][cg * CPW + c * 16 + u4 * 4]) =
-                make_float4(hi[u4 * 4] + lo[u4 * 4], hi[u4 * 4 + 1] + lo[u4 * 4 + 1], hi[u4 * 4 + 2] + lo[u4 * 4 + 2],
-                            hi[u4 * 4 + 3] + lo[u4 * 4 + 3]);
-        }
-      }
-      tc::fence_before();
-      __syncwarp();
-      if (lane == 0) ws_arrive(&sm.dempty);             // the MMA warp may start the product of tile k + 1
-      ws_cons_sync<WS_CW * 32>();                                   // B: product tile + node constants visible
-      if (has_next && ct < TILE) {                      // node constants of the next tile (latency hidden by the stream)
-        const int64_t gi = (int64_t)In * TILE + ct, gj = (int64_t)Jn * TILE + ct;
+        const int64_t gi = (int64_t)t.I * TILE + ct, gj = (int64_t)t.J * TILE + ct;
         sm.nxt[0][ct] = gi < n ? fa.r[gi] : 0.f;
         sm.nxt[1][ct] = gj < n ? fa.r[gj] : 0.f;
         sm.nxt[2][ct] = gi < n ? fa.rho[gi] : 0.f;
         sm.nxt[3][ct] = gj < n ? fa.rho[gj] : 0.f;
       }
+    };
+    if (my_tiles > 0) {
+      load_A(cur.I);
+      load_consts(cur);
+    }
+    tc::fence_before();
+    __syncwarp();
+    if (lane == 0) ws_arrive(&sm.dempty);                // phase 0: A of the first tile row is in place
 
-      float* xt = tiles + (int64_t)tix * TILE_ELEMS;
-      float* mt = mbuf + (int64_t)tix * TILE_ELEMS;
-      float* vt = vbuf + (int64_t)tix * TILE_ELEMS;
-      const bool interior = (J < I) && (i0 + TILE <= n);
-      float rj4[4], rhoj4[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { rj4[q] = sm.rJ[b0 + q]; rhoj4[q] = sm.rhoJ[b0 + q]; }
-      float s_clamp = 0.f, s_sq = 0.f;
-      float colp[4] = {0.f, 0.f, 0.f, 0.f};
-      if (MODE != 4 && interior) {
-        const int64_t onext = (int64_t)tixn * TILE_ELEMS + lofs;
+    double d_sq = 0.0, d_clamp = 0.0;
+    uint32_t s = 0, ph = 0;
+    int Iprev = 0, Jprev = 0;
 #pragma unroll 1
-        for (int it = 0; it < WS_NIT; ++it) {
-          const bool more = it + 1 < WS_NIT;
-#pragma unroll
-          for (int u0 = 0; u0 < WS_UNR; u0 += PAIR) {
-            int a[PAIR];
-            float4 cx[PAIR], cm[PAIR], cv[PAIR], cf[PAIR];
-#pragma unroll
-            for (int r = 0; r < PAIR; ++r) {
-              const int uu = u0 + r;
-              a[r] = (it * WS_UNR + uu) * WS_CW + cw;
-              cx[r] = bx[uu]; cm[r] = bm[uu]; cv[r] = bv[uu]; cf[r] = bf[uu];
-              // re-issue the loads of this slot: same slot of the next iteration, or of the next tile's first iteration
-              if (more || has_next) {
-                const int64_t o = more ? (int64_t)tix * TILE_ELEMS + (int64_t)(a[r] + WS_UNR * WS_CW) * TILE + b0
-                                       : onext + uu * WS_CW * TILE;
-                bx[uu] = LD4S(tiles + o);
-                bm[uu] = LD4S(mbuf + o);
-                bv[uu] = LD4S(vbuf + o);
-                if (use_f) bf[uu] = LD4S(fa.Ftiles + o);
-              }
-            }
-            if (MODE == 0) fold_rows_fast<MCGRA_M_MSE, true, PAIR, CS>(sm, fc, xt, mt, vt, a, b0, cx, cm, cv, cf, rj4, rhoj4, s_sq, colp, rowpart_lane);
-            else if (MODE == 1) fold_rows_fast<MCGRA_M_MSE, false, PAIR, CS>(sm, fc, xt, mt, vt, a, b0, cx, cm, cv, cf, rj4, rhoj4, s_sq, colp, rowpart_lane);
-            else if (MODE == 2) fold_rows_fast<MCGRA_M_PRE, true, PAIR, CS>(sm, fc, xt, mt, vt, a, b0, cx, cm, cv, cf, rj4, rhoj4, s_sq, colp, rowpart_lane);
-            else fold_rows_fast<MCGRA_M_NONE, true, PAIR, CS>(sm, fc, xt, mt, vt, a, b0, cx, cm, cv, cf, rj4, rhoj4, s_sq, colp, rowpart_lane);
-          }
+    for (int k = 0; k < my_tiles; ++k) {
+      const bool has_next = k + 1 < my_tiles;
+      RunIter nx = cur;
+      nx.next();
+      const int64_t i0 = (int64_t)cur.I * TILE, j0 = (int64_t)cur.J * TILE;
+      tc::mbar_wait(&sm.dfull, (uint32_t)(k & 1));
+      tc::fence_after();
+      rs_cons_sync();                                    // A: every consumer finished streaming tile k - 1
+      if (ct < TILE) {
+        if (k > 0) {                                     // row / column sums of tile k - 1 -> next iteration's degrees
+          const float rs = sm.rowacc[ct], cs = sm.colacc[ct];
+          const int64_t gi = (int64_t)Iprev * TILE + ct, gj = (int64_t)Jprev * TILE + ct;
+          if (rs != 0.f) atomicAdd(fa.d_next + gi, rs);
+          if (cs != 0.f) atomicAdd(fa.d_next + gj, cs);
+          sm.rowacc[ct] = 0.f;
+          sm.colacc[ct] = 0.f;
         }
-        s_clamp = (colp[0] + colp[1]) + (colp[2] + colp[3]);
-        prev_fast = true;
-      } else {
-        prev_fast = false;
-        // generic tile: plain loads row by row (the slots prefetched for this tile are simply re-read), then the slots
-        // are refilled for the next tile
-        const float* gt_up = fa.Gtiles ? fa.Gtiles + (int64_t)tix * TILE_ELEMS : nullptr;
+        sm.rI[ct] = sm.nxt[0][ct]; sm.rJ[ct] = sm.nxt[1][ct]; sm.rhoI[ct] = sm.nxt[2][ct]; sm.rhoJ[ct] = sm.nxt[3][ct];
+      }
+      {  // drain: TMEM lane quarter qq, 32-column group cw / 4; hi + lo, 16 columns at a time
+        const int cg = cw >> 2;
+        const int row = qq * 32 + lane;
+        const uint32_t taddr = tm + ((uint32_t)(qq * 32) << 16) + (uint32_t)(cg * 32);
 #pragma unroll 1
-        for (int rr = 0; rr < TILE / WS_CW; ++rr) {
-          const int a = rr * WS_CW + cw;
-          const int off = a * TILE + b0;
-          const float4 cx = ld4(xt + off), cm = ld4(mt + off), cv = ld4(vt + off);
-          const float4 cf = use_f ? ld4(fa.Ftiles + (int64_t)tix * TILE_ELEMS + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-          fold_row<false, -1, true>(sm, fa, pv, ec, xt, mt, vt, gt_up, a, b0, i0, j0, interior, cx, cm, cv, cf, rj4, rhoj4, s_clamp, s_sq, xmin, xmax, colp);
-        }
-        if (has_next) {
+        for (int c = 0; c < 2; ++c) {
+          float hi[16], lo[16];
+          tc::tmem_ld16(taddr + c * 16, hi);
+          tc::tmem_ld16(taddr + 128 + c * 16, lo);
 #pragma unroll
-          for (int uu = 0; uu < WS_UNR; ++uu) {
-            const int64_t o = (int64_t)tixn * TILE_ELEMS + uu * WS_CW * TILE + lofs;
-            bx[uu] = LD4S(tiles + o);
-            bm[uu] = LD4S(mbuf + o);
-            bv[uu] = LD4S(vbuf + o);
-            if (use_f) bf[uu] = LD4S(fa.Ftiles + o);
-          }
+          for (int u4 = 0; u4 < 4; ++u4)
+            *reinterpret_cast<float4*>(&sm.u.gt[row][cg * 32 + c * 16 + u4 * 4]) =
+                make_float4(hi[u4 * 4] + lo[u4 * 4], hi[u4 * 4 + 1] + lo[u4 * 4 + 1], hi[u4 * 4 + 2] + lo[u4 * 4 + 2],
+                            hi[u4 * 4 + 3] + lo[u4 * 4 + 3]);
         }
       }
+      if (has_next && nx.I != cur.I) load_A(nx.I);       // (the MMAs that read the old rows completed before dfull)
+      tc::fence_before();
+      __syncwarp();
+      if (lane == 0) ws_arrive(&sm.dempty);              // the MMA warp may form the product of tile k + 1
+      rs_cons_sync();                                    // B: product tile + node vectors visible
+      if (has_next) load_consts(nx);
+
+      float* xt = tiles + (t_begin + k) * (int64_t)TILE_ELEMS;
+      float* mt = mbuf + (t_begin + k) * (int64_t)TILE_ELEMS;
+      float* vt = vbuf + (t_begin + k) * (int64_t)TILE_ELEMS;
+      const bool interior = (cur.J < cur.I) && (i0 + TILE <= n);
+      const float rj[2] = {sm.rJ[b0], sm.rJ[b0 + 1]};
+      const float rhoj[2] = {sm.rhoJ[b0], sm.rhoJ[b0 + 1]};
+      float s_sq = 0.f;
+      float colp[2] = {0.f, 0.f};
+#pragma unroll 1
+      for (int ch = 0; ch < TILE / RS_R; ++ch) {
+        tc::mbar_wait(&sm.sfull[s], ph);
+        const float* b = &sm.ring[s][0][rw * TILE + b0];
+        const float2 X = *reinterpret_cast<const float2*>(b);
+        const float2 M = *reinterpret_cast<const float2*>(b + RS_CH);
+        const float2 V = *reinterpret_cast<const float2*>(b + 2 * RS_CH);
+        const float2 F = USE_F ? *reinterpret_cast<const float2*>(b + 3 * RS_CH) : make_float2(0.f, 0.f);
+        __syncwarp();
+        if (lane == 0) ws_arrive(&sm.sempty[s]);         // this warp's part of the stage is in registers
+        if (++s == RS_S) { s = 0; ph ^= 1u; }
+        const int a = ch * RS_R + rw;
+        const float ri = sm.rI[a], rhoi = sm.rhoI[a];
+        const float2 G = *reinterpret_cast<const float2*>(&sm.u.gt[a][b0]);
+        const float xs[2] = {X.x, X.y}, ms[2] = {M.x, M.y}, vs[2] = {V.x, V.y}, fs[2] = {F.x, F.y}, gs[2] = {G.x, G.y};
+        float xo[2], mo[2], vo[2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (colp[q] != 0.f) atomicAdd(&sm.colacc[b0 + q], colp[q]);
-      {
-        const double w1 = warp_sum_d((double)s_clamp), w2 = warp_sum_d((double)s_sq);
-        if (lane == 0) {
-          atomicAdd(&sm.dsum[0], w1);
-          atomicAdd(&sm.dsum[1], w2);
+        for (int e = 0; e < 2; ++e) {
+          const float rirj = ri * rj[e];
+          const float ah = rirj * xs[e];
+          float esym = 0.f;
+          if (MEAS == MCGRA_M_MSE) esym = fc.k1x4 * (ah - fs[e]);
+          else if (MEAS == MCGRA_M_PRE) esym = fs[e];
+          if (ENT && ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(fc.k6x2, __log2f(ah) + INV_LN2, esym);
+          float gg = fmaf(rirj, esym, rhoi + rhoj[e] + gs[e]);
+          gg = fmaf(fc.norm_scale, xs[e], gg);
+          const float mn = fmaf(fc.omb1, gg - ms[e], ms[e]);
+          const float vn = fmaf(fc.omb2, gg * gg - vs[e], vs[e]);
+          const float denom = fmaf(sqrt_approx(vn), fc.inv_sqrt_bc2, fc.adam_eps);
+          const float c = __saturatef(fmaf(fc.neg_step, __fdividef(mn, denom), xs[e]));
+          // diagonal / last-row tiles: entries on or above the diagonal and beyond n stay zero
+          const bool valid = interior || ((j0 + b0 + e) < (i0 + a) && (i0 + a) < n);
+          xo[e] = valid ? c : 0.f;
+          mo[e] = valid ? mn : 0.f;
+          vo[e] = valid ? vn : 0.f;
+          s_sq = fmaf(xo[e], xo[e], s_sq);
+          colp[e] += xo[e];
         }
+        const int off = a * TILE + b0;
+        *reinterpret_cast<float2*>(xt + off) = make_float2(xo[0], xo[1]);
+        *reinterpret_cast<float2*>(mt + off) = make_float2(mo[0], mo[1]);
+        *reinterpret_cast<float2*>(vt + off) = make_float2(vo[0], vo[1]);
+        const float rp = warp_sum(xo[0] + xo[1]);
+        if (lane == 0 && rp != 0.f) atomicAdd(&sm.rowacc[a], rp);
       }
-      Jprev = J; Iprev = I;
-      I = In; J = Jn; tix = tixn;
+      if (colp[0] != 0.f) atomicAdd(&sm.colacc[b0], colp[0]);
+      if (colp[1] != 0.f) atomicAdd(&sm.colacc[b0 + 1], colp[1]);
+      d_sq += (double)s_sq;
+      d_clamp += (double)(colp[0] + colp[1]);
+      Iprev = cur.I; Jprev = cur.J;
+      cur = nx;
     }
-    ws_cons_sync<WS_CW * 32>();
+    rs_cons_sync();
     if (ct < TILE && my_tiles > 0) {
-      const int64_t gj = (int64_t)Jprev * TILE + ct;
-      const float cs = sm.colacc[ct];
-      if (gj < n && cs != 0.f) atomicAdd(fa.d_next + gj, cs);
-      if (prev_fast) {
-        float rs = 0.f;
-#pragma unroll 8
-        for (int l = 0; l < 32; ++l) rs += rowpart[ct * 33 + l];
-        if (rs != 0.f) atomicAdd(fa.d_next + (int64_t)Iprev * TILE + ct, rs);
-      }
+      const float rs = sm.rowacc[ct], cs = sm.colacc[ct];
+      const int64_t gi = (int64_t)Iprev * TILE + ct, gj = (int64_t)Jprev * TILE + ct;
+      if (rs != 0.f) atomicAdd(fa.d_next + gi, rs);
+      if (cs != 0.f) atomicAdd(fa.d_next + gj, cs);
     }
+    d_clamp = warp_sum_d(d_clamp);
+    d_sq = warp_sum_d(d_sq);
+    if (lane == 0) {
+      atomicAdd(&sm.dsum[0], d_clamp);
+      atomicAdd(&sm.dsum[1], d_sq);
+    }
+    rs_cons_sync();
     if (ct == 0) {
       if (sm.dsum[0] != 0.0) atomicAdd(fa.acc_next + MCGRA_ACC_SUMCLAMP, sm.dsum[0]);
       if (sm.dsum[1] != 0.0) atomicAdd(fa.acc_next + MCGRA_ACC_SUMSQ, sm.dsum[1]);
     }
-    xmin = warp_min(xmin);
-    xmax = warp_max(xmax);
-    if (lane == 0) {
-      if (xmin != INFINITY) atomic_min_f(minmax, xmin);
-      if (xmax != -INFINITY) atomic_max_f(minmax + 1, xmax);
-    }
   }
   tc::fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tm, 256);
-#undef LD4S
+  if (warp == 2) tc::tmem_dealloc(tm, 512);
 }
 
-int g_fold_engine = 2;     // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2), 2 = tcgen05 one tile per CTA (v3), 3 = persistent warp-specialised tcgen05 (v4); 2 and 3 need fa.Wk
+int g_fold_engine = 3;     // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2), 2 = tcgen05 one tile per CTA (v3), 3 = persistent warp-specialised tcgen05 (v4); 2 and 3 need fa.Wk
 
 // ---------------------------------------------------------------------------------------------------------
 // Bisection on device.  state: [0]=a [1]=b [2]=mu(last midpoint) [3]=done [4]=active
@@ -1316,11 +1235,9 @@ __global__ void k_bisect_reset(int64_t n, const float* state, double* acc_next, 
 
 extern "C" {
 
-int g_fold_ws_dbg = 0;      // experiment bits (mcgra_set_engine(1, 1000 + bits)): 2 = no L2 hint on operand copies, 4 = spin without back-off
 int g_fold_ws_grid = 0;     // test knob: cap on the persistent grid (0 = one CTA per SM), mcgra_set_engine(1, 100 + cap)
 int mcgra_set_fold_engine_(int value) {
-  if (value >= 1000) g_fold_ws_dbg = value - 1000;
-  else if (value >= 100) g_fold_ws_grid = value - 100;
+  if (value >= 100) g_fold_ws_grid = value - 100;
   else g_fold_engine = value;
   return 0;
 }
@@ -1331,7 +1248,9 @@ int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const fl
                     const mcgra_fold_args* a, float* minmax, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
-  if (g_fold_engine >= 3 && a->Wk != nullptr) {
+  const bool fastable = raw == 2 && a->store_clamped && a->k2 == 0.f && a->measure != MCGRA_M_KL && !a->plain_gd &&
+                        a->Gtiles == nullptr && !(a->measure != MCGRA_M_NONE && a->Ftiles == nullptr);
+  if (g_fold_engine == 3 && a->Wk != nullptr && fastable) {
     const int64_t np = a->npad;
     k_prep_w<<<(unsigned)((np * 128 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->Wt, np, (unsigned char*)a->Wk);
     static int sms = 0;
@@ -1340,43 +1259,27 @@ int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const fl
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const bool fastable = raw == 2 && a->store_clamped && a->k2 == 0.f && a->measure != MCGRA_M_KL && !a->plain_gd && a->Gtiles == nullptr;
-    int mode = 4;
-    if (fastable) {
-      if (a->measure == MCGRA_M_MSE) mode = a->k6 != 0.f ? 0 : 1;
-      else if (a->measure == MCGRA_M_PRE) mode = 2;
-      else mode = 3;
-    }
-    const size_t smem4 = sizeof(FoldWsSmem) + 1024;
     const int cap = g_fold_ws_grid > 0 ? g_fold_ws_grid : sms;
     const unsigned grid = (unsigned)(nt < cap ? nt : cap);
+    const size_t smem4 = sizeof(FoldRsSmem) + 1024;
     const unsigned char* wk = (const unsigned char*)a->Wk;
     cudaError_t e4 = cudaSuccess;
-#define MCGRA_FOLD_WS_(M, CW, UNR, PAIR, CS)                                                                          \
-  e4 = cudaFuncSetAttribute(k_fold_ws<M, CW, UNR, PAIR, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4); \
+#define MCGRA_FOLD_RS(MEAS, ENT)                                                                                      \
+  e4 = cudaFuncSetAttribute(k_fold_rs<MEAS, ENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);           \
   if (e4 != cudaSuccess) return (int)e4;                                                                              \
-  k_fold_ws<M, CW, UNR, PAIR, CS><<<grid, 64 + CW * 32, smem4, (cudaStream_t)stream>>>(tiles, m, v, tr0, tr1, (int)nt, mu, raw, *a, minmax, wk, g_fold_ws_dbg)
-#define MCGRA_FOLD_WS(M)                                                                                              \
-  if (M == 0 && g_fold_engine == 5) { MCGRA_FOLD_WS_(M, 8, 4, 2, true); }                                             \
-  else if (M == 0 && g_fold_engine == 6) { MCGRA_FOLD_WS_(M, 8, 4, 1, false); }                                       \
-  else if (M == 0 && g_fold_engine == 7) { MCGRA_FOLD_WS_(M, 8, 4, 2, false); }                                       \
-  else if (M == 0 && g_fold_engine == 8) { MCGRA_FOLD_WS_(M, 8, 4, 4, false); }                                       \
-  else if (M == 0 && g_fold_engine == 9) { MCGRA_FOLD_WS_(M, 16, 2, 2, false); }                                      \
-  else if (g_fold_engine == 4) { MCGRA_FOLD_WS_(M, 16, 2, 1, true); }                                                 \
-  else { MCGRA_FOLD_WS_(M, 8, 4, 1, true); }
-    switch (mode) {
-      case 0: MCGRA_FOLD_WS(0); break;
-      case 1: MCGRA_FOLD_WS(1); break;
-      case 2: MCGRA_FOLD_WS(2); break;
-      case 3: MCGRA_FOLD_WS(3); break;
-      default: MCGRA_FOLD_WS(4); break;
+  k_fold_rs<MEAS, ENT><<<grid, RS_THREADS, smem4, (cudaStream_t)stream>>>(tiles, m, v, tr0, nt, *a, wk)
+    if (a->measure == MCGRA_M_MSE) {
+      if (a->k6 != 0.f) { MCGRA_FOLD_RS(MCGRA_M_MSE, true); } else { MCGRA_FOLD_RS(MCGRA_M_MSE, false); }
+    } else if (a->measure == MCGRA_M_PRE) {
+      if (a->k6 != 0.f) { MCGRA_FOLD_RS(MCGRA_M_PRE, true); } else { MCGRA_FOLD_RS(MCGRA_M_PRE, false); }
+    } else {
+      if (a->k6 != 0.f) { MCGRA_FOLD_RS(MCGRA_M_NONE, true); } else { MCGRA_FOLD_RS(MCGRA_M_NONE, false); }
     }
-#undef MCGRA_FOLD_WS
-#undef MCGRA_FOLD_WS_
+#undef MCGRA_FOLD_RS
     MCGRA_LAUNCH_CHECK();
     return 0;
   }
-  if (g_fold_engine == 2 && a->Wk != nullptr) {
+  if (g_fold_engine >= 2 && a->Wk != nullptr) {
     const int64_t np = a->npad;
     k_prep_w<<<(unsigned)((np * 128 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->Wt, np, (unsigned char*)a->Wk);
     const size_t smem3 = sizeof(FoldTcSmem) + 1024;

@@ -107,10 +107,10 @@ def test_multi_tile_matches_oracle(n, weights, density):
     np.testing.assert_allclose(got["modified_adj"], ref["modified_adj"].numpy(), rtol=1e-3, atol=1e-3)
 
 
-DEFAULT_ENGINE = {0: 5, 1: 2, 2: 2}      # propagate: tcgen05 fp16x2 (v5); fold: tcgen05 (one tile per CTA); pairs: tcgen05 (entropy-only) / mma.sync
+DEFAULT_ENGINE = {0: 5, 1: 3, 2: 2}      # propagate: tcgen05 fp16x2 (v5); fold: persistent row-run tcgen05 (TMEM-resident A); pairs: tcgen05 (entropy-only) / mma.sync
 
 
-@pytest.mark.parametrize("which,eng", [(0, 1), (0, 4), (0, 5), (1, 1), (1, 2), (1, 3), (1, 4), (2, 1)])
+@pytest.mark.parametrize("which,eng", [(0, 1), (0, 4), (0, 5), (1, 1), (1, 2), (1, 3), (2, 1)])
 def test_engines_agree(which, eng):
     """exact-fp32 FFMA engine (v1) vs the tensor-core engines (mma.sync 3xTF32, tcgen05 3xTF32) of propagate (0) /
     fold (1) / pairs (2) on the same inputs."""
@@ -127,13 +127,13 @@ def test_engines_agree(which, eng):
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
 
 
-@pytest.mark.parametrize("eng", [3, 4])
+@pytest.mark.parametrize("eng", [3])
 @pytest.mark.parametrize("density,grid", [(1e7, 5), (1e7, 0), (1.0, 7)])
 def test_fold_persistent_engine_multi_tile(eng, density, grid):
-    """fold engines 3 / 4 (persistent, warp-specialised: bulk-copy operand ring, MMA of tile k + 1 under the stream of
-    tile k, rolling prefetch across tiles) against engine 2 (one tile per CTA) with several tiles per CTA: n = 1500
-    (78 tiles) on a grid capped to 5 / 7 CTAs and n = 1500 uncapped; density 1e7 = fast path from the second
-    iteration (clamped store), density 1 = budget binds (generic path, lazy projection)."""
+    """fold engine 3 (persistent, warp-specialised, row runs with the A operand resident in tensor memory, bulk-copy
+    rings for B and for x / m / v / F) against engine 2 (one tile per CTA) with several tiles and several tile rows per
+    CTA: n = 1500 (78 tiles, 12 tile rows, last row ragged) on a grid capped to 5 / 7 CTAs and uncapped; density 1e7 =
+    fast path from the second iteration (clamped store), density 1 = budget binds (engine 3 defers to engine 2)."""
     from helpers import synthetic_case
     from mcgra_b200 import _native as N
     d = synthetic_case(1500, 40, 5, weights={1: 0.01, 6: 10.0, 7: 10.0, 9: 10.0, 10: 1000.0}, epochs=4, density=density,

@@ -1,4 +1,5 @@
-for e in "1:6" "1:7" "1:8" "1:3" "1:5" "1:9" "1:6,1:1002" "1:6,1:1004" "1:6,1:1006" "1:2"; do
+# same-box A/B of the fold engines at the bench shape (n = 65 536, Profile A): MCGRA_ENGINES="1:<engine>"
+for e in "1:3" "1:2" "1:3" "1:2"; do
 MCGRA_ENGINES="$e" timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --no-parity > gpurun_out/fold_ab.json 2>gpurun_out/fold_ab.err
 python - "$e" <<PY
 import json,sys

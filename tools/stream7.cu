@@ -120,6 +120,124 @@ __global__ void k_bulk(float* __restrict__ x, float* __restrict__ m, float* __re
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+
+// ---- fold-shaped probe: bulk-staged loads (ring of S stages x 8 rows x 4 arrays), 16 consumer warps in two groups that
+// read their row from shared memory, run the fold's per-element arithmetic (Adam + entropy term, 3 MUFU / element), write
+// x, m, v with coalesced STG, plus a dummy operand producer that pulls 8 x 32 KB per tile from a 64 MB buffer (the factor
+// blocks of the real kernel) and two consumer-wide barriers per tile.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* b, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+template <int S, int OPS>
+__global__ void __launch_bounds__(576, 1)
+k_probe(float* __restrict__ x, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ f, int ntiles,
+        const unsigned char* __restrict__ W, int wblocks, float* __restrict__ dnext, float k1x4, float k6x2, float nsc, float step) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int R = 8, CH = R * TILE;                      // floats per array per stage
+  float* ring = reinterpret_cast<float*>(smem);            // [S][4][CH]
+  float* gt = ring + (size_t)S * 4 * CH;                   // [128][132]
+  unsigned char* ops = reinterpret_cast<unsigned char*>(gt + 128 * 132);   // [2][32896]
+  float* rowacc = reinterpret_cast<float*>(ops + 2 * 32896);               // [128]
+  float* colacc = rowacc + 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(colacc + 128);
+  uint64_t* empty = full + S;
+  uint64_t* ofull = empty + S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 16); }
+    mbar_init(&ofull[0], 1); mbar_init(&ofull[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = tid; e < 128 * 132; e += blockDim.x) gt[e] = 1e-6f * (e & 255);
+  if (tid < 256) rowacc[tid] = 0.f;
+  __syncthreads();
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_tiles * 16;
+  if (warp == 0) {
+    if (lane == 0)
+      for (int c = 0; c < total; ++c) {
+        const int s = c % S;
+        mbar_wait_sleep(&empty[s], (uint32_t)(((c / S) & 1) ^ 1));
+        const int t = blockIdx.x + (c >> 4) * gridDim.x;
+        const int64_t o = (int64_t)t * TE + (int64_t)(c & 15) * CH;
+        float* b = ring + (size_t)s * 4 * CH;
+        mbar_expect(&full[s], 4u * CH * 4u);
+        bulk_g2s(b, x + o, CH * 4, &full[s]);
+        bulk_g2s(b + CH, m + o, CH * 4, &full[s]);
+        bulk_g2s(b + 2 * CH, v + o, CH * 4, &full[s]);
+        bulk_g2s(b + 3 * CH, f + o, CH * 4, &full[s]);
+      }
+  } else if (warp == 1) {
+    if (lane == 0 && OPS)
+      for (int c = 0; c < my_tiles * 8; ++c) {               // 8 K-eighths x (16 448 + 16 448) B per tile, alternating stages
+        const int s = c & 1;
+        if (c >= 2) mbar_wait_sleep(&ofull[s], (uint32_t)(((c >> 1) - 1) & 1));
+        const int blk = (int)(((int64_t)blockIdx.x * 7 + (c >> 3) * 13) % wblocks);
+        mbar_expect(&ofull[s], 32896u);
+        bulk_g2s(ops + s * 32896, W + (int64_t)blk * 131584 + (c & 7) * 16448, 16448, &ofull[s]);
+        bulk_g2s(ops + s * 32896 + 16448, W + (int64_t)((blk * 5 + 3) % wblocks) * 131584 + (c & 7) * 16448, 16448, &ofull[s]);
+      }
+  } else {
+    // one group of 16 warps: a stage = 8 rows, warp cw takes row cw >> 1, column half cw & 1 (lane -> 2 columns)
+    const int cw = warp - 2, rw = cw >> 1, b0 = (cw & 1) * 64 + lane * 2;
+    float colp[4] = {0.f, 0.f, 0.f, 0.f};
+    float s_sq = 0.f;
+    for (int c = 0; c < total; ++c) {
+      const int s = c % S;
+      const int t = blockIdx.x + (c >> 4) * gridDim.x;
+      const int a = (c & 15) * R + rw;                       // row inside the tile
+      if ((c & 15) == 0) {                                   // tile switch: two consumer-wide barriers
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid - 64 < 128) { const float rs = rowacc[tid - 64]; if (rs != 0.f) atomicAdd(dnext + (t & 1023) * 128 + tid - 64, rs); rowacc[tid - 64] = 0.f; }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+      }
+      mbar_wait(&full[s], (uint32_t)((c / S) & 1));
+      const float* b = ring + (size_t)s * 4 * CH + rw * TILE + b0;
+      const float2 X = *(const float2*)b, M = *(const float2*)(b + CH), V = *(const float2*)(b + 2 * CH), F = *(const float2*)(b + 3 * CH);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      const float2 G = *(const float2*)(gt + a * 132 + b0);
+      const float xs[2] = {X.x, X.y}, ms[2] = {M.x, M.y}, vs[2] = {V.x, V.y}, fs[2] = {F.x, F.y}, gs[2] = {G.x, G.y};
+      float xo[2], mo[2], vo[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float rirj = 0.5f + 1e-3f * k;
+        const float ah = rirj * xs[k];
+        float esym = k1x4 * (ah - fs[k]);
+        if (ah >= 1e-4f && ah <= 0.9999f) esym = fmaf(k6x2, __log2f(ah) + 1.4426950408889634f, esym);
+        float gg = fmaf(rirj, esym, 0.25f + gs[k]);
+        gg = fmaf(nsc, xs[k], gg);
+        const float mn = fmaf(0.1f, gg - ms[k], ms[k]);
+        const float vn = fmaf(0.001f, gg * gg - vs[k], vs[k]);
+        float sq;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(vn));
+        const float c_ = __saturatef(fmaf(-step, __fdividef(mn, fmaf(sq, 1.01f, 1e-8f)), xs[k]));
+        xo[k] = c_; mo[k] = mn; vo[k] = vn;
+        s_sq = fmaf(c_, c_, s_sq);
+        colp[k] += c_;
+      }
+      const int64_t o = (int64_t)t * TE + a * TILE + b0;
+      *(float2*)(x + o) = make_float2(xo[0], xo[1]);
+      *(float2*)(m + o) = make_float2(mo[0], mo[1]);
+      *(float2*)(v + o) = make_float2(vo[0], vo[1]);
+      const float rp = warp_sum(xo[0] + xo[1]);
+      if (lane == 0) atomicAdd(&rowacc[a], rp);
+    }
+    if (s_sq + colp[0] + colp[1] + colp[2] + colp[3] == 12345.f) dnext[0] = 1.f;
+  }
+}
+
 template <typename F>
 float timeit(F&& launch, int reps = 5) {
   cudaEvent_t a, b;
@@ -150,6 +268,8 @@ int main(int argc, char** argv) {
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const double gb = 7.0 * bytes / 1e9;
   printf("tiles %d, %.1f GB per array, algorithmic traffic %.1f GB, %d SMs\n", ntiles, bytes / 1e9, gb, sms);
+  const bool only_probe = argc > 2;
+  if (!only_probe) {
   {  // plain copy reference: x -> m (read 1, write 1)
     float ms = timeit([&] { CK(cudaMemcpyAsync(m, x, bytes, cudaMemcpyDeviceToDevice)); });
     printf("cudaMemcpy d2d            : %.3f ms  %.0f GB/s (read+write)\n", ms, 2.0 * bytes / 1e6 / ms);
@@ -184,5 +304,27 @@ int main(int argc, char** argv) {
   RUN_BULK(4, 8, 256, 2)
   RUN_BULK(6, 8, 256, 1)
   RUN_BULK(3, 8, 128, 4)
+  }
+  {
+    const int wblocks = 512;
+    unsigned char* W;
+    float* dn;
+    CK(cudaMalloc(&W, (size_t)wblocks * 131584));
+    CK(cudaMemset(W, 0, (size_t)wblocks * 131584));
+    CK(cudaMalloc(&dn, 1024 * 128 * 4));
+    CK(cudaMemset(dn, 0, 1024 * 128 * 4));
+    CK(cudaMemset(x, 0, bytes)); CK(cudaMemset(m, 0, bytes)); CK(cudaMemset(v, 0, bytes));
+#define RUN_PROBE(S, OPS)                                                                                         \
+  {                                                                                                               \
+    const size_t sm = (size_t)S * 4 * 8 * TILE * 4 + 128 * 132 * 4 + 2 * 32896 + 1024 + (2 * S + 2) * 8 + 64;      \
+    CK(cudaFuncSetAttribute(k_probe<S, OPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));               \
+    float ms = timeit([&] { k_probe<S, OPS><<<sms, 576, sm>>>(x, m, v, f, ntiles, W, wblocks, dn, 0.04f, -2.f, 1e-4f, 0.01f); }); \
+    printf("probe S=%d operand-traffic=%d (%zu KB smem): %.3f ms  %.0f GB/s\n", S, OPS, sm / 1024, ms, gb * 1e3 / ms); \
+  }
+    RUN_PROBE(5, 1)
+    RUN_PROBE(5, 0)
+    RUN_PROBE(4, 1)
+    RUN_PROBE(3, 1)
+  }
   return 0;
 }
