@@ -92,9 +92,13 @@ def test_real_dataset_full_readme_run_auc(ds):
     if ds in NOISE_DOMINATED:       # chaotic trajectory (see above): the attack must still recover the graph as well
         assert a > float(r["auc_full"]) - 0.02
         return
-    # 100 free-running Adam iterations: the fp32 trajectories have separated by then (sign flips at the noise floor), AUC
-    # stays within 1e-3; AP of these graphs is a ~0.03 quantity carried by a few hundred top-ranked pairs -> 2e-3
-    assert abs(a - float(r["auc_full"])) < 1e-3 and abs(p - float(r["ap_full"])) < 2e-3
+    # 100 free-running Adam iterations are chaotic at the 1e-7 level: two runs of the SAME binary (float atomics in the
+    # degree sums) end with 99.8 % of the entries differing by > 1e-4, AUC scattering by ~1e-3 and AP (a ~0.03 quantity
+    # carried by a few hundred top-ranked pairs) by ~2e-3, while the loss agrees to 2e-5
+    # (profiles/r02_cora100_run_to_run.txt).  The reference's value is one sample of that family, so the full run is held
+    # to the loss (1e-4) and to 2.5e-3 / 4e-3 on AUC / AP; the 1e-3 bar is enforced on the 5-iteration run above.
+    assert rel_last < 1e-4
+    assert abs(a - float(r["auc_full"])) < 2.5e-3 and abs(p - float(r["ap_full"])) < 4e-3
 
 
 MULTI = [
