@@ -212,7 +212,7 @@ def large_parity(a, prob, args, PROFILE_W, num_edges, device, world, iters=5, ro
     out = {}
     runs = {}
     try:
-        for name, engines in (("exact", {0: 0, 1: 0, 2: 0}), ("default", {0: 5, 1: 2, 2: 2})):
+        for name, engines in (("exact", {0: 0, 1: 0, 2: 0}), ("default", {0: 5, 1: 3, 2: 2})):
             for w, v in engines.items():
                 N.lib().mcgra_set_engine(w, v)
             atk, adj = make_attack(prob, device)
@@ -254,7 +254,7 @@ def large_parity(a, prob, args, PROFILE_W, num_edges, device, world, iters=5, ro
             del eng, atk
             torch.cuda.empty_cache()
     finally:
-        for w, v in {0: 5, 1: 2, 2: 2}.items():
+        for w, v in {0: 5, 1: 3, 2: 2}.items():
             N.lib().mcgra_set_engine(w, v)
     le, xe = runs["exact"]
     ld, xd = runs["default"]

@@ -9,10 +9,14 @@
 //   g = mask * [ U_i.V_j + V_i.U_j  +  r_i r_j (e'_ij + e'_ji)  +  rho_i + rho_j ]  +  0.001 w_sup x / ||x||
 // with U = [r dZ1 | r dZ2 | dQ1 | dQ2], V = [r S1 | r S2 | S1 | T2] (rank-64 factors built by the node kernels),
 // e' the element-wise loss derivatives at A_hat_ij and rho the degree gradient.
-// One CTA per 128x128 tile: rank-128 product (k_fold_adam: fp32 register-tiled FFMA; k_fold_mma: mma.sync 3xTF32;
-// k_fold_tc [default]: tcgen05 kind::tf32 with N = 256 [W_hi | W_lo] operands pre-formatted by k_prep_w, CTAs in an
-// L2-friendly blocked tile order), then a streaming epilogue that reads x', m, v (and feature_adj) once and writes
-// x', m, v once:  24 (+4) bytes per entry.
+// Engines (mcgra_set_engine(1, v)):
+//   0  k_fold_adam  one CTA per tile, fp32 register-tiled FFMA product (exact; reference of the agreement tests)
+//   2  k_fold_tc    one CTA per tile, tcgen05 kind::tf32 3xTF32 product (N = 256 [W_hi | W_lo] operands pre-formatted by
+//                   k_prep_w, L2-friendly blocked tile order), every parameter view / measure
+//   3  k_fold_rs    DEFAULT for "fast" launches (buffer holds the clamped parameter, MSE / precomputed / no c1 term):
+//                   persistent row runs, A operand resident in tensor memory, bulk-copy rings for B and for x' / m / v / F,
+//                   16 streaming warps; other launches run on k_fold_tc
+// All read x', m, v (and feature_adj) once and write x', m, v once: 24 (+4) bytes per entry.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -216,38 +220,7 @@ k_fold_adam(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restri
 }
 
 
-// ---------------------------------------------------------------------------------------------------------
-// v2 engine: the rank-128 factor product on warp-level tensor-core MMA (mma.sync m16n8k8 tf32, 3xTF32 split,
-// fp32 accumulate), result tile parked in shared memory, then a fully coalesced streaming epilogue (one warp =
-// one 512 B tile row per step, 4 rows in flight per warp).
-// ---------------------------------------------------------------------------------------------------------
-constexpr int W_LD = TILE + 8;     // k-major operand rows: banks 8t+g distinct for fragment loads
-constexpr int G_LD = TILE + 4;
-
-struct FoldMmaSmem {
-  union {
-    struct { float wi[64][W_LD]; float wj[64][W_LD]; } op;     // operands of one K half
-    float gt[TILE][G_LD];                                       // rank-part gradient tile (aliases operands)
-  } u;
-  float zI[TILE][HID + 1];
-  float zJt[HID][TILE + 4];
-  float rI[TILE], rJ[TILE], rhoI[TILE], rhoJ[TILE];
-  float lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE];
-  float colacc[TILE];
-  double red[32];
-};
-
-__device__ __forceinline__ void split_tf32f(float v, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;      // round-to-nearest tf32: unbiased split
-  lo = __float_as_uint(v - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32f(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
+constexpr int G_LD = TILE + 4;     // padded row stride of the parked product tile
 
 struct EpiConst {
   float step_size, inv_sqrt_bc2, omb1, omb2, norm_scale;
@@ -390,156 +363,6 @@ __device__ __forceinline__ void fold_stream(SM& sm, const mcgra_fold_args& fa, c
       fold_row<FAST, MEAS, ENT>(sm, fa, pv, ec, xt, mt, vt, gt_up, a, b0, i0, j0, interior, x4[uu], m4[uu], v4[uu], f4[uu],
                                 rj4, rhoj4, s_clamp, s_sq, xmin, xmax, colp);
     }
-  }
-}
-
-__global__ void __launch_bounds__(256, 2)
-k_fold_mma(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int64_t t0, const float* mu,
-           int raw, mcgra_fold_args fa, float* __restrict__ minmax) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FoldMmaSmem& sm = *reinterpret_cast<FoldMmaSmem*>(smem_raw);
-  int I, J;
-  tile_coords(t0 + blockIdx.x, I, J);
-  const ParamView pv = load_view(mu, raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
-  const int64_t n = fa.n, np = fa.npad;
-
-  if (tid < TILE) {
-    const int64_t gi = i0 + tid, gj = j0 + tid;
-    sm.rI[tid] = gi < n ? fa.r[gi] : 0.f;
-    sm.rJ[tid] = gj < n ? fa.r[gj] : 0.f;
-    sm.rhoI[tid] = gi < n ? fa.rho[gi] : 0.f;
-    sm.rhoJ[tid] = gj < n ? fa.rho[gj] : 0.f;
-    if (fa.measure == MCGRA_M_KL) {
-      sm.lseAI[tid] = gi < n ? fa.lseA[gi] : 0.f;
-      sm.lseAJ[tid] = gj < n ? fa.lseA[gj] : 0.f;
-      sm.lseFI[tid] = gi < n ? fa.lseF[gi] : 0.f;
-      sm.lseFJ[tid] = gj < n ? fa.lseF[gj] : 0.f;
-    }
-    sm.colacc[tid] = 0.f;
-  }
-  if (fa.k2 != 0.f) {
-    for (int e = tid; e < TILE * HID; e += 256) {
-      const int a = e >> 4, k = e & 15;
-      sm.zI[a][k] = (i0 + a < n) ? fa.zhat[(i0 + a) * HID + k] : 0.f;
-      sm.zJt[k][a] = (j0 + a < n) ? fa.zhat[(j0 + a) * HID + k] : 0.f;
-    }
-  }
-
-  // ---- rank-128 product: warp (wm, wn) owns rows [32 wm, +32) x cols [64 wn, +64) ----
-  const int wm = warp >> 1, wn = warp & 1;
-  float acc[2][8][4];
-#pragma unroll
-  for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[mb][nb][q] = 0.f;
-
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    __syncthreads();
-    const int rowI = half == 0 ? 0 : 64;     // U rows for I in half 0, V rows in half 1
-    const int rowJ = half == 0 ? 64 : 0;
-    for (int e = tid; e < 64 * 32; e += 256) {
-      const int k = e >> 5, c4 = e & 31;
-      *reinterpret_cast<float4*>(&sm.u.op.wi[k][c4 * 4]) = ld4(fa.Wt + (int64_t)(rowI + k) * np + i0 + c4 * 4);
-      *reinterpret_cast<float4*>(&sm.u.op.wj[k][c4 * 4]) = ld4(fa.Wt + (int64_t)(rowJ + k) * np + j0 + c4 * 4);
-    }
-    __syncthreads();
-#pragma unroll 2
-    for (int ks = 0; ks < 8; ++ks) {
-      const int k0 = ks * 8;
-      uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const int m0 = wm * 32 + mb * 16;
-        split_tf32f(sm.u.op.wi[k0 + t][m0 + g], ahi[mb][0], alo[mb][0]);
-        split_tf32f(sm.u.op.wi[k0 + t][m0 + g + 8], ahi[mb][1], alo[mb][1]);
-        split_tf32f(sm.u.op.wi[k0 + t + 4][m0 + g], ahi[mb][2], alo[mb][2]);
-        split_tf32f(sm.u.op.wi[k0 + t + 4][m0 + g + 8], ahi[mb][3], alo[mb][3]);
-      }
-      uint32_t bh[8][2], bl[8][2];
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        const int n0 = wn * 64 + nb * 8;
-        split_tf32f(sm.u.op.wj[k0 + t][n0 + g], bh[nb][0], bl[nb][0]);
-        split_tf32f(sm.u.op.wj[k0 + t + 4][n0 + g], bh[nb][1], bl[nb][1]);
-      }
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) mma_tf32f(acc[mb][nb], alo[mb], bh[nb][0], bh[nb][1]);
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) mma_tf32f(acc[mb][nb], ahi[mb], bl[nb][0], bl[nb][1]);
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) mma_tf32f(acc[mb][nb], ahi[mb], bh[nb][0], bh[nb][1]);
-    }
-  }
-  __syncthreads();                           // operands dead: park the product tile over them
-#pragma unroll
-  for (int mb = 0; mb < 2; ++mb) {
-    const int ra = wm * 32 + mb * 16 + g;
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const int cb = wn * 64 + nb * 8 + 2 * t;
-      *reinterpret_cast<float2*>(&sm.u.gt[ra][cb]) = make_float2(acc[mb][nb][0], acc[mb][nb][1]);
-      *reinterpret_cast<float2*>(&sm.u.gt[ra + 8][cb]) = make_float2(acc[mb][nb][2], acc[mb][nb][3]);
-    }
-  }
-  __syncthreads();
-
-  // ---- streaming epilogue ----
-  const double sumsq_prev = fa.acc_prev[MCGRA_ACC_SUMSQ];
-  const float inv_norm = sumsq_prev > 0.0 ? (float)(1.0 / sqrt(sumsq_prev)) : 0.f;
-  const int adam_step = fa.step_ptr != nullptr ? (*fa.step_ptr + 1) : fa.step;
-  const double bc1 = 1.0 - pow((double)fa.beta1, (double)adam_step);
-  const double bc2 = 1.0 - pow((double)fa.beta2, (double)adam_step);
-  EpiConst ec;
-  ec.step_size = (float)((double)fa.lr / bc1);
-  ec.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  ec.omb1 = 1.f - fa.beta1;
-  ec.omb2 = 1.f - fa.beta2;
-  ec.norm_scale = fa.norm_coef * inv_norm;
-  const bool interior = (J < I) && (i0 + TILE <= n);
-  float s_clamp = 0.f, s_sq = 0.f, xmin = INFINITY, xmax = -INFINITY;
-  float colp[4] = {0.f, 0.f, 0.f, 0.f};
-  // specialise the hot combinations (uniform per CTA): plain parameter view + interior tile + MSE/none + no c2
-  const bool fastview = (pv.raw == 2) && interior && fa.k2 == 0.f && fa.measure != MCGRA_M_KL && !fa.plain_gd && fa.Gtiles == nullptr;
-  if (fastview) {
-    if (fa.measure == MCGRA_M_MSE) {
-      if (fa.k6 != 0.f) fold_stream<true, MCGRA_M_MSE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
-      else fold_stream<true, MCGRA_M_MSE, false>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
-    } else if (fa.measure == MCGRA_M_PRE) {
-      fold_stream<true, MCGRA_M_PRE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
-    } else {
-      fold_stream<true, MCGRA_M_NONE, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
-    }
-  } else {
-    fold_stream<false, -1, true>(sm, fa, pv, ec, blockIdx.x, tiles, mbuf, vbuf, I, J, s_clamp, s_sq, xmin, xmax, colp);
-  }
-  const int b0 = lane * 4;
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (colp[k] != 0.f) atomicAdd(&sm.colacc[b0 + k], colp[k]);
-  __syncthreads();
-  if (tid < TILE) {
-    const int64_t gj = j0 + tid;
-    if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(fa.d_next + gj, sm.colacc[tid]);
-  }
-  block_atomic_add_d((double)s_clamp, fa.acc_next + MCGRA_ACC_SUMCLAMP, sm.red);
-  block_atomic_add_d((double)s_sq, fa.acc_next + MCGRA_ACC_SUMSQ, sm.red);
-  xmin = warp_min(xmin);
-  xmax = warp_max(xmax);
-  if (lane == 0) {
-    if (xmin != INFINITY) atomic_min_f(minmax, xmin);
-    if (xmax != -INFINITY) atomic_max_f(minmax + 1, xmax);
   }
 }
 
@@ -1097,7 +920,8 @@ k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
   if (warp == 2) tc::tmem_dealloc(tm, 512);
 }
 
-int g_fold_engine = 3;     // 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2), 2 = tcgen05 one tile per CTA (v3), 3 = persistent warp-specialised tcgen05 (v4); 2 and 3 need fa.Wk
+int g_fold_engine = 3;     // 0 = exact fp32 FFMA (reference of the agreement tests), 2 = tcgen05 one tile per CTA (k_fold_tc: every
+                           // parameter view / measure), 3 = persistent row-run tcgen05 (k_fold_rs) for fast launches, k_fold_tc otherwise
 
 // ---------------------------------------------------------------------------------------------------------
 // Bisection on device.  state: [0]=a [1]=b [2]=mu(last midpoint) [3]=done [4]=active
@@ -1287,14 +1111,6 @@ int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const fl
     if (e3 != cudaSuccess) return (int)e3;
     k_fold_tc<<<(unsigned)nt, 256, smem3, (cudaStream_t)stream>>>(tiles, m, v, tr0, tr1, mu, raw, *a, minmax,
                                                                   (const unsigned char*)a->Wk);
-    MCGRA_LAUNCH_CHECK();
-    return 0;
-  }
-  if (g_fold_engine == 1) {
-    const size_t smem2 = sizeof(FoldMmaSmem);
-    cudaError_t e2 = cudaFuncSetAttribute(k_fold_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e2 != cudaSuccess) return (int)e2;
-    k_fold_mma<<<(unsigned)nt, 256, smem2, (cudaStream_t)stream>>>(tiles, m, v, tri(tr0), mu, raw, *a, minmax);
     MCGRA_LAUNCH_CHECK();
     return 0;
   }

@@ -12,11 +12,8 @@
 //
 // Engines (mcgra_set_engine(0, v)), all with HBM traffic = one read of the tile shard (4 bytes per stored
 // entry) + O(n K):
-//   v0 k_propagate        fp32 FFMA, 2 x K register tile per thread (exact fp32; the reference of the agreement tests)
-//   v1 k_propagate_mma    mma.sync m16n8k8 3xTF32, both products
-//   v2 k_propagate_tc     direct product on tcgen05 (SS operands, D in TMEM), mirrored product on mma.sync
-//   v4 k_propagate_tc2    both products on tcgen05 kind::tf32; T^T written to tensor memory (tcgen05.st), TS-mode MMAs
-//   v5 k_propagate_h      both products on tcgen05 kind::f16 from ONE fp16x2 image per tile (K-major for the direct,
+//   0  k_propagate        fp32 FFMA, 2 x K register tile per thread (exact fp32; the reference of the agreement tests)
+//   5  k_propagate_h      both products on tcgen05 kind::f16 from ONE fp16x2 image per tile (K-major for the direct,
 //                         MN-major for the mirrored product); DEFAULT
 // plus k_elem_stats (the element-wise terms as a stand-alone streaming pass), k_degree, k_row_sumexp.
 #include <cuda_fp16.h>
@@ -293,880 +290,6 @@ k_row_sumexp(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
   for (int k = 0; k < 4; ++k) atomicAdd(&colacc[lane * 4 + k], col[k]);
   __syncthreads();
   if (j0 + tid < n && colacc[tid] != 0.f) atomicAdd(sumexp + j0 + tid, colacc[tid]);
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
-// v2 engine: warp-level tensor-core MMA (mma.sync.m16n8k8 tf32) with the 3xTF32 split
-//   a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits), a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate
-// so results keep fp32-level accuracy (error ~2^-20 relative per product).  One CTA = tile row I, a run of up to
-// PROP_RUN consecutive J tiles: the direct product Y[I rows] accumulates in registers over the run and is flushed
-// once; the mirrored product Y[J rows] is flushed per tile.  Fragments are read straight from the staged tile:
-//   direct  : A[m=i][k=j] = xs[i][j]          (k slots t, t+4  -> j = k0+t, k0+t+4)
-//   mirrored: A[m=j][k=i] = xs[i][j]          (k slots t, t+4  -> i = k0+2t, k0+2t+1: conflict-free banks)
-// ---------------------------------------------------------------------------------------------------------
-constexpr int PROP_RUN = 4;
-constexpr int BJ_LD_EXTRA = 8;    // bj row stride KC+8  -> banks 8t+g distinct for rows t, cols g
-constexpr int BI_LD_EXTRA = 4;    // bi row stride KC+4  -> banks (2t)*(KC+4)+g = 8t+g (KC=32) distinct
-
-template <int KC>
-struct PropMmaSmem {
-  float xs[TILE][XS_LD];
-  float bj[TILE][KC + BJ_LD_EXTRA];
-  float bi[TILE][KC + BI_LD_EXTRA];
-  float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE], dlI[TILE], dlJ[TILE];
-  float rowacc[TILE], colacc[TILE];
-  double red[32];
-};
-
-__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;      // round-to-nearest tf32: unbiased split
-  lo = __float_as_uint(v - __uint_as_float(hi));
-}
-
-__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// 256 threads: all 8 warps stage the tile (and do the fused element-wise terms); then warps 0-3 run the direct
-// product (accumulating over the run) while warps 4-7 run the mirrored product of the same staged tile.
-// MMAs are issued term-major over 8 independent accumulators so dependent MMAs are >= 8 instructions apart.
-template <int KC, bool ELEM>
-__global__ void __launch_bounds__(256, 2)
-k_propagate_mma(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
-                const float* __restrict__ B, float* __restrict__ Y, mcgra_elem_args ea) {
-  const int I = tr0 + (int)blockIdx.y;
-  const int Jbeg = (int)blockIdx.x * PROP_RUN;
-  if (Jbeg > I) return;
-  const int Jend = min(I + 1, Jbeg + PROP_RUN);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  PropMmaSmem<KC>& sm = *reinterpret_cast<PropMmaSmem<KC>*>(smem_raw);
-  const ParamView pv = load_view(mu, raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int64_t i0 = (int64_t)I * TILE;
-  constexpr int NB = KC / 8;
-  const bool direct = warp < 4;
-  const int wq = warp & 3;
-
-  for (int e = tid; e < TILE * KC / 4; e += 256) {
-    const int row = e / (KC / 4), c4 = e % (KC / 4);
-    float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i0 + row < n) vi = reinterpret_cast<const float4*>(B + (i0 + row) * KC)[c4];
-    *reinterpret_cast<float4*>(&sm.bi[row][c4 * 4]) = vi;
-  }
-  if (ELEM && tid < TILE) {
-    const int64_t gi = i0 + tid;
-    sm.rI[tid] = gi < n ? ea.r[gi] : 0.f;
-    if (ea.measure == MCGRA_M_KL) {
-      sm.lseAI[tid] = gi < n ? ea.lseA[gi] : 0.f;
-      sm.lseFI[tid] = gi < n ? ea.lseF[gi] : 0.f;
-      sm.dlI[tid] = gi < n ? ea.dlse[gi] : 0.f;
-    }
-    sm.rowacc[tid] = 0.f;
-  }
-  float acc[2][NB][4];               // direct warps: running sum over the run; mirrored warps: per tile
-#pragma unroll
-  for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[mb][nb][q] = 0.f;
-  float v1 = 0.f, v6 = 0.f;
-
-  for (int J = Jbeg; J < Jend; ++J) {
-    const int64_t j0 = (int64_t)J * TILE;
-    const int64_t tix = tri((int64_t)I) + J - tri((int64_t)tr0);
-    const float4* src = reinterpret_cast<const float4*>(tiles + tix * TILE_ELEMS);
-    __syncthreads();                       // previous tile's consumers are done with xs / bj
-    for (int e = tid; e < TILE * KC / 4; e += 256) {
-      const int row = e / (KC / 4), c4 = e % (KC / 4);
-      float4 vj = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + row < n) vj = reinterpret_cast<const float4*>(B + (j0 + row) * KC)[c4];
-      *reinterpret_cast<float4*>(&sm.bj[row][c4 * 4]) = vj;
-    }
-    if (ELEM) {
-      if (tid < TILE) {
-        const int64_t gj = j0 + tid;
-        sm.rJ[tid] = gj < n ? ea.r[gj] : 0.f;
-        if (ea.measure == MCGRA_M_KL) {
-          sm.lseAJ[tid] = gj < n ? ea.lseA[gj] : 0.f;
-          sm.lseFJ[tid] = gj < n ? ea.lseF[gj] : 0.f;
-          sm.dlJ[tid] = gj < n ? ea.dlse[gj] : 0.f;
-        }
-        sm.colacc[tid] = 0.f;
-      }
-      __syncthreads();
-    }
-    // ---- stage the tile (8 warps, one 512 B row each per step), fused element-wise terms ----
-    float col_e[4] = {0.f, 0.f, 0.f, 0.f};
-    const float4* fsrc = (ELEM && ea.Ftiles != nullptr) ? reinterpret_cast<const float4*>(ea.Ftiles + tix * TILE_ELEMS)
-                                                        : nullptr;
-    const bool interior = (J < I) && (i0 + TILE <= n);     // every entry valid
-    float rj4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ELEM) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) rj4[k] = sm.rJ[lane * 4 + k];
-    }
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-      const int row = it * 8 + warp;
-      const int idx = row * 32 + lane;
-      const float4 raw4 = src[idx];
-      float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ELEM && fsrc != nullptr) f4 = fsrc[idx];
-      const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
-      float xv[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
-      bool ok[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        ok[k] = interior || ((gj + k < gi) && (gi < n));
-        xv[k] = ok[k] ? pv.adj(xv[k]) : 0.f;
-      }
-      *reinterpret_cast<float4*>(&sm.xs[row][lane * 4]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-      if (ELEM) {
-        const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
-        const float ri = sm.rI[row];
-        float row_e = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (!ok[k]) continue;
-          const float rj = rj4[k];
-          const float ah = ri * xv[k] * rj;
-          float esym = 0.f;   // e'_ij + e'_ji
-          if (ea.measure == MCGRA_M_MSE) {
-            const float df = ah - fv[k];
-            v1 = fmaf(2.f * df, df, v1);
-            esym = 4.f * ea.k1 * df;
-          } else if (ea.measure == MCGRA_M_KL) {
-            const float xij = __expf(fv[k] - sm.lseFI[row]);
-            const float xji = __expf(fv[k] - sm.lseFJ[lane * 4 + k]);
-            const float lij = ah - sm.lseAI[row];
-            const float lji = ah - sm.lseAJ[lane * 4 + k];
-            v1 += xij * ((fv[k] - ah) - sm.dlI[row]) + xji * ((fv[k] - ah) - sm.dlJ[lane * 4 + k]);
-            esym = ea.k1 * ((__expf(lij) - xij) + (__expf(lji) - xji));
-          }
-          if (ea.k6 != 0.f) {
-            const float q = fminf(fmaxf(ah, ENT_LO), ENT_HI);
-            const float lg = __log2f(q);
-            v6 = fmaf(2.f * q, lg, v6);
-            if (ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(2.f * ea.k6, lg + INV_LN2, esym);
-          }
-          const float tt = esym * xv[k];
-          row_e = fmaf(tt, rj, row_e);
-          col_e[k] = fmaf(tt, ri, col_e[k]);
-        }
-        row_e = warp_sum(row_e);
-        if (lane == 0) sm.rowacc[row] += row_e;
-      }
-    }
-    if (ELEM) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) atomicAdd(&sm.colacc[lane * 4 + k], col_e[k]);
-    }
-    __syncthreads();
-
-    if (direct) {
-      // ---- direct product: rows i in [32 wq, +32), accumulate over the run ----
-#pragma unroll 2
-      for (int ks = 0; ks < TILE / 8; ++ks) {
-        const int k0 = ks * 8;
-        uint32_t ahi[2][4], alo[2][4], bh[NB][2], bl[NB][2];
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          const int m0 = wq * 32 + mb * 16;
-          split_tf32(sm.xs[m0 + g][k0 + t], ahi[mb][0], alo[mb][0]);
-          split_tf32(sm.xs[m0 + g + 8][k0 + t], ahi[mb][1], alo[mb][1]);
-          split_tf32(sm.xs[m0 + g][k0 + t + 4], ahi[mb][2], alo[mb][2]);
-          split_tf32(sm.xs[m0 + g + 8][k0 + t + 4], ahi[mb][3], alo[mb][3]);
-        }
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          split_tf32(sm.bj[k0 + t][nb * 8 + g], bh[nb][0], bl[nb][0]);
-          split_tf32(sm.bj[k0 + t + 4][nb * 8 + g], bh[nb][1], bl[nb][1]);
-        }
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], alo[mb], bh[nb][0], bh[nb][1]);
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], ahi[mb], bl[nb][0], bl[nb][1]);
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], ahi[mb], bh[nb][0], bh[nb][1]);
-      }
-    } else {
-      // ---- mirrored product: rows j in [32 wq, +32), flushed per tile ----
-#pragma unroll 2
-      for (int ks = 0; ks < TILE / 8; ++ks) {
-        const int k0 = ks * 8;
-        uint32_t ahi[2][4], alo[2][4], bh[NB][2], bl[NB][2];
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          const int m0 = wq * 32 + mb * 16;
-          split_tf32(sm.xs[k0 + 2 * t][m0 + g], ahi[mb][0], alo[mb][0]);
-          split_tf32(sm.xs[k0 + 2 * t][m0 + g + 8], ahi[mb][1], alo[mb][1]);
-          split_tf32(sm.xs[k0 + 2 * t + 1][m0 + g], ahi[mb][2], alo[mb][2]);
-          split_tf32(sm.xs[k0 + 2 * t + 1][m0 + g + 8], ahi[mb][3], alo[mb][3]);
-        }
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          split_tf32(sm.bi[k0 + 2 * t][nb * 8 + g], bh[nb][0], bl[nb][0]);
-          split_tf32(sm.bi[k0 + 2 * t + 1][nb * 8 + g], bh[nb][1], bl[nb][1]);
-        }
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], alo[mb], bh[nb][0], bh[nb][1]);
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], ahi[mb], bl[nb][0], bl[nb][1]);
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-          for (int mb = 0; mb < 2; ++mb) mma_tf32(acc[mb][nb], ahi[mb], bh[nb][0], bh[nb][1]);
-      }
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const int64_t ra = j0 + wq * 32 + mb * 16 + g, rb = ra + 8;
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t),
-                                make_float2(acc[mb][nb][0], acc[mb][nb][1]));
-          if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t),
-                                make_float2(acc[mb][nb][2], acc[mb][nb][3]));
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[mb][nb][q] = 0.f;
-        }
-      }
-    }
-    if (ELEM && tid < TILE) {
-      const int64_t gj = j0 + tid;
-      if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(ea.eps_row + gj, sm.colacc[tid]);
-    }
-  }
-  // ---- flush the direct product of the run ----
-  if (direct) {
-#pragma unroll
-    for (int mb = 0; mb < 2; ++mb) {
-      const int64_t ra = i0 + wq * 32 + mb * 16 + g, rb = ra + 8;
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t),
-                              make_float2(acc[mb][nb][0], acc[mb][nb][1]));
-        if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t),
-                              make_float2(acc[mb][nb][2], acc[mb][nb][3]));
-      }
-    }
-  }
-  if (ELEM) {
-    __syncthreads();
-    if (tid < TILE) {
-      const int64_t gi = i0 + tid;
-      if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(ea.eps_row + gi, sm.rowacc[tid]);
-    }
-    if (ea.measure != MCGRA_M_NONE) block_atomic_add_d((double)v1 * (double)ea.k1, ea.acc + MCGRA_ACC_C1, sm.red);
-    if (ea.k6 != 0.f) block_atomic_add_d((double)v6 * (double)ea.k6, ea.acc + MCGRA_ACC_C6, sm.red);
-  }
-}
-
-template <int KC, bool ELEM>
-int launch_prop_mma(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
-                    const mcgra_elem_args* elem, cudaStream_t st) {
-  const size_t smem = sizeof(PropMmaSmem<KC>);
-  cudaError_t e = cudaFuncSetAttribute(k_propagate_mma<KC, ELEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  mcgra_elem_args ea = {};
-  if (ELEM) ea = *elem;
-  if (tr1 - tr0 > 65535) return -3;
-  dim3 grid((unsigned)((tr1 + PROP_RUN - 1) / PROP_RUN), (unsigned)(tr1 - tr0));
-  k_propagate_mma<KC, ELEM><<<grid, 256, smem, st>>>(tiles, n, tr0, mu, raw, B, Y, ea);
-  MCGRA_LAUNCH_CHECK();
-  return 0;
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
-// v3 engine (hybrid): the DIRECT product Y[I rows] += T * B[J rows] runs on the 5th-generation tensor cores
-// (tcgen05.mma kind::tf32, accumulator in TMEM), the MIRRORED product Y[J rows] += T^T * B[I rows] on warp-level
-// mma.sync, both from ONE staged copy of the tile.
-//   * tile staged by CUDA threads in the SWIZZLE_NONE K-major core-matrix layout  off(i,j) = (j/4)*SJ + (i/8)*128 +
-//     (i%8)*16 + (j%4)*4  (T_hi = value rounded to nearest tf32, T_lo = value - T_hi: an unbiased split; kind::tf32
-//     itself truncates the low 13 mantissa bits -- verified on B200 by tools/umma_test.cu)
-//   * 3xTF32 on tcgen05:  D[128 x 2K] (+)= T_hi * [B_hi | B_lo]  and  D[:, :K] += T_lo * B_hi ; Y = D[:, :K] + D[:, K:]
-//   * MN-major tf32 operands exist only in the SW128_32B layout on sm_100 (cutlass sm100_common.inl:92), so the
-//     transposed use of the same buffer goes through mma.sync fragments (bank = g + 8t: conflict free)
-//   * D accumulates in TMEM over a run of TC_RUN tiles of one tile row; one tcgen05.commit / mbarrier per tile
-//   * next tile's global loads are issued into registers while the tensor cores work on the current one
-// ---------------------------------------------------------------------------------------------------------
-constexpr int TC_RUN = 8;
-constexpr uint32_t TC_SJ = 16 * 128 + 16;          // stride between 4-column groups (padded: conflict-free staging)
-
-template <int KC>
-struct PropTcSmem {
-  unsigned char thi[32 * TC_SJ];                   // 128 x 128 tile, K-major core-matrix layout, raw fp32 (hi)
-  unsigned char tlo[32 * TC_SJ];                   // value - trunc_tf32(value)
-  unsigned char bk[32 * ((2 * KC) * 16 + 16)];     // B[J rows]: K-major B operand, N = 2*KC ([hi | lo])
-  float bih[TILE][KC + BI_LD_EXTRA];               // B[I rows] tf32 hi / lo for the mirrored mma.sync product
-  float bil[TILE][KC + BI_LD_EXTRA];
-  float rI[TILE], rJ[TILE], lseAI[TILE], lseAJ[TILE], lseFI[TILE], lseFJ[TILE], dlI[TILE], dlJ[TILE];
-  float rowacc[TILE], colacc[TILE];
-  double red[32];
-  uint64_t bar;
-  uint32_t tmem_base;
-};
-
-__device__ __forceinline__ uint32_t tc_off(int i, int j) {
-  return (uint32_t)(j >> 2) * TC_SJ + (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u + (uint32_t)(j & 3) * 4u;
-}
-
-// B pre-formatting for the tcgen05 engine, once per call: tf32 round-to-nearest split and
-//   Bk  : per 128-node block, K-major B-operand core-matrix layout with N = 2*KC ([hi | lo])
-//   Bhl : row-major [npad][2*KC] = [hi | lo] (operand of the mirrored mma.sync product)
-template <int KC>
-__global__ void k_prep_b(const float* __restrict__ B, int64_t n, int64_t npad, unsigned char* __restrict__ Bk,
-                         float* __restrict__ Bhl) {
-  constexpr uint32_t LBO_BK = (2 * KC) * 16 + 16;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= npad * KC) return;
-  const int64_t node = e / KC;
-  const int c = (int)(e % KC);
-  const float v = node < n ? B[e] : 0.f;
-  const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-  const float lo = v - hi;
-  const int j = (int)(node & 127);
-  unsigned char* blk = Bk + (node >> 7) * (int64_t)(32 * LBO_BK) + (uint32_t)(j >> 2) * LBO_BK + (uint32_t)(j & 3) * 4u;
-  *reinterpret_cast<float*>(blk + (uint32_t)(c >> 3) * 128u + (uint32_t)(c & 7) * 16u) = hi;
-  const int c2 = c + KC;
-  *reinterpret_cast<float*>(blk + (uint32_t)(c2 >> 3) * 128u + (uint32_t)(c2 & 7) * 16u) = lo;
-  Bhl[node * (2 * KC) + c] = hi;
-  Bhl[node * (2 * KC) + KC + c] = lo;
-}
-
-// 288 threads: warps 0-7 stage the tile (+ fused element-wise terms) and run the mirrored mma.sync product;
-// warp 8 is the tensor-core warp: it copies the pre-formatted B[J] operand block, issues the tcgen05 MMAs of the
-// direct product (one lane) and commits them to the mbarrier.
-template <int KC, bool ELEM>
-__global__ void __launch_bounds__(288, 1)
-k_propagate_tc(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
-               const unsigned char* __restrict__ Bk, const float* __restrict__ Bhl, float* __restrict__ Y,
-               mcgra_elem_args ea) {
-  const int I = tr0 + (int)blockIdx.y;
-  const int Jbeg = (int)blockIdx.x * TC_RUN;
-  if (Jbeg > I) return;
-  const int Jend = min(I + 1, Jbeg + TC_RUN);
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  PropTcSmem<KC>& sm = *reinterpret_cast<PropTcSmem<KC>*>(smem_raw);
-  const ParamView pv = load_view(mu, raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int64_t i0 = (int64_t)I * TILE;
-  constexpr int NB = KC / 8;
-  constexpr uint32_t LBO_BK = (2 * KC) * 16 + 16;
-  constexpr uint32_t TCOLS = 2 * KC;               // 64 or 32 TMEM columns
-  const bool tcwarp = warp == 8;
-
-  // ---- prologue: TMEM, barrier, B[I rows] ----
-  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, TCOLS);
-  if (tid == 0) tc::mbar_init(&sm.bar, 1);
-  if (!tcwarp) {
-    for (int e = tid; e < TILE * (2 * KC) / 4; e += 256) {      // [hi | lo] rows of the I block (padded rows are 0)
-      const int row = e / (2 * KC / 4), c4 = e % (2 * KC / 4);
-      const float4 vv = reinterpret_cast<const float4*>(Bhl + (i0 + row) * (2 * KC))[c4];
-      if (c4 < KC / 4) *reinterpret_cast<float4*>(&sm.bih[row][c4 * 4]) = vv;
-      else *reinterpret_cast<float4*>(&sm.bil[row][(c4 - KC / 4) * 4]) = vv;
-    }
-    if (ELEM && tid < TILE) {
-      const int64_t gi = i0 + tid;
-      sm.rI[tid] = gi < n ? ea.r[gi] : 0.f;
-      if (ea.measure == MCGRA_M_KL) {
-        sm.lseAI[tid] = gi < n ? ea.lseA[gi] : 0.f;
-        sm.lseFI[tid] = gi < n ? ea.lseF[gi] : 0.f;
-        sm.dlI[tid] = gi < n ? ea.dlse[gi] : 0.f;
-      }
-      sm.rowacc[tid] = 0.f;
-    }
-  } else {                                    // B[J] operand block of the first tile
-    const float4* bsrc = reinterpret_cast<const float4*>(Bk + (int64_t)Jbeg * (32 * LBO_BK));
-    for (int e = lane; e < (int)(32 * LBO_BK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(sm.bk) + e, bsrc + e);
-    tc::cp_async_wait_all();
-  }
-  tc::fence_before();
-  __syncthreads();
-  tc::fence_after();
-  const uint32_t tm = sm.tmem_base;
-
-  float v1 = 0.f, v6 = 0.f;
-  float4 pre[16];
-  if (!tcwarp) {                              // register prefetch of the first tile
-    const int64_t tix = tri((int64_t)I) + Jbeg - tri((int64_t)tr0);
-    const float4* src = reinterpret_cast<const float4*>(tiles + tix * TILE_ELEMS);
-#pragma unroll
-    for (int it = 0; it < 16; ++it) pre[it] = src[(it * 8 + warp) * 32 + lane];
-  }
-  uint32_t phase = 0;
-  for (int J = Jbeg; J < Jend; ++J) {
-    const int64_t j0 = (int64_t)J * TILE;
-    const int64_t tix = tri((int64_t)I) + J - tri((int64_t)tr0);
-    if (!tcwarp) {
-      if (J > Jbeg) {                          // tensor cores are done with the staged tile of the previous step
-        tc::mbar_wait(&sm.bar, phase);
-        phase ^= 1;
-        tc::fence_after();
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // ... and so are the mma.sync readers (warps 0-7 only)
-      if (ELEM) {
-        if (tid < TILE) {
-          const int64_t gj = j0 + tid;
-          sm.rJ[tid] = gj < n ? ea.r[gj] : 0.f;
-          if (ea.measure == MCGRA_M_KL) {
-            sm.lseAJ[tid] = gj < n ? ea.lseA[gj] : 0.f;
-            sm.lseFJ[tid] = gj < n ? ea.lseF[gj] : 0.f;
-            sm.dlJ[tid] = gj < n ? ea.dlse[gj] : 0.f;
-          }
-          sm.colacc[tid] = 0.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-      // ---- stage the tile from the prefetched registers (+ fused element-wise terms) ----
-      float col_e[4] = {0.f, 0.f, 0.f, 0.f};
-      const float4* fsrc = (ELEM && ea.Ftiles != nullptr)
-                               ? reinterpret_cast<const float4*>(ea.Ftiles + tix * TILE_ELEMS) : nullptr;
-      const bool interior = (J < I) && (i0 + TILE <= n);
-      float rj4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (ELEM) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) rj4[k] = sm.rJ[lane * 4 + k];
-      }
-      if (!ELEM && interior && pv.raw == 2) {
-        // fast path: every entry valid and already in [0,1]: split and store, nothing else
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int row = it * 8 + warp;
-          const float4 v = pre[it];
-          float4 h, l;
-          h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
-          h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
-          h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
-          h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
-          const uint32_t off = (uint32_t)lane * TC_SJ + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-          *reinterpret_cast<float4*>(sm.thi + off) = h;
-          *reinterpret_cast<float4*>(sm.tlo + off) = l;
-        }
-      } else {
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int row = it * 8 + warp;
-          const float4 raw4 = pre[it];
-          float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ELEM && fsrc != nullptr) f4 = fsrc[row * 32 + lane];
-          const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
-          float xv[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
-          float xh[4], xl[4];
-          bool ok[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            ok[k] = interior || ((gj + k < gi) && (gi < n));
-            xv[k] = ok[k] ? pv.adj(xv[k]) : 0.f;
-            xh[k] = __uint_as_float((__float_as_uint(xv[k]) + 0x1000u) & 0xffffe000u);   // round-to-nearest tf32
-            xl[k] = xv[k] - xh[k];
-          }
-          const uint32_t off = (uint32_t)lane * TC_SJ + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-          *reinterpret_cast<float4*>(sm.thi + off) = make_float4(xh[0], xh[1], xh[2], xh[3]);
-          *reinterpret_cast<float4*>(sm.tlo + off) = make_float4(xl[0], xl[1], xl[2], xl[3]);
-          if (ELEM) {
-            const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
-            const float ri = sm.rI[row];
-            float row_e = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (!ok[k]) continue;
-              const float rj = rj4[k];
-              const float ah = ri * xv[k] * rj;
-              float esym = 0.f;
-              if (ea.measure == MCGRA_M_MSE) {
-                const float df = ah - fv[k];
-                v1 = fmaf(2.f * df, df, v1);
-                esym = 4.f * ea.k1 * df;
-              } else if (ea.measure == MCGRA_M_KL) {
-                const float xij = __expf(fv[k] - sm.lseFI[row]);
-                const float xji = __expf(fv[k] - sm.lseFJ[lane * 4 + k]);
-                const float lij = ah - sm.lseAI[row];
-                const float lji = ah - sm.lseAJ[lane * 4 + k];
-                v1 += xij * ((fv[k] - ah) - sm.dlI[row]) + xji * ((fv[k] - ah) - sm.dlJ[lane * 4 + k]);
-                esym = ea.k1 * ((__expf(lij) - xij) + (__expf(lji) - xji));
-              }
-              if (ea.k6 != 0.f) {
-                const float q = fminf(fmaxf(ah, ENT_LO), ENT_HI);
-                const float lg = __log2f(q);
-                v6 = fmaf(2.f * q, lg, v6);
-                if (ah >= ENT_LO && ah <= ENT_HI) esym = fmaf(2.f * ea.k6, lg + INV_LN2, esym);
-              }
-              const float tt = esym * xv[k];
-              row_e = fmaf(tt, rj, row_e);
-              col_e[k] = fmaf(tt, ri, col_e[k]);
-            }
-            row_e = warp_sum(row_e);
-            if (lane == 0) sm.rowacc[row] += row_e;
-          }
-        }
-      }
-      if (ELEM) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) atomicAdd(&sm.colacc[lane * 4 + k], col_e[k]);
-      }
-      tc::fence_async_smem();                // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    } else {
-      tc::fence_async_smem();                // the B[J] block this warp copied
-    }
-    __syncthreads();                         // tile + B[J] staged
-
-    if (tcwarp) {
-      // ---- direct product on tcgen05: 2 MMAs per K step of 8, then commit; then fetch the next B[J] block ----
-      if (lane == 0) {
-        tc::fence_after();
-        const uint64_t a_hi0 = tc::make_desc(tc::smem_u32(sm.thi), TC_SJ, 128u);
-        const uint64_t a_lo0 = tc::make_desc(tc::smem_u32(sm.tlo), TC_SJ, 128u);
-        const uint64_t b0 = tc::make_desc(tc::smem_u32(sm.bk), LBO_BK, 128u);
-        const uint32_t idesc_cat = tc::make_idesc_tf32(128, 2 * KC, 0, 0);
-        const uint32_t idesc_lo = tc::make_idesc_tf32(128, KC, 0, 0);
-#pragma unroll 4
-        for (int ks = 0; ks < TILE / 8; ++ks) {
-          const uint64_t da = (uint64_t)((uint32_t)ks * ((2u * TC_SJ) >> 4));
-          const uint64_t db = (uint64_t)((uint32_t)ks * ((2u * LBO_BK) >> 4));
-          tc::mma_tf32(tm, a_hi0 + da, b0 + db, idesc_cat, (J > Jbeg || ks > 0) ? 1u : 0u);
-          tc::mma_tf32(tm, a_lo0 + da, b0 + db, idesc_lo, 1u);
-        }
-        tc::mma_commit(&sm.bar);
-      }
-      __syncwarp();
-      if (J + 1 < Jend) {
-        tc::mbar_wait(&sm.bar, phase);       // tensor cores finished reading bk: refill it for the next tile
-        const float4* bsrc = reinterpret_cast<const float4*>(Bk + (int64_t)(J + 1) * (32 * LBO_BK));
-        for (int e = lane; e < (int)(32 * LBO_BK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(sm.bk) + e, bsrc + e);
-        tc::cp_async_wait_all();
-      }
-      phase ^= 1;
-    } else {
-      // ---- prefetch the next tile of the run into registers while the tensor cores work ----
-      if (J + 1 < Jend) {
-        const float4* nsrc = reinterpret_cast<const float4*>(tiles + (tix + 1) * TILE_ELEMS);
-#pragma unroll
-        for (int it = 0; it < 16; ++it) pre[it] = nsrc[(it * 8 + warp) * 32 + lane];
-      }
-      // ---- mirrored product on mma.sync: warp w owns rows j in [16 w, +16) ----
-      float acc[NB][4];
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[nb][q] = 0.f;
-      const int m0 = warp * 16;
-#pragma unroll 2
-      for (int ks = 0; ks < TILE / 8; ++ks) {
-        const int k0 = ks * 8;
-        uint32_t ahi[4], alo[4], bh[NB][2], bl[NB][2];
-        {
-          const uint32_t o0 = tc_off(k0 + 2 * t, m0 + g), o1 = tc_off(k0 + 2 * t, m0 + g + 8);
-          const uint32_t o2 = tc_off(k0 + 2 * t + 1, m0 + g), o3 = tc_off(k0 + 2 * t + 1, m0 + g + 8);
-          ahi[0] = *reinterpret_cast<const uint32_t*>(sm.thi + o0); alo[0] = *reinterpret_cast<const uint32_t*>(sm.tlo + o0);
-          ahi[1] = *reinterpret_cast<const uint32_t*>(sm.thi + o1); alo[1] = *reinterpret_cast<const uint32_t*>(sm.tlo + o1);
-          ahi[2] = *reinterpret_cast<const uint32_t*>(sm.thi + o2); alo[2] = *reinterpret_cast<const uint32_t*>(sm.tlo + o2);
-          ahi[3] = *reinterpret_cast<const uint32_t*>(sm.thi + o3); alo[3] = *reinterpret_cast<const uint32_t*>(sm.tlo + o3);
-        }
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          bh[nb][0] = __float_as_uint(sm.bih[k0 + 2 * t][nb * 8 + g]);
-          bl[nb][0] = __float_as_uint(sm.bil[k0 + 2 * t][nb * 8 + g]);
-          bh[nb][1] = __float_as_uint(sm.bih[k0 + 2 * t + 1][nb * 8 + g]);
-          bl[nb][1] = __float_as_uint(sm.bil[k0 + 2 * t + 1][nb * 8 + g]);
-        }
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) mma_tf32(acc[nb], alo, bh[nb][0], bh[nb][1]);
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) mma_tf32(acc[nb], ahi, bl[nb][0], bl[nb][1]);
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) mma_tf32(acc[nb], ahi, bh[nb][0], bh[nb][1]);
-      }
-      const int64_t ra = j0 + m0 + g, rb = ra + 8;
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        if (ra < n) atomicAdd(reinterpret_cast<float2*>(Y + ra * KC + nb * 8 + 2 * t), make_float2(acc[nb][0], acc[nb][1]));
-        if (rb < n) atomicAdd(reinterpret_cast<float2*>(Y + rb * KC + nb * 8 + 2 * t), make_float2(acc[nb][2], acc[nb][3]));
-      }
-      if (ELEM && tid < TILE) {
-        const int64_t gj = j0 + tid;
-        if (gj < n && sm.colacc[tid] != 0.f) atomicAdd(ea.eps_row + gj, sm.colacc[tid]);
-      }
-    }
-  }
-  // ---- epilogue: D (TMEM) -> Y[I rows] ----
-  if (!tcwarp) {
-    tc::mbar_wait(&sm.bar, phase);
-    tc::fence_after();
-  }
-  if (warp < 4) {
-    const int row = warp * 32 + lane;
-    const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
-    float hi[KC], lo[KC];
-    if (KC == 32) {
-      tc::tmem_ld32(taddr, hi);
-      tc::tmem_ld32(taddr + 32, lo);
-    } else {
-      tc::tmem_ld16(taddr, hi);
-      tc::tmem_ld16(taddr + 16, lo);
-    }
-    const int64_t gr = i0 + row;
-    if (gr < n) {
-      float4* dst = reinterpret_cast<float4*>(Y + gr * KC);
-#pragma unroll
-      for (int c4 = 0; c4 < KC / 4; ++c4)
-        atomicAdd(dst + c4, make_float4(hi[c4 * 4] + lo[c4 * 4], hi[c4 * 4 + 1] + lo[c4 * 4 + 1],
-                                        hi[c4 * 4 + 2] + lo[c4 * 4 + 2], hi[c4 * 4 + 3] + lo[c4 * 4 + 3]));
-    }
-  }
-  tc::fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tm, TCOLS);
-  if (ELEM && !tcwarp) {
-    if (tid < TILE) {
-      const int64_t gi = i0 + tid;
-      if (gi < n && sm.rowacc[tid] != 0.f) atomicAdd(ea.eps_row + gi, sm.rowacc[tid]);
-    }
-  }
-  if (ELEM) {      // block-wide reductions: every thread of the CTA participates (warp 8 contributes zeros)
-    if (ea.measure != MCGRA_M_NONE) block_atomic_add_d((double)v1 * (double)ea.k1, ea.acc + MCGRA_ACC_C1, sm.red);
-    if (ea.k6 != 0.f) block_atomic_add_d((double)v6 * (double)ea.k6, ea.acc + MCGRA_ACC_C6, sm.red);
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
-// v4 engine: BOTH products on tcgen05.
-//   direct   Y[I] += T   * B[J] : A = staged tile (smem, K-major core layout), B = B[J] block (smem)  -> D1 (TMEM)
-//   mirrored Y[J] += T^T * B[I] : A = T^T held in TENSOR MEMORY (lane = column j, one 32-bit TMEM column per row i),
-//                                 written with tcgen05.st by 128 threads that read the staged tile column-wise
-//                                 (bank = j mod 32: conflict free), B = B[I] block (smem)                -> D2 (TMEM)
-// so the tile is staged ONCE in shared memory (hi / lo), no second (MN-major) copy and no legacy mma.sync.
-// TMEM columns: D1 [0,64) (accumulates over the run), D2 [64,128), T^T hi [128,256), T^T lo [256,384).
-// Warps 0-7: staging; warps 0-3 then transpose into TMEM, warps 4-7 drain D2 and flush it; warp 8 issues all MMAs.
-// Validated layouts / instruction forms: tools/umma_test.cu (modes 0 and 3).
-// ---------------------------------------------------------------------------------------------------------
-template <int KC>
-struct PropTc2Smem {
-  unsigned char thi[32 * TC_SJ];
-  unsigned char tlo[32 * TC_SJ];
-  unsigned char bkJ[32 * ((2 * KC) * 16 + 16)];    // B[J rows] block, K-major B operand, N = 2*KC ([hi | lo])
-  unsigned char bkI[32 * ((2 * KC) * 16 + 16)];    // B[I rows] block (mirrored product), same format
-  uint64_t bar_d, bar_m;
-  uint32_t tmem_base;
-};
-
-template <int KC>
-__device__ __forceinline__ void tc2_flush(float* __restrict__ Y, int64_t n, int64_t row, uint32_t taddr) {
-  float hi[KC], lo[KC];
-  if (KC == 32) { tc::tmem_ld32(taddr, hi); tc::tmem_ld32(taddr + 32, lo); }
-  else { tc::tmem_ld16(taddr, hi); tc::tmem_ld16(taddr + 16, lo); }
-  if (row < n) {
-    float4* dst = reinterpret_cast<float4*>(Y + row * KC);
-#pragma unroll
-    for (int c4 = 0; c4 < KC / 4; ++c4)
-      atomicAdd(dst + c4, make_float4(hi[c4 * 4] + lo[c4 * 4], hi[c4 * 4 + 1] + lo[c4 * 4 + 1],
-                                      hi[c4 * 4 + 2] + lo[c4 * 4 + 2], hi[c4 * 4 + 3] + lo[c4 * 4 + 3]));
-  }
-}
-
-// Per tile k: warps 0-7 stage tile k (hi/lo) into smem; (B1); warp 8 issues the direct MMAs; warps 0-3 transpose the
-// staged tile into tensor memory (no live prefetch registers in that loop) and then prefetch their share of tile k+1;
-// (B2: warps 0-3 + warp 8) warp 8 issues the mirrored MMAs; warps 4-7 prefetch tile k+1, then drain and flush D2(k).
-template <int KC>
-__global__ void __launch_bounds__(288, 1)
-k_propagate_tc2(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
-                const unsigned char* __restrict__ Bk, float* __restrict__ Y) {
-  const int I = tr0 + (int)blockIdx.y;
-  const int Jbeg = (int)blockIdx.x * TC_RUN;
-  if (Jbeg > I) return;
-  const int Jend = min(I + 1, Jbeg + TC_RUN);
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  PropTc2Smem<KC>& sm = *reinterpret_cast<PropTc2Smem<KC>*>(smem_raw);
-  const ParamView pv = load_view(mu, raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t i0 = (int64_t)I * TILE;
-  constexpr uint32_t LBO_BK = (2 * KC) * 16 + 16;
-  constexpr uint32_t COL_D1 = 0, COL_D2 = 64, COL_AH = 128, COL_AL = 256;
-  const bool tcwarp = warp == 8;
-
-  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
-  if (tid == 0) { tc::mbar_init(&sm.bar_d, 1); tc::mbar_init(&sm.bar_m, 1); }
-  if (tcwarp) {
-    const float4* bI = reinterpret_cast<const float4*>(Bk + (int64_t)I * (32 * LBO_BK));
-    const float4* bJ = reinterpret_cast<const float4*>(Bk + (int64_t)Jbeg * (32 * LBO_BK));
-    for (int e = lane; e < (int)(32 * LBO_BK / 16); e += 32) {
-      tc::cp_async16(reinterpret_cast<float4*>(sm.bkI) + e, bI + e);
-      tc::cp_async16(reinterpret_cast<float4*>(sm.bkJ) + e, bJ + e);
-    }
-    tc::cp_async_wait_all();
-  }
-  tc::fence_before();
-  __syncthreads();
-  tc::fence_after();
-  const uint32_t tm = sm.tmem_base;
-  const int q = warp & 3;
-  const uint32_t tlane = tm + ((uint32_t)(q * 32) << 16);
-
-  float4 pre[16];
-  if (!tcwarp) {
-    const int64_t tix = tri((int64_t)I) + Jbeg - tri((int64_t)tr0);
-    const float4* src = reinterpret_cast<const float4*>(tiles + tix * TILE_ELEMS);
-#pragma unroll
-    for (int it = 0; it < 16; ++it) pre[it] = src[(it * 8 + warp) * 32 + lane];
-  }
-  uint32_t phase = 0;
-  for (int J = Jbeg; J < Jend; ++J) {
-    const int64_t j0 = (int64_t)J * TILE;
-    const int64_t tix = tri((int64_t)I) + J - tri((int64_t)tr0);
-    if (!tcwarp) {
-      if (J > Jbeg) {                          // direct MMAs of the previous tile are done reading thi / tlo
-        tc::mbar_wait(&sm.bar_d, phase ^ 1);
-        tc::fence_after();
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // warps 0-3 finished their column reads of the previous tile
-      const bool interior = (J < I) && (i0 + TILE <= n);
-      if (interior && pv.raw == 2) {
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int row = it * 8 + warp;
-          const float4 v = pre[it];
-          float4 h, l;
-          h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
-          h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
-          h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
-          h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
-          const uint32_t off = (uint32_t)lane * TC_SJ + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-          *reinterpret_cast<float4*>(sm.thi + off) = h;
-          *reinterpret_cast<float4*>(sm.tlo + off) = l;
-        }
-      } else {
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int row = it * 8 + warp;
-          const float4 raw4 = pre[it];
-          const int gi = (int)(i0 + row), gj = (int)(j0 + lane * 4);
-          const float xr[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
-          float xh[4], xl[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool ok = interior || ((gj + k < gi) && (gi < n));
-            const float xv = ok ? pv.adj(xr[k]) : 0.f;
-            xh[k] = __uint_as_float((__float_as_uint(xv) + 0x1000u) & 0xffffe000u);
-            xl[k] = xv - xh[k];
-          }
-          const uint32_t off = (uint32_t)lane * TC_SJ + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-          *reinterpret_cast<float4*>(sm.thi + off) = make_float4(xh[0], xh[1], xh[2], xh[3]);
-          *reinterpret_cast<float4*>(sm.tlo + off) = make_float4(xl[0], xl[1], xl[2], xl[3]);
-        }
-      }
-      tc::fence_async_smem();
-    } else {
-      tc::fence_async_smem();                  // the bkJ block this warp copied
-    }
-    __syncthreads();                           // (B1) tile + B[J] staged; previous D2 drained
-
-    if (tcwarp) {
-      if (lane == 0) {                         // ---- direct product ----
-        tc::fence_after();
-        const uint64_t a_hi0 = tc::make_desc(tc::smem_u32(sm.thi), TC_SJ, 128u);
-        const uint64_t a_lo0 = tc::make_desc(tc::smem_u32(sm.tlo), TC_SJ, 128u);
-        const uint64_t b0 = tc::make_desc(tc::smem_u32(sm.bkJ), LBO_BK, 128u);
-        const uint32_t idesc_cat = tc::make_idesc_tf32(128, 2 * KC, 0, 0);
-        const uint32_t idesc_lo = tc::make_idesc_tf32(128, KC, 0, 0);
-#pragma unroll 4
-        for (int ks = 0; ks < TILE / 8; ++ks) {
-          const uint64_t da = (uint64_t)((uint32_t)ks * ((2u * TC_SJ) >> 4));
-          const uint64_t db = (uint64_t)((uint32_t)ks * ((2u * LBO_BK) >> 4));
-          tc::mma_tf32(tm + COL_D1, a_hi0 + da, b0 + db, idesc_cat, (J > Jbeg || ks > 0) ? 1u : 0u);
-          tc::mma_tf32(tm + COL_D1, a_lo0 + da, b0 + db, idesc_lo, 1u);
-        }
-        tc::mma_commit(&sm.bar_d);
-      }
-      __syncwarp();
-      asm volatile("bar.sync 2, 160;" ::: "memory");   // (B2) with warps 0-3: T^T is in tensor memory
-      if (lane == 0) {                         // ---- mirrored product: A from TMEM ----
-        tc::fence_after();
-        const uint64_t b0 = tc::make_desc(tc::smem_u32(sm.bkI), LBO_BK, 128u);
-        const uint32_t idesc_cat = tc::make_idesc_tf32(128, 2 * KC, 0, 0);
-        const uint32_t idesc_lo = tc::make_idesc_tf32(128, KC, 0, 0);
-#pragma unroll 4
-        for (int ks = 0; ks < TILE / 8; ++ks) {
-          const uint64_t db = (uint64_t)((uint32_t)ks * ((2u * LBO_BK) >> 4));
-          tc::mma_tf32_ts(tm + COL_D2, tm + COL_AH + ks * 8, b0 + db, idesc_cat, ks > 0 ? 1u : 0u);
-          tc::mma_tf32_ts(tm + COL_D2, tm + COL_AL + ks * 8, b0 + db, idesc_lo, 1u);
-        }
-        tc::mma_commit(&sm.bar_m);
-      }
-      __syncwarp();
-      if (J + 1 < Jend) {                      // refill B[J] for the next tile once the direct MMAs are done with it
-        tc::mbar_wait(&sm.bar_d, phase);
-        const float4* bJ = reinterpret_cast<const float4*>(Bk + (int64_t)(J + 1) * (32 * LBO_BK));
-        for (int e = lane; e < (int)(32 * LBO_BK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(sm.bkJ) + e, bJ + e);
-        tc::cp_async_wait_all();
-      }
-    } else if (warp < 4) {
-      // ---- T^T -> tensor memory: thread = column j of the tile, 16 rows per tcgen05.st ----
-      if (J > Jbeg) {                          // mirrored MMAs of the previous tile are done reading the TMEM operand
-        tc::mbar_wait(&sm.bar_m, phase ^ 1);
-        tc::fence_after();
-      }
-      const uint32_t cbase = (uint32_t)(tid >> 2) * TC_SJ + (uint32_t)(tid & 3) * 4u;
-#pragma unroll 2
-      for (int r0 = 0; r0 < TILE; r0 += 16) {
-        uint32_t h[16], l[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const uint32_t off = cbase + (uint32_t)((r0 + u) >> 3) * 128u + (uint32_t)((r0 + u) & 7) * 16u;
-          h[u] = *reinterpret_cast<const uint32_t*>(sm.thi + off);
-          l[u] = *reinterpret_cast<const uint32_t*>(sm.tlo + off);
-        }
-        tc::tmem_st16(tlane + COL_AH + r0, h);
-        tc::tmem_st16(tlane + COL_AL + r0, l);
-      }
-      tc::tmem_st_wait();
-      tc::fence_before();
-      asm volatile("bar.sync 2, 160;" ::: "memory");   // (B2) hand T^T to the tensor-core warp
-      if (J + 1 < Jend) {                      // prefetch this warp's share of the next tile
-        const float4* nsrc = reinterpret_cast<const float4*>(tiles + (tix + 1) * TILE_ELEMS);
-#pragma unroll
-        for (int it = 0; it < 16; ++it) pre[it] = nsrc[(it * 8 + warp) * 32 + lane];
-      }
-    } else {
-      // ---- warps 4-7: prefetch, then drain D2 (mirrored result of THIS tile) and flush it ----
-      if (J + 1 < Jend) {
-        const float4* nsrc = reinterpret_cast<const float4*>(tiles + (tix + 1) * TILE_ELEMS);
-#pragma unroll
-        for (int it = 0; it < 16; ++it) pre[it] = nsrc[(it * 8 + warp) * 32 + lane];
-      }
-      tc::mbar_wait(&sm.bar_m, phase);
-      tc::fence_after();
-      tc2_flush<KC>(Y, n, j0 + q * 32 + lane, tlane + COL_D2);
-      tc::fence_before();
-    }
-    phase ^= 1;
-  }
-  // ---- epilogue: D1 (direct product of the whole run) -> Y[I rows] ----
-  if (!tcwarp) {
-    tc::mbar_wait(&sm.bar_d, phase ^ 1);
-    tc::fence_after();
-    if (warp < 4) tc2_flush<KC>(Y, n, i0 + q * 32 + lane, tlane + COL_D1);
-  }
-  tc::fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tm, 512);
 }
 
 
@@ -1463,32 +586,10 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
   if (warp == 0) tc::tmem_dealloc(tm, 512);
 }
 
-template <int KC>
-int launch_prop_h(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
-                  void* ws, cudaStream_t st);
-
 inline int64_t prop_ws_bk_bytes(int64_t n, int K) {
   const int64_t T = (n + TILE - 1) / TILE;
   return (T * 32 * ((2 * K) * 16 + 16) + 255) / 256 * 256;
 }
-
-template <int KC>
-int launch_prop_tc2(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
-                    void* ws, cudaStream_t st) {
-  const int64_t npad = (n + TILE - 1) / TILE * TILE;
-  unsigned char* Bk = reinterpret_cast<unsigned char*>(ws);
-  float* Bhl = reinterpret_cast<float*>(Bk + prop_ws_bk_bytes(n, KC));
-  k_prep_b<KC><<<(unsigned)((npad * KC + 255) / 256), 256, 0, st>>>(B, n, npad, Bk, Bhl);
-  const size_t smem = sizeof(PropTc2Smem<KC>) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(k_propagate_tc2<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  if (tr1 - tr0 > 65535) return -3;
-  dim3 grid((unsigned)((tr1 + TC_RUN - 1) / TC_RUN), (unsigned)(tr1 - tr0));
-  k_propagate_tc2<KC><<<grid, 288, smem, st>>>(tiles, n, tr0, mu, raw, Bk, Y);
-  MCGRA_LAUNCH_CHECK();
-  return 0;
-}
-
 
 template <int KC>
 int launch_prop_h(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
@@ -1511,29 +612,9 @@ int launch_prop_h(const float* tiles, int64_t n, int tr0, int tr1, const float* 
   return 0;
 }
 
-template <int KC, bool ELEM>
-int launch_prop_tc(const float* tiles, int64_t n, int tr0, int tr1, const float* mu, int raw, const float* B, float* Y,
-                   const mcgra_elem_args* elem, void* ws, cudaStream_t st) {
-  const int64_t npad = (n + TILE - 1) / TILE * TILE;
-  unsigned char* Bk = reinterpret_cast<unsigned char*>(ws);
-  float* Bhl = reinterpret_cast<float*>(Bk + prop_ws_bk_bytes(n, KC));
-  k_prep_b<KC><<<(unsigned)((npad * KC + 255) / 256), 256, 0, st>>>(B, n, npad, Bk, Bhl);
-  const size_t smem = sizeof(PropTcSmem<KC>) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(k_propagate_tc<KC, ELEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  mcgra_elem_args ea = {};
-  if (ELEM) ea = *elem;
-  if (tr1 - tr0 > 65535) return -3;
-  dim3 grid((unsigned)((tr1 + TC_RUN - 1) / TC_RUN), (unsigned)(tr1 - tr0));
-  k_propagate_tc<KC, ELEM><<<grid, 288, smem, st>>>(tiles, n, tr0, mu, raw, Bk, Bhl, Y, ea);
-  MCGRA_LAUNCH_CHECK();
-  return 0;
-}
-
-// 0 = fp32 FFMA (v1), 1 = mma.sync 3xTF32 (v2), 2 = tcgen05 + mma.sync hybrid (v3) everywhere,
-// 3 = v3 for the plain 32-wide passes only, 4 = both products on tcgen05 with T^T in tensor memory (v4, default).
-// Same-process A/B on B200 at n = 65536 (tools/engine_ab.py): K = 32: v4 4.26 ms, v3 5.32 ms, v2 7.04 ms;
-// K = 16: 3.72 / 3.80 / 5.41 ms
+// 0 = exact fp32 FFMA (reference of the engine-agreement tests; also runs the fused element-wise variant),
+// 5 = tcgen05 kind::f16 on the fp16x2 image (default).  (Engines 1-4 of rounds 1-2 -- mma.sync 3xTF32, the tcgen05 tf32
+// hybrids -- are gone; their measurements are in profiles/history and profiles/r01_umma_rate.txt.)
 int g_prop_engine = 5;
 
 
@@ -1718,30 +799,6 @@ int mcgra_propagate(const float* tiles, int64_t n, int tr0, int tr1, const float
   if (ws != nullptr && g_prop_engine == 5 && elem == nullptr) {
     if (K == 32) return launch_prop_h<32>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
     if (K == 16) return launch_prop_h<16>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
-    return -1;
-  }
-  if (ws != nullptr && g_prop_engine == 4 && elem == nullptr) {
-    if (K == 32) return launch_prop_tc2<32>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
-    if (K == 16) return launch_prop_tc2<16>(tiles, n, tr0, tr1, mu, raw, B, Y, ws, st);
-    return -1;
-  }
-  const bool use_tc = ws != nullptr && (g_prop_engine == 2 || g_prop_engine == 4 || g_prop_engine == 5 || (g_prop_engine == 3 && K == 32 && elem == nullptr));
-  if (use_tc) {
-    if (K == 32)
-      return elem ? launch_prop_tc<32, true>(tiles, n, tr0, tr1, mu, raw, B, Y, elem, ws, st)
-                  : launch_prop_tc<32, false>(tiles, n, tr0, tr1, mu, raw, B, Y, nullptr, ws, st);
-    if (K == 16)
-      return elem ? launch_prop_tc<16, true>(tiles, n, tr0, tr1, mu, raw, B, Y, elem, ws, st)
-                  : launch_prop_tc<16, false>(tiles, n, tr0, tr1, mu, raw, B, Y, nullptr, ws, st);
-    return -1;
-  }
-  if (g_prop_engine >= 1) {
-    if (K == 32)
-      return elem ? launch_prop_mma<32, true>(tiles, n, tr0, tr1, mu, raw, B, Y, elem, st)
-                  : launch_prop_mma<32, false>(tiles, n, tr0, tr1, mu, raw, B, Y, nullptr, st);
-    if (K == 16)
-      return elem ? launch_prop_mma<16, true>(tiles, n, tr0, tr1, mu, raw, B, Y, elem, st)
-                  : launch_prop_mma<16, false>(tiles, n, tr0, tr1, mu, raw, B, Y, nullptr, st);
     return -1;
   }
   if (K == 32) {

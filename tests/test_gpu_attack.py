@@ -110,10 +110,10 @@ def test_multi_tile_matches_oracle(n, weights, density):
 DEFAULT_ENGINE = {0: 5, 1: 3, 2: 2}      # propagate: tcgen05 fp16x2 (v5); fold: persistent row-run tcgen05 (TMEM-resident A); pairs: tcgen05 (entropy-only) / mma.sync
 
 
-@pytest.mark.parametrize("which,eng", [(0, 1), (0, 4), (0, 5), (1, 1), (1, 2), (1, 3), (2, 1)])
+@pytest.mark.parametrize("which,eng", [(0, 5), (1, 2), (1, 3), (2, 1)])
 def test_engines_agree(which, eng):
-    """exact-fp32 FFMA engine (v1) vs the tensor-core engines (mma.sync 3xTF32, tcgen05 3xTF32) of propagate (0) /
-    fold (1) / pairs (2) on the same inputs."""
+    """exact-fp32 FFMA engine 0 vs the tensor-core engines of propagate (0: tcgen05 fp16x2) / fold (1: tcgen05 3xTF32,
+    one tile per CTA and persistent row runs) / pairs (2: mma.sync 3xTF32) on the same inputs."""
     from mcgra_b200 import _native as N
     d = np.load(os.path.join(GOLDEN, "attack_mse_all_n150.npz"))
     try:
@@ -184,7 +184,7 @@ def test_pairs_tcgen05_engine_agrees(n, f, epochs):
         assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
 
 
-@pytest.mark.parametrize("eng", [2, 4, 5])
+@pytest.mark.parametrize("eng", [5])
 @pytest.mark.parametrize("case", ["mse_all_n150", "kl_C_n150"])
 def test_tcgen05_propagate_engine_agrees(case, eng):
     """tcgen05 propagate engines (2: direct product on tcgen05/TMEM + mirrored on mma.sync; 4: both on tcgen05 with the
@@ -202,7 +202,7 @@ def test_tcgen05_propagate_engine_agrees(case, eng):
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-5
 
 
-@pytest.mark.parametrize("eng", [2, 4, 5])
+@pytest.mark.parametrize("eng", [5])
 def test_tcgen05_propagate_multi_tile(eng):
     from helpers import synthetic_case
     from mcgra_b200 import _native as N
