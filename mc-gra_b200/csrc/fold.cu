@@ -834,7 +834,7 @@ k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
       __syncwarp();
       if (lane == 0) ws_arrive(&sm.dempty);              // the MMA warp may form the product of tile k + 1
       rs_cons_sync();                                    // B: product tile + node vectors visible
-      if (has_next) load_consts(nx);
+      if (has_next) load_consts(nx);                     // (deferring the shared-memory stores to the end of the tile measured slower)
 
       float* xt = tiles + (t_begin + k) * (int64_t)TILE_ELEMS;
       float* mt = mbuf + (t_begin + k) * (int64_t)TILE_ELEMS;

@@ -616,6 +616,8 @@ int launch_prop_h(const float* tiles, int64_t n, int tr0, int tr1, const float* 
 // 5 = tcgen05 kind::f16 on the fp16x2 image (default).  (Engines 1-4 of rounds 1-2 -- mma.sync 3xTF32, the tcgen05 tf32
 // hybrids -- are gone; their measurements are in profiles/history and profiles/r01_umma_rate.txt.)
 int g_prop_engine = 5;
+int g_elem_engine = 1;     // mcgra_set_engine(4, v): 0 = k_elem_stats everywhere, 1 = bulk-staged persistent k_elem_rs for the steady state
+int g_elem_grid = 0;       // test knob: cap on the persistent grid (mcgra_set_engine(4, 100 + cap); 0 = one CTA per SM)
 
 
 // ---------------------------------------------------------------------------------------------------------
@@ -730,6 +732,193 @@ k_elem_stats(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
   if (ea.k6 != 0.f) block_atomic_add_d((double)v6 * (double)ea.k6, ea.acc + MCGRA_ACC_C6, red);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_elem_rs: the same pass as k_elem_stats for the steady state of the headline profile (buffer holds the clamped
+// parameter, MSE against feature_adj, optional entropy term), persistent and bulk-staged: every CTA walks a contiguous run
+// of tiles in storage order; one producer lane streams x' and F rows (16 rows per stage) through a cp.async.bulk ring in
+// shared memory, 16 warps consume one row each per stage.  Row / column sums, node vectors and the tile switch are double
+// buffered by tile parity: one consumer barrier per tile.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ES_S = 6;                        // ring stages
+constexpr int ES_R = 16;                       // rows per stage
+constexpr int ES_CH = ES_R * TILE;             // floats per array per stage
+constexpr int ES_CW = 16;                      // consumer warps
+constexpr int ES_THREADS = 32 + ES_CW * 32;
+
+struct ElemRsSmem {
+  float ring[ES_S][2][ES_CH];                  // x', F
+  float rI[2][TILE], rJ[2][TILE];              // by tile parity
+  float rowacc[2][TILE], colacc[2][TILE];
+  double dsum[2];
+  uint64_t full[ES_S], empty[ES_S];
+};
+
+__global__ void __launch_bounds__(ES_THREADS, 1)
+k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, const __grid_constant__ mcgra_elem_args ea) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ElemRsSmem& sm = *reinterpret_cast<ElemRsSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t t_begin = (int64_t)blockIdx.x * ntiles / gridDim.x;
+  const int64_t t_end = (int64_t)(blockIdx.x + 1) * ntiles / gridDim.x;
+  const int my_tiles = (int)(t_end - t_begin);
+  if (tid == 0) {
+    for (int s = 0; s < ES_S; ++s) {
+      tc::mbar_init(&sm.full[s], 1);
+      tc::mbar_init(&sm.empty[s], ES_CW);
+    }
+    sm.dsum[0] = 0.0;
+    sm.dsum[1] = 0.0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 2 * TILE) { (&sm.rowacc[0][0])[tid] = 0.f; (&sm.colacc[0][0])[tid] = 0.f; }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        const int64_t base = (t_begin + k) * (int64_t)TILE_ELEMS;
+#pragma unroll 1
+        for (int ch = 0; ch < TILE / ES_R; ++ch) {
+          tc::mbar_wait_backoff(&sm.empty[s], ph ^ 1u);
+          const int64_t o = base + (int64_t)ch * ES_CH;
+          tc::mbar_expect_tx(&sm.full[s], 2u * ES_CH * 4u);
+          tc::bulk_g2s(sm.ring[s][0], tiles + o, ES_CH * 4u, &sm.full[s]);
+          tc::bulk_g2s(sm.ring[s][1], ea.Ftiles + o, ES_CH * 4u, &sm.full[s]);
+          if (++s == ES_S) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+  const int cw = warp - 1, ct = tid - 32;
+  const int b0 = lane * 4;
+  int I, J;
+  tile_coords(tri((int64_t)tr0) + t_begin, I, J);
+  auto load_r = [&](int buf, int Ix, int Jx) {
+    if (ct < TILE) {
+      const int64_t gi = (int64_t)Ix * TILE + ct, gj = (int64_t)Jx * TILE + ct;
+      sm.rI[buf][ct] = gi < n ? ea.r[gi] : 0.f;
+      sm.rJ[buf][ct] = gj < n ? ea.r[gj] : 0.f;
+    }
+  };
+  if (my_tiles > 0) load_r(0, I, J);
+  const float k1x4 = 4.f * ea.k1, k6x2 = 2.f * ea.k6;
+  const bool ent = ea.k6 != 0.f;
+  double d1 = 0.0, d6 = 0.0;
+  uint32_t s = 0, ph = 0;
+  int Iprev = 0, Jprev = 0;
+#pragma unroll 1
+  for (int k = 0; k < my_tiles; ++k) {
+    const int p = k & 1;
+    int In = I, Jn = J + 1;
+    if (Jn > In) { ++In; Jn = 0; }
+    asm volatile("bar.sync 1, %0;" ::"n"(ES_CW * 32) : "memory");   // tile k - 1 complete everywhere; r[p] visible
+    if (ct < TILE) {
+      if (k > 0) {                               // sums of tile k - 1 (parity p ^ 1) -> eps_row, while tile k streams
+        const float rs = sm.rowacc[p ^ 1][ct], cs = sm.colacc[p ^ 1][ct];
+        const int64_t gi = (int64_t)Iprev * TILE + ct, gj = (int64_t)Jprev * TILE + ct;
+        if (gi < n && rs != 0.f) atomicAdd(ea.eps_row + gi, rs);
+        if (gj < n && cs != 0.f) atomicAdd(ea.eps_row + gj, cs);
+        sm.colacc[p ^ 1][ct] = 0.f;
+      }
+    }
+    // node vectors of tile k + 1: loads issued now, parked in shared memory after the stream (no stall on their latency)
+    float nrI = 0.f, nrJ = 0.f;
+    if (k + 1 < my_tiles && ct < TILE) {
+      const int64_t gi = (int64_t)In * TILE + ct, gj = (int64_t)Jn * TILE + ct;
+      nrI = gi < n ? ea.r[gi] : 0.f;
+      nrJ = gj < n ? ea.r[gj] : 0.f;
+    }
+    const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
+    const bool interior = (J < I) && (i0 + TILE <= n);
+    float rj4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rj4[q] = sm.rJ[p][b0 + q];
+    float col_e[4] = {0.f, 0.f, 0.f, 0.f};
+    float v1 = 0.f, v6 = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < TILE / ES_R; ++ch) {
+      tc::mbar_wait(&sm.full[s], ph);
+      const float4 X = *reinterpret_cast<const float4*>(&sm.ring[s][0][cw * TILE + b0]);
+      const float4 F = *reinterpret_cast<const float4*>(&sm.ring[s][1][cw * TILE + b0]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive1(&sm.empty[s]);
+      if (++s == ES_S) { s = 0; ph ^= 1u; }
+      const int a = ch * ES_R + cw;
+      const float ri = sm.rI[p][a];
+      const float xs[4] = {X.x, X.y, X.z, X.w}, fs[4] = {F.x, F.y, F.z, F.w};
+      float row_e = 0.f;
+      if (interior) {                              // every entry valid: ~16 instructions per entry
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float ah = (ri * rj4[q]) * xs[q];
+          const float df = ah - fs[q];
+          v1 = fmaf(df, df, v1);                   // (x 2 below)
+          float esym = k1x4 * df;
+          if (ent) {
+            const float qc = fminf(fmaxf(ah, ENT_LO), ENT_HI);
+            const float lg = __log2f(qc);
+            v6 = fmaf(qc, lg, v6);                 // (x 2 below)
+            if (qc == ah) esym = fmaf(k6x2, lg + INV_LN2, esym);
+          }
+          const float tt = esym * xs[q];
+          row_e = fmaf(tt, rj4[q], row_e);
+          col_e[q] = fmaf(tt, ri, col_e[q]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool valid = ((j0 + b0 + q) < (i0 + a) && (i0 + a) < n);
+          if (!valid) continue;
+          const float ah = (ri * rj4[q]) * xs[q];
+          const float df = ah - fs[q];
+          v1 = fmaf(df, df, v1);
+          float esym = k1x4 * df;
+          if (ent) {
+            const float qc = fminf(fmaxf(ah, ENT_LO), ENT_HI);
+            const float lg = __log2f(qc);
+            v6 = fmaf(qc, lg, v6);
+            if (qc == ah) esym = fmaf(k6x2, lg + INV_LN2, esym);
+          }
+          const float tt = esym * xs[q];
+          row_e = fmaf(tt, rj4[q], row_e);
+          col_e[q] = fmaf(tt, ri, col_e[q]);
+        }
+      }
+      row_e = warp_sum(row_e);
+      if (lane == 0) sm.rowacc[p][a] = row_e;      // every row is visited by exactly one warp per tile
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (col_e[q] != 0.f) atomicAdd(&sm.colacc[p][b0 + q], col_e[q]);
+    if (k + 1 < my_tiles && ct < TILE) { sm.rI[p ^ 1][ct] = nrI; sm.rJ[p ^ 1][ct] = nrJ; }   // (last read by tile k - 1)
+    d1 += 2.0 * (double)v1;
+    d6 += 2.0 * (double)v6;
+    Iprev = I; Jprev = J;
+    I = In; J = Jn;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(ES_CW * 32) : "memory");
+  if (ct < TILE && my_tiles > 0) {
+    const int p = (my_tiles - 1) & 1;
+    const float rs = sm.rowacc[p][ct], cs = sm.colacc[p][ct];
+    const int64_t gi = (int64_t)Iprev * TILE + ct, gj = (int64_t)Jprev * TILE + ct;
+    if (gi < n && rs != 0.f) atomicAdd(ea.eps_row + gi, rs);
+    if (gj < n && cs != 0.f) atomicAdd(ea.eps_row + gj, cs);
+  }
+  d1 = warp_sum_d(d1);
+  d6 = warp_sum_d(d6);
+  if (lane == 0) {
+    atomicAdd(&sm.dsum[0], d1);
+    atomicAdd(&sm.dsum[1], d6);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(ES_CW * 32) : "memory");
+  if (ct == 0) {
+    if (sm.dsum[0] != 0.0) atomicAdd(ea.acc + MCGRA_ACC_C1, sm.dsum[0] * (double)ea.k1);
+    if (ent && sm.dsum[1] != 0.0) atomicAdd(ea.acc + MCGRA_ACC_C6, sm.dsum[1] * (double)ea.k6);
+  }
+}
+
 template <int KC, bool ELEM>
 int launch_prop(const float* tiles, int64_t n, int64_t t0, int64_t nt, const float* mu, int raw, const float* B,
                 float* Y, const mcgra_elem_args* elem, cudaStream_t st) {
@@ -752,6 +941,11 @@ int mcgra_set_pairs_engine_(int value);
 int mcgra_set_gemm_engine_(int value);
 int mcgra_set_engine(int which, int value) {
   if (which == 3) return mcgra_set_gemm_engine_(value);
+  if (which == 4) {
+    if (value >= 100) g_elem_grid = value - 100;
+    else g_elem_engine = value;
+    return 0;
+  }
   if (which == 0 && value >= 100) { g_prop_dbg = value - 100; return 0; }
   if (which == 0) { g_prop_engine = value; return 0; }
   if (which == 1) return mcgra_set_fold_engine_(value);
@@ -780,6 +974,21 @@ int mcgra_elem_stats(const float* tiles, int64_t n, int tr0, int tr1, const floa
                      const mcgra_elem_args* elem, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0 || elem == nullptr) return 0;
+  if (g_elem_engine == 1 && raw == 2 && elem->measure == MCGRA_M_MSE && elem->Ftiles != nullptr) {
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const size_t smem = sizeof(ElemRsSmem) + 128;
+    cudaError_t e = cudaFuncSetAttribute(k_elem_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int cap = g_elem_grid > 0 ? g_elem_grid : sms;
+    k_elem_rs<<<(unsigned)(nt < cap ? nt : cap), ES_THREADS, smem, (cudaStream_t)stream>>>(tiles, n, tr0, nt, *elem);
+    MCGRA_LAUNCH_CHECK();
+    return 0;
+  }
   k_elem_stats<<<(unsigned)nt, 256, 0, (cudaStream_t)stream>>>(tiles, n, tri(tr0), mu, raw, *elem);
   MCGRA_LAUNCH_CHECK();
   return 0;

@@ -107,10 +107,10 @@ def test_multi_tile_matches_oracle(n, weights, density):
     np.testing.assert_allclose(got["modified_adj"], ref["modified_adj"].numpy(), rtol=1e-3, atol=1e-3)
 
 
-DEFAULT_ENGINE = {0: 5, 1: 3, 2: 2}      # propagate: tcgen05 fp16x2 (v5); fold: persistent row-run tcgen05 (TMEM-resident A); pairs: tcgen05 (entropy-only) / mma.sync
+DEFAULT_ENGINE = {0: 5, 1: 3, 2: 2, 4: 1}      # propagate: tcgen05 fp16x2 (v5); fold: persistent row-run tcgen05 (TMEM-resident A); pairs: tcgen05 (entropy-only) / mma.sync
 
 
-@pytest.mark.parametrize("which,eng", [(0, 5), (1, 2), (1, 3), (2, 1)])
+@pytest.mark.parametrize("which,eng", [(0, 5), (1, 2), (1, 3), (2, 1), (4, 1)])
 def test_engines_agree(which, eng):
     """exact-fp32 FFMA engine 0 vs the tensor-core engines of propagate (0: tcgen05 fp16x2) / fold (1: tcgen05 3xTF32,
     one tile per CTA and persistent row runs) / pairs (2: mma.sync 3xTF32) on the same inputs."""
@@ -151,6 +151,26 @@ def test_fold_persistent_engine_multi_tile(eng, density, grid):
     # (not bit-equal: the degree row sums and the norm term are accumulated with float / double atomics in tile order)
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-6
     np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-5, atol=5e-6)
+
+
+@pytest.mark.parametrize("grid", [5, 0])
+def test_elem_persistent_engine_multi_tile(grid):
+    """element-wise pass: bulk-staged persistent kernel (engine 1 of stage 4) against the one-tile-per-CTA kernel with
+    several tiles and tile rows per CTA (n = 1500, ragged last row, grid capped to 5 CTAs / uncapped)."""
+    from helpers import synthetic_case
+    from mcgra_b200 import _native as N
+    d = synthetic_case(1500, 40, 5, weights={1: 0.01, 6: 10.0, 7: 10.0, 9: 10.0, 10: 1000.0}, epochs=4, mean_deg=8.0)
+    try:
+        N.lib().mcgra_set_engine(4, 0)
+        a = run_native_case(d)
+        N.lib().mcgra_set_engine(4, 1)
+        N.lib().mcgra_set_engine(4, 100 + grid)
+        b = run_native_case(d)
+    finally:
+        N.lib().mcgra_set_engine(4, 100)
+        N.lib().mcgra_set_engine(4, DEFAULT_ENGINE[4])
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)
+    assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-6
 
 
 @pytest.mark.parametrize("n,f,epochs", [(150, 24, 4), (1300, 40, 2), (4500, 32, 2)])

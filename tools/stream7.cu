@@ -238,6 +238,70 @@ k_probe(float* __restrict__ x, float* __restrict__ m, float* __restrict__ v, con
   }
 }
 
+// ---- pure-read probes (the element-wise pass reads x and F only) ----
+template <int U>
+__global__ void k_read_ldg(const float* __restrict__ x, const float* __restrict__ f, int ntiles, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float acc = 0.f;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = (int64_t)t * TE + lane * 4;
+    for (int it = 0; it < TILE / nw / U; ++it) {
+      float4 X[U], F[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t o = base + (int64_t)((it * U + u) * nw + warp) * TILE;
+        X[u] = *(const float4*)(x + o); F[u] = *(const float4*)(f + o);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc += X[u].x * F[u].x + X[u].y * F[u].y + X[u].z * F[u].z + X[u].w * F[u].w;
+    }
+  }
+  if (acc == 12345.f) out[0] = acc;
+}
+template <int S, int R>
+__global__ void k_read_bulk(const float* __restrict__ x, const float* __restrict__ f, int ntiles, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int CH = R * TILE;
+  float* buf = reinterpret_cast<float*>(smem);            // [S][2][CH]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * 2 * CH * 4);
+  uint64_t* empty = full + S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ncw = (blockDim.x >> 5) - 1;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncw); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_tiles * (TILE / R);
+  if (warp == 0) {
+    if (lane == 0)
+      for (int c = 0; c < total; ++c) {
+        const int s = c % S;
+        mbar_wait_sleep(&empty[s], (uint32_t)(((c / S) & 1) ^ 1));
+        const int t = blockIdx.x + (c / (TILE / R)) * gridDim.x;
+        const int64_t o = (int64_t)t * TE + (int64_t)(c % (TILE / R)) * CH;
+        mbar_expect(&full[s], 2u * CH * 4u);
+        bulk_g2s(buf + (size_t)s * 2 * CH, x + o, CH * 4, &full[s]);
+        bulk_g2s(buf + (size_t)s * 2 * CH + CH, f + o, CH * 4, &full[s]);
+      }
+    return;
+  }
+  float acc = 0.f;
+  const int ct = tid - 32, nct = ncw * 32;
+  for (int c = 0; c < total; ++c) {
+    const int s = c % S;
+    mbar_wait(&full[s], (uint32_t)((c / S) & 1));
+    const float* b = buf + (size_t)s * 2 * CH;
+    for (int e = ct * 4; e < CH; e += nct * 4) {
+      const float4 X = *(const float4*)(b + e), F = *(const float4*)(b + CH + e);
+      acc += X.x * F.x + X.y * F.y + X.z * F.z + X.w * F.w;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  if (acc == 12345.f) out[0] = acc;
+}
+
 template <typename F>
 float timeit(F&& launch, int reps = 5) {
   cudaEvent_t a, b;
@@ -321,6 +385,13 @@ int main(int argc, char** argv) {
     float ms = timeit([&] { k_probe<S, OPS><<<sms, 576, sm>>>(x, m, v, f, ntiles, W, wblocks, dn, 0.04f, -2.f, 1e-4f, 0.01f); }); \
     printf("probe S=%d operand-traffic=%d (%zu KB smem): %.3f ms  %.0f GB/s\n", S, OPS, sm / 1024, ms, gb * 1e3 / ms); \
   }
+    {
+      const double gbr = 2.0 * bytes / 1e9;
+#define RUN_RLDG(U, W, B) { float ms = timeit([&] { k_read_ldg<U><<<sms * B, W * 32>>>(x, f, ntiles, dn); }); printf("read ldg U=%d warps=%d cta/sm=%d: %.3f ms %.0f GB/s\n", U, W, B, ms, gbr * 1e3 / ms); }
+      RUN_RLDG(8, 8, 2) RUN_RLDG(4, 8, 4) RUN_RLDG(8, 8, 4) RUN_RLDG(4, 16, 2)
+#define RUN_RBULK(S, R, T) { const size_t sm = (size_t)S * 2 * R * TILE * 4 + 2 * S * 8 + 64; CK(cudaFuncSetAttribute(k_read_bulk<S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); float ms = timeit([&] { k_read_bulk<S, R><<<sms, T, sm>>>(x, f, ntiles, dn); }); printf("read bulk S=%d R=%d threads=%d (%zu KB): %.3f ms %.0f GB/s\n", S, R, T, sm / 1024, ms, gbr * 1e3 / ms); }
+      RUN_RBULK(6, 16, 544) RUN_RBULK(8, 16, 544) RUN_RBULK(12, 16, 288) RUN_RBULK(6, 32, 544) RUN_RBULK(4, 64, 544)
+    }
     RUN_PROBE(5, 1)
     RUN_PROBE(5, 0)
     RUN_PROBE(4, 1)
