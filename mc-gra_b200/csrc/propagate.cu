@@ -739,8 +739,8 @@ k_elem_stats(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
 // shared memory, 16 warps consume one row each per stage.  Row / column sums, node vectors and the tile switch are double
 // buffered by tile parity: one consumer barrier per tile.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int ES_S = 6;                        // ring stages
-constexpr int ES_R = 16;                       // rows per stage
+constexpr int ES_S = 4;                        // ring stages
+constexpr int ES_R = 32;                       // rows per stage: warp cw takes rows cw and cw + 16 of a stage
 constexpr int ES_CH = ES_R * TILE;             // floats per array per stage
 constexpr int ES_CW = 16;                      // consumer warps
 constexpr int ES_THREADS = 32 + ES_CW * 32;
@@ -748,7 +748,8 @@ constexpr int ES_THREADS = 32 + ES_CW * 32;
 struct ElemRsSmem {
   float ring[ES_S][2][ES_CH];                  // x', F
   float rI[2][TILE], rJ[2][TILE];              // by tile parity
-  float rowacc[2][TILE], colacc[2][TILE];
+  float rowpart[2][TILE][33];                  // per-lane row sums (summed once per tile instead of a shuffle chain per row)
+  float colacc[2][TILE];
   double dsum[2];
   uint64_t full[ES_S], empty[ES_S];
 };
@@ -770,7 +771,7 @@ k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, c
     sm.dsum[1] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 2 * TILE) { (&sm.rowacc[0][0])[tid] = 0.f; (&sm.colacc[0][0])[tid] = 0.f; }
+  if (tid < 2 * TILE) (&sm.colacc[0][0])[tid] = 0.f;
   __syncthreads();
 
   if (warp == 0) {
@@ -795,34 +796,32 @@ k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, c
   const int b0 = lane * 4;
   int I, J;
   tile_coords(tri((int64_t)tr0) + t_begin, I, J);
-  auto load_r = [&](int buf, int Ix, int Jx) {
-    if (ct < TILE) {
-      const int64_t gi = (int64_t)Ix * TILE + ct, gj = (int64_t)Jx * TILE + ct;
-      sm.rI[buf][ct] = gi < n ? ea.r[gi] : 0.f;
-      sm.rJ[buf][ct] = gj < n ? ea.r[gj] : 0.f;
-    }
-  };
-  if (my_tiles > 0) load_r(0, I, J);
+  if (my_tiles > 0 && ct < TILE) {
+    const int64_t gi = (int64_t)I * TILE + ct, gj = (int64_t)J * TILE + ct;
+    sm.rI[0][ct] = gi < n ? ea.r[gi] : 0.f;
+    sm.rJ[0][ct] = gj < n ? ea.r[gj] : 0.f;
+  }
   const float k1x4 = 4.f * ea.k1, k6x2 = 2.f * ea.k6;
   const bool ent = ea.k6 != 0.f;
   double d1 = 0.0, d6 = 0.0;
   uint32_t s = 0, ph = 0;
   int Iprev = 0, Jprev = 0;
+  auto flush = [&](int p, int Ix, int Jx) {          // sums of a finished tile (parity p) -> eps_row (threads < 128)
+    float rs = 0.f;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) rs += sm.rowpart[p][ct][l];
+    const float cs = sm.colacc[p][ct];
+    const int64_t gi = (int64_t)Ix * TILE + ct, gj = (int64_t)Jx * TILE + ct;
+    if (gi < n && rs != 0.f) atomicAdd(ea.eps_row + gi, rs);
+    if (gj < n && cs != 0.f) atomicAdd(ea.eps_row + gj, cs);
+    sm.colacc[p][ct] = 0.f;
+  };
 #pragma unroll 1
   for (int k = 0; k < my_tiles; ++k) {
     const int p = k & 1;
     int In = I, Jn = J + 1;
     if (Jn > In) { ++In; Jn = 0; }
     asm volatile("bar.sync 1, %0;" ::"n"(ES_CW * 32) : "memory");   // tile k - 1 complete everywhere; r[p] visible
-    if (ct < TILE) {
-      if (k > 0) {                               // sums of tile k - 1 (parity p ^ 1) -> eps_row, while tile k streams
-        const float rs = sm.rowacc[p ^ 1][ct], cs = sm.colacc[p ^ 1][ct];
-        const int64_t gi = (int64_t)Iprev * TILE + ct, gj = (int64_t)Jprev * TILE + ct;
-        if (gi < n && rs != 0.f) atomicAdd(ea.eps_row + gi, rs);
-        if (gj < n && cs != 0.f) atomicAdd(ea.eps_row + gj, cs);
-        sm.colacc[p ^ 1][ct] = 0.f;
-      }
-    }
     // node vectors of tile k + 1: loads issued now, parked in shared memory after the stream (no stall on their latency)
     float nrI = 0.f, nrJ = 0.f;
     if (k + 1 < my_tiles && ct < TILE) {
@@ -830,6 +829,7 @@ k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, c
       nrI = gi < n ? ea.r[gi] : 0.f;
       nrJ = gj < n ? ea.r[gj] : 0.f;
     }
+    if (k > 0 && ct < TILE) flush(p ^ 1, Iprev, Jprev);            // while tile k streams
     const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
     const bool interior = (J < I) && (i0 + TILE <= n);
     float rj4[4];
@@ -840,54 +840,60 @@ k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, c
 #pragma unroll 1
     for (int ch = 0; ch < TILE / ES_R; ++ch) {
       tc::mbar_wait(&sm.full[s], ph);
-      const float4 X = *reinterpret_cast<const float4*>(&sm.ring[s][0][cw * TILE + b0]);
-      const float4 F = *reinterpret_cast<const float4*>(&sm.ring[s][1][cw * TILE + b0]);
+      float4 X[2], F[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        X[h] = *reinterpret_cast<const float4*>(&sm.ring[s][0][(h * 16 + cw) * TILE + b0]);
+        F[h] = *reinterpret_cast<const float4*>(&sm.ring[s][1][(h * 16 + cw) * TILE + b0]);
+      }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive1(&sm.empty[s]);
       if (++s == ES_S) { s = 0; ph ^= 1u; }
-      const int a = ch * ES_R + cw;
-      const float ri = sm.rI[p][a];
-      const float xs[4] = {X.x, X.y, X.z, X.w}, fs[4] = {F.x, F.y, F.z, F.w};
-      float row_e = 0.f;
-      if (interior) {                              // every entry valid: ~16 instructions per entry
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float ah = (ri * rj4[q]) * xs[q];
-          const float df = ah - fs[q];
-          v1 = fmaf(df, df, v1);                   // (x 2 below)
-          float esym = k1x4 * df;
-          if (ent) {
-            const float qc = fminf(fmaxf(ah, ENT_LO), ENT_HI);
-            const float lg = __log2f(qc);
-            v6 = fmaf(qc, lg, v6);                 // (x 2 below)
-            if (qc == ah) esym = fmaf(k6x2, lg + INV_LN2, esym);
-          }
-          const float tt = esym * xs[q];
-          row_e = fmaf(tt, rj4[q], row_e);
-          col_e[q] = fmaf(tt, ri, col_e[q]);
-        }
-      } else {
+      for (int h = 0; h < 2; ++h) {
+        const int a = ch * ES_R + h * 16 + cw;
+        const float ri = sm.rI[p][a];
+        const float xs[4] = {X[h].x, X[h].y, X[h].z, X[h].w}, fs[4] = {F[h].x, F[h].y, F[h].z, F[h].w};
+        float row_e = 0.f;
+        if (interior) {                            // every entry valid: ~16 instructions per entry
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool valid = ((j0 + b0 + q) < (i0 + a) && (i0 + a) < n);
-          if (!valid) continue;
-          const float ah = (ri * rj4[q]) * xs[q];
-          const float df = ah - fs[q];
-          v1 = fmaf(df, df, v1);
-          float esym = k1x4 * df;
-          if (ent) {
-            const float qc = fminf(fmaxf(ah, ENT_LO), ENT_HI);
-            const float lg = __log2f(qc);
-            v6 = fmaf(qc, lg, v6);
-            if (qc == ah) esym = fmaf(k6x2, lg + INV_LN2, esym);
+          for (int q = 0; q < 4; ++q) {
+            const float ah = (ri * rj4[q]) * xs[q];
+            const float df = ah - fs[q];
+            v1 = fmaf(df, df, v1);                 // (x 2 below)
+            float esym = k1x4 * df;
+            if (ent) {
+              const float qc = fminf(fmaxf(ah, ENT_LO), ENT_HI);
+              const float lg = __log2f(qc);
+              v6 = fmaf(qc, lg, v6);               // (x 2 below)
+              if (qc == ah) esym = fmaf(k6x2, lg + INV_LN2, esym);
+            }
+            const float tt = esym * xs[q];
+            row_e = fmaf(tt, rj4[q], row_e);
+            col_e[q] = fmaf(tt, ri, col_e[q]);
           }
-          const float tt = esym * xs[q];
-          row_e = fmaf(tt, rj4[q], row_e);
-          col_e[q] = fmaf(tt, ri, col_e[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool valid = ((j0 + b0 + q) < (i0 + a) && (i0 + a) < n);
+            if (!valid) continue;
+            const float ah = (ri * rj4[q]) * xs[q];
+            const float df = ah - fs[q];
+            v1 = fmaf(df, df, v1);
+            float esym = k1x4 * df;
+            if (ent) {
+              const float qc = fminf(fmaxf(ah, ENT_LO), ENT_HI);
+              const float lg = __log2f(qc);
+              v6 = fmaf(qc, lg, v6);
+              if (qc == ah) esym = fmaf(k6x2, lg + INV_LN2, esym);
+            }
+            const float tt = esym * xs[q];
+            row_e = fmaf(tt, rj4[q], row_e);
+            col_e[q] = fmaf(tt, ri, col_e[q]);
+          }
         }
+        sm.rowpart[p][a][lane] = row_e;            // every row is visited by exactly one warp per tile
       }
-      row_e = warp_sum(row_e);
-      if (lane == 0) sm.rowacc[p][a] = row_e;      // every row is visited by exactly one warp per tile
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -899,13 +905,7 @@ k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, c
     I = In; J = Jn;
   }
   asm volatile("bar.sync 1, %0;" ::"n"(ES_CW * 32) : "memory");
-  if (ct < TILE && my_tiles > 0) {
-    const int p = (my_tiles - 1) & 1;
-    const float rs = sm.rowacc[p][ct], cs = sm.colacc[p][ct];
-    const int64_t gi = (int64_t)Iprev * TILE + ct, gj = (int64_t)Jprev * TILE + ct;
-    if (gi < n && rs != 0.f) atomicAdd(ea.eps_row + gi, rs);
-    if (gj < n && cs != 0.f) atomicAdd(ea.eps_row + gj, cs);
-  }
+  if (ct < TILE && my_tiles > 0) flush((my_tiles - 1) & 1, Iprev, Jprev);
   d1 = warp_sum_d(d1);
   d6 = warp_sum_d(d6);
   if (lane == 0) {
