@@ -53,12 +53,16 @@ def full(reps, out):
 
 
 if __name__ == "__main__":
-    launches("r02_large_A_launches.csv", "r02_large_A_launches.txt", "bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-parity (n = 65536, Profile A)")
+    launches("r02_large_A_launches.csv", "r02_large_A_launches.txt", "bench.py --steps 2 --warmup 2 --no-e2e --no-cpu --no-parity (n = 65536, Profile A)")
     launches("r02_pubmed_B_launches.csv", "r02_pubmed_B_launches.txt", "bench.py --workload pubmed --profile B --steps 2 --warmup 1 ... (n = 19717, HSIC)")
-    t = full(["r02_fold_tc.ncu-rep", "r02_pairs_tc.ncu-rep", "r02_gemm3.ncu-rep"], "r02_ncu_full.csv")
+    # r02_fold_rs / r02_elem_rs: the final streaming kernels (tools/profile_r2b.sh); r02b_fold_tc: the one-tile-per-CTA
+    # engine they replaced, steady-state launch; pairs / gemm captures from tools/profile_r2.sh
+    t = full(["r02_fold_rs.ncu-rep", "r02_elem_rs.ncu-rep", "r02b_fold_tc.ncu-rep", "r02_pairs_tc.ncu-rep", "r02_gemm3.ncu-rep"],
+             "r02_ncu_full.csv")
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     allt = json.load(open(tp)) if os.path.exists(tp) else {}
-    allt["large_A"] = {"mcgra_fold_adam": round(t.get("k_fold_tc", 0)), "mcgra_pairs": round(t.get("k_pairs_tc", 0))}
+    allt["large_A"] = {"mcgra_fold_adam": round(t.get("k_fold_rs", t.get("k_fold_tc", 0))), "elem_stats": round(t.get("k_elem_rs", 0)),
+                       "mcgra_pairs": round(t.get("k_pairs_tc", 0))}
     allt["pubmed_B"] = {k: round(t.get("k_gemm3<2>", 0)) for k in ("gemm_grad", "gemm_c1", "gemm_c2_T")}
     allt["_source_r02"] = "profiles/r02_ncu_full.csv (ncu --set full --clock-control none; dram bytes read + written per launch)"
     json.dump(allt, open(tp, "w"), indent=1, sort_keys=True)

@@ -36,10 +36,18 @@ def main():
         d = np.load(os.path.join(ROOT, "tests", "golden", f"attack_{case}.npz"))
         got = run_native_case(d, device=f"cuda:{local}")
         e_loss = float(np.max(np.abs(got["loss"] - d["loss"]) / np.abs(d["loss"])))
+        if case.startswith("kde"):
+            # the reference's fp32 MutualInformation is itself 1e-4 .. 1e-3 from its fp64 value (tests/test_oracle_golden.py::
+            # test_kde_reference_fp32_is_off_its_fp64): hold the sharded run to the fp64 oracle at its own parameter
+            prob64, cfg64 = O.problem_from_npz(d, dtype=torch.float64)
+            xs_prev = [d["x0"]] + got["x_iters"][:-1]
+            forced = np.array([float(O.iteration_terms(torch.from_numpy(np.asarray(xp)).double(), prob64, cfg64)[0]) for xp in xs_prev])
+            e_loss = float(np.max(np.abs(np.asarray(got["loss"]) - forced) / np.abs(forced)))
         dx = np.abs(np.stack(got["x_iters"]) - d["x_iters"])
         frac = float(np.mean(dx > 2e-4))
         if rank == 0:
-            print(f"[mgpu world={dist.get_world_size()}] {case}: rel loss err {e_loss:.2e} frac|dx|>2e-4 {frac:.2e}")
+            print(f"[mgpu world={dist.get_world_size()}] {case}: rel loss err {e_loss:.2e} frac|dx|>2e-4 {frac:.2e}"
+                  + (" (loss vs fp64 oracle at the native parameter)" if case.startswith("kde") else ""))
         # (kl_* and hsic_all_n90 are the listed tie-break cases of tests/test_gpu_attack.py: their free-running fp32
         #  trajectories are allowed to separate from the reference's by more than 1e-4)
         ok &= e_loss < (4e-4 if (case.startswith("kl") or case == "hsic_all_n90") else 1e-4) and frac < 0.01

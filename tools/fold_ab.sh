@@ -1,5 +1,5 @@
 # same-box A/B of fold variants at the bench shape (n = 65 536, Profile A): MCGRA_ENGINES="1:<engine or 1000 + experiment bits>"
-for e in "1:1000" "1:1001" "1:1000" "1:1001" "1:2"; do
+for e in "1:1000" "1:1003" "1:1007" "1:1002" "1:1004" "1:1000" "1:1007"; do
 MCGRA_ENGINES="$e" timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --no-parity > gpurun_out/fold_ab.json 2>gpurun_out/fold_ab.err
 python - "$e" <<PY
 import json,sys
