@@ -61,8 +61,11 @@ if __name__ == "__main__":
              "r02_ncu_full.csv")
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     allt = json.load(open(tp)) if os.path.exists(tp) else {}
-    allt["large_A"] = {"mcgra_fold_adam": round(t.get("k_fold_rs", t.get("k_fold_tc", 0))), "elem_stats": round(t.get("k_elem_rs", 0)),
-                       "mcgra_pairs": round(t.get("k_pairs_tc", 0))}
+    pick = lambda pre: next((v for k, v in t.items() if k.startswith(pre)), 0)
+    allt["large_A"] = {"mcgra_fold_adam": round(pick("k_fold_rs")), "elem_stats": round(pick("k_elem_rs")),
+                       "mcgra_pairs": round(pick("k_pairs_tc")),
+                       "_note": "k_elem_rs: dram__bytes_read 17.2 GB (= algorithmic) + 16-17 GB that ncu books as dram writes although the "
+                                "kernel writes O(n) bytes and the sum would exceed the DRAM peak; fold: read 40.3 + write 25.8 GB"}
     allt["pubmed_B"] = {k: round(t.get("k_gemm3<2>", 0)) for k in ("gemm_grad", "gemm_c1", "gemm_c2_T")}
     allt["_source_r02"] = "profiles/r02_ncu_full.csv (ncu --set full --clock-control none; dram bytes read + written per launch)"
     json.dump(allt, open(tp, "w"), indent=1, sort_keys=True)

@@ -10,7 +10,7 @@ timeout 600 python bench.py --workload pubmed --profile B --steps 10 --warmup 3 
 timeout 600 python bench.py --density 1 --steps 10 --warmup 3 --no-cpu --no-e2e --no-parity > gpurun_out/r02_bench_large_A_density1.json 2> gpurun_out/r02_bench_density1.err
 timeout 600 python bench.py --workload cora --steps 200 --warmup 20 --no-cpu --no-parity > gpurun_out/r02_bench_cora_A.json 2> gpurun_out/r02_bench_cora.err
 # launch list (serialised, cold-cache: shares of the step, not absolute times)
-$NCU --metrics gpu__time_duration.sum -c 300 --csv --log-file gpurun_out/r02_large_A_launches.csv \
+$NCU --metrics gpu__time_duration.sum -k regex:"k_|mcgra" -c 400 --csv --log-file gpurun_out/r02_large_A_launches.csv \
   python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu --no-parity > gpurun_out/r02_prof_a.log 2>&1
 # full captures of the two new streaming kernels (steady-state launches)
 $NCU --set full --import-source on -k regex:k_fold_rs -s 2 -c 1 -o gpurun_out/r02_fold_rs -f \
