@@ -474,6 +474,9 @@ def run_native(a):
     if not graphed:
         kt = {k: float(np.mean([s.elapsed_time(e) for s, e in v])) for k, v in N.TIMERS['on'].items()}
         kcount = {k: len(v) / float(K) for k, v in N.TIMERS['on'].items()}
+        if os.environ.get("MCGRA_BENCH_DUMP_KERNEL") in N.TIMERS['on'] and rank == 0:     # per-launch times of one kernel
+            v = N.TIMERS['on'][os.environ["MCGRA_BENCH_DUMP_KERNEL"]]
+            print("[per-launch ms]", [round(s.elapsed_time(e), 3) for s, e in v][:40], file=sys.stderr)
         N.TIMERS['on'] = None
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)

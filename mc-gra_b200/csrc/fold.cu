@@ -639,11 +639,14 @@ struct RunIter {
   }
 };
 
-// MEAS: MCGRA_M_MSE / MCGRA_M_PRE / MCGRA_M_NONE; ENT: entropy term on
-template <int MEAS, bool ENT>
+// MEAS: MCGRA_M_MSE / MCGRA_M_PRE / MCGRA_M_NONE; ENT: entropy term on; LAZY: the buffer holds the un-projected Adam output
+// x' (raw == 0: parameter = clamp(x' - mu, 0, 1) on read, un-clamped store, min / max tracked for the next bisection)
+// instead of the clamped parameter itself (raw == 2)
+template <int MEAS, bool ENT, bool LAZY>
 __global__ void __launch_bounds__(RS_THREADS, 1)
 k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict__ vbuf, int tr0, int64_t ntiles,
-          const __grid_constant__ mcgra_fold_args fa, const unsigned char* __restrict__ Wk, int flags) {
+          const __grid_constant__ mcgra_fold_args fa, const unsigned char* __restrict__ Wk, int flags, const float* mu_ptr,
+          float* __restrict__ minmax) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   FoldRsSmem& sm = *reinterpret_cast<FoldRsSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -774,6 +777,8 @@ k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
       fc.k6x2 = 2.f * fa.k6;
       fc.adam_eps = fa.adam_eps;
     }
+    const float mu = LAZY ? *mu_ptr : 0.f;
+    float xmin = INFINITY, xmax = -INFINITY;
     const int qq = cw & 3;                               // TMEM lane quarter of this warp (= warp % 4)
     const int rw = cw >> 1, b0 = (cw & 1) * 64 + lane * 2;   // stage row / first column of this lane
     RunIter cur;
@@ -885,7 +890,8 @@ k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
         const int a = ch * RS_R + rw;
         const float ri = sm.rI[a], rhoi = sm.rhoI[a];
         const float2 G = *reinterpret_cast<const float2*>(&sm.u.gt[a][b0]);
-        const float xs[2] = {X.x, X.y}, ms[2] = {M.x, M.y}, vs[2] = {V.x, V.y}, fs[2] = {F.x, F.y}, gs[2] = {G.x, G.y};
+        const float xr[2] = {X.x, X.y}, ms[2] = {M.x, M.y}, vs[2] = {V.x, V.y}, fs[2] = {F.x, F.y}, gs[2] = {G.x, G.y};
+        const float xs[2] = {LAZY ? __saturatef(xr[0] - mu) : xr[0], LAZY ? __saturatef(xr[1] - mu) : xr[1]};
         float xo[2], mo[2], vo[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -900,15 +906,19 @@ k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
           const float mn = fmaf(fc.omb1, gg - ms[e], ms[e]);
           const float vn = fmaf(fc.omb2, gg * gg - vs[e], vs[e]);
           const float denom = fmaf(sqrt_approx(vn), fc.inv_sqrt_bc2, fc.adam_eps);
-          const float c = __saturatef(fmaf(fc.neg_step, __fdividef(mn, denom), xs[e]));
+          const float xn = fmaf(fc.neg_step, __fdividef(mn, denom), xs[e]);
+          const float c = __saturatef(xn);
           // diagonal / last-row tiles: entries on or above the diagonal and beyond n stay zero
           const bool valid = interior || ((j0 + b0 + e) < (i0 + a) && (i0 + a) < n);
-          xo[e] = valid ? c : 0.f;
+          const float cv = valid ? c : 0.f;
+          xo[e] = LAZY ? (valid ? xn : 0.f) : cv;
           mo[e] = valid ? mn : 0.f;
           vo[e] = valid ? vn : 0.f;
-          s_sq = fmaf(xo[e], xo[e], s_sq);
-          colp[e] += xo[e];
+          s_sq = fmaf(cv, cv, s_sq);
+          colp[e] += cv;
+          if (LAZY && valid) { xmin = fminf(xmin, xn); xmax = fmaxf(xmax, xn); }
         }
+        const float rowc = LAZY ? (__saturatef(xo[0]) + __saturatef(xo[1])) : (xo[0] + xo[1]);
         const int off = a * TILE + b0;
         if (flags & 4) {
           __stcs(reinterpret_cast<float2*>(xt + off), make_float2(xo[0], xo[1]));
@@ -919,7 +929,7 @@ k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
           *reinterpret_cast<float2*>(mt + off) = make_float2(mo[0], mo[1]);
           *reinterpret_cast<float2*>(vt + off) = make_float2(vo[0], vo[1]);
         }
-        const float rp = warp_sum(xo[0] + xo[1]);
+        const float rp = warp_sum(rowc);
         if (lane == 0 && rp != 0.f) atomicAdd(&sm.rowacc[a], rp);
       }
       if (colp[0] != 0.f) atomicAdd(&sm.colacc[b0], colp[0]);
@@ -946,6 +956,14 @@ k_fold_rs(float* __restrict__ tiles, float* __restrict__ mbuf, float* __restrict
     if (ct == 0) {
       if (sm.dsum[0] != 0.0) atomicAdd(fa.acc_next + MCGRA_ACC_SUMCLAMP, sm.dsum[0]);
       if (sm.dsum[1] != 0.0) atomicAdd(fa.acc_next + MCGRA_ACC_SUMSQ, sm.dsum[1]);
+    }
+    if (LAZY) {
+      xmin = warp_min(xmin);
+      xmax = warp_max(xmax);
+      if (lane == 0) {
+        if (xmin != INFINITY) atomic_min_f(minmax, xmin);
+        if (xmax != -INFINITY) atomic_max_f(minmax + 1, xmax);
+      }
     }
   }
   tc::fence_before();
@@ -1107,7 +1125,8 @@ int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const fl
                     const mcgra_fold_args* a, float* minmax, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0) return 0;
-  const bool fastable = raw == 2 && a->store_clamped && a->k2 == 0.f && a->measure != MCGRA_M_KL && !a->plain_gd &&
+  const bool lazy = raw == 0 && !a->store_clamped;        // un-projected buffer + mu (the budget may bind)
+  const bool fastable = ((raw == 2 && a->store_clamped) || lazy) && a->k2 == 0.f && a->measure != MCGRA_M_KL && !a->plain_gd &&
                         a->Gtiles == nullptr && !(a->measure != MCGRA_M_NONE && a->Ftiles == nullptr);
   if (g_fold_engine == 3 && a->Wk != nullptr && fastable) {
     const int64_t np = a->npad;
@@ -1123,10 +1142,12 @@ int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const fl
     const size_t smem4 = sizeof(FoldRsSmem) + 1024;
     const unsigned char* wk = (const unsigned char*)a->Wk;
     cudaError_t e4 = cudaSuccess;
-#define MCGRA_FOLD_RS(MEAS, ENT)                                                                                      \
-  e4 = cudaFuncSetAttribute(k_fold_rs<MEAS, ENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);           \
+#define MCGRA_FOLD_RS_(MEAS, ENT, LZ)                                                                                 \
+  e4 = cudaFuncSetAttribute(k_fold_rs<MEAS, ENT, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);       \
   if (e4 != cudaSuccess) return (int)e4;                                                                              \
-  k_fold_rs<MEAS, ENT><<<grid, RS_THREADS, smem4, (cudaStream_t)stream>>>(tiles, m, v, tr0, nt, *a, wk, g_fold_flags)
+  k_fold_rs<MEAS, ENT, LZ><<<grid, RS_THREADS, smem4, (cudaStream_t)stream>>>(tiles, m, v, tr0, nt, *a, wk, g_fold_flags, mu, minmax)
+#define MCGRA_FOLD_RS(MEAS, ENT)                                                                                      \
+  if (lazy) { MCGRA_FOLD_RS_(MEAS, ENT, true); } else { MCGRA_FOLD_RS_(MEAS, ENT, false); }
     if (a->measure == MCGRA_M_MSE) {
       if (a->k6 != 0.f) { MCGRA_FOLD_RS(MCGRA_M_MSE, true); } else { MCGRA_FOLD_RS(MCGRA_M_MSE, false); }
     } else if (a->measure == MCGRA_M_PRE) {
@@ -1135,6 +1156,7 @@ int mcgra_fold_adam(float* tiles, float* m, float* v, int tr0, int tr1, const fl
       if (a->k6 != 0.f) { MCGRA_FOLD_RS(MCGRA_M_NONE, true); } else { MCGRA_FOLD_RS(MCGRA_M_NONE, false); }
     }
 #undef MCGRA_FOLD_RS
+#undef MCGRA_FOLD_RS_
     MCGRA_LAUNCH_CHECK();
     return 0;
   }

@@ -754,8 +754,11 @@ struct ElemRsSmem {
   uint64_t full[ES_S], empty[ES_S];
 };
 
+// LAZY: the buffer holds the un-projected Adam output (raw == 0): entry = clamp(x' - mu, 0, 1) on read
+template <bool LAZY>
 __global__ void __launch_bounds__(ES_THREADS, 1)
-k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, const __grid_constant__ mcgra_elem_args ea) {
+k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, const __grid_constant__ mcgra_elem_args ea,
+          const float* mu_ptr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ElemRsSmem& sm = *reinterpret_cast<ElemRsSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -803,6 +806,7 @@ k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, c
   }
   const float k1x4 = 4.f * ea.k1, k6x2 = 2.f * ea.k6;
   const bool ent = ea.k6 != 0.f;
+  const float mu = LAZY ? *mu_ptr : 0.f;
   double d1 = 0.0, d6 = 0.0;
   uint32_t s = 0, ph = 0;
   int Iprev = 0, Jprev = 0;
@@ -853,7 +857,9 @@ k_elem_rs(const float* __restrict__ tiles, int64_t n, int tr0, int64_t ntiles, c
       for (int h = 0; h < 2; ++h) {
         const int a = ch * ES_R + h * 16 + cw;
         const float ri = sm.rI[p][a];
-        const float xs[4] = {X[h].x, X[h].y, X[h].z, X[h].w}, fs[4] = {F[h].x, F[h].y, F[h].z, F[h].w};
+        const float fs[4] = {F[h].x, F[h].y, F[h].z, F[h].w};
+        const float xs[4] = {LAZY ? __saturatef(X[h].x - mu) : X[h].x, LAZY ? __saturatef(X[h].y - mu) : X[h].y,
+                             LAZY ? __saturatef(X[h].z - mu) : X[h].z, LAZY ? __saturatef(X[h].w - mu) : X[h].w};
         float row_e = 0.f;
         if (interior) {                            // every entry valid: ~16 instructions per entry
 #pragma unroll
@@ -974,7 +980,7 @@ int mcgra_elem_stats(const float* tiles, int64_t n, int tr0, int tr1, const floa
                      const mcgra_elem_args* elem, void* stream) {
   const int64_t nt = tri(tr1) - tri(tr0);
   if (nt <= 0 || elem == nullptr) return 0;
-  if (g_elem_engine == 1 && raw == 2 && elem->measure == MCGRA_M_MSE && elem->Ftiles != nullptr) {
+  if (g_elem_engine == 1 && (raw == 2 || raw == 0) && elem->measure == MCGRA_M_MSE && elem->Ftiles != nullptr) {
     static int sms = 0;
     if (sms == 0) {
       int dev = 0;
@@ -982,10 +988,18 @@ int mcgra_elem_stats(const float* tiles, int64_t n, int tr0, int tr1, const floa
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const size_t smem = sizeof(ElemRsSmem) + 128;
-    cudaError_t e = cudaFuncSetAttribute(k_elem_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
     const int cap = g_elem_grid > 0 ? g_elem_grid : sms;
-    k_elem_rs<<<(unsigned)(nt < cap ? nt : cap), ES_THREADS, smem, (cudaStream_t)stream>>>(tiles, n, tr0, nt, *elem);
+    const unsigned grid = (unsigned)(nt < cap ? nt : cap);
+    cudaError_t e;
+    if (raw == 0) {
+      e = cudaFuncSetAttribute(k_elem_rs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      k_elem_rs<true><<<grid, ES_THREADS, smem, (cudaStream_t)stream>>>(tiles, n, tr0, nt, *elem, mu);
+    } else {
+      e = cudaFuncSetAttribute(k_elem_rs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      k_elem_rs<false><<<grid, ES_THREADS, smem, (cudaStream_t)stream>>>(tiles, n, tr0, nt, *elem, mu);
+    }
     MCGRA_LAUNCH_CHECK();
     return 0;
   }
