@@ -19,7 +19,10 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
            "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
-           "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct"]
+           "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+           # (r2) tensor-core operand traffic from shared memory and the HMMA sub-pipe's busy cycles
+           "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",
+           "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def short(name):

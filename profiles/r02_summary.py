@@ -57,7 +57,7 @@ if __name__ == "__main__":
     launches("r02_pubmed_B_launches.csv", "r02_pubmed_B_launches.txt", "bench.py --workload pubmed --profile B --steps 2 --warmup 1 ... (n = 19717, HSIC)")
     # r02_fold_rs / r02_elem_rs: the final streaming kernels (tools/profile_r2b.sh); r02b_fold_tc: the one-tile-per-CTA
     # engine they replaced, steady-state launch; pairs / gemm captures from tools/profile_r2.sh
-    t = full(["r02_fold_rs.ncu-rep", "r02_elem_rs.ncu-rep", "r02b_fold_tc.ncu-rep", "r02_pairs_tc.ncu-rep", "r02_gemm3.ncu-rep"],
+    t = full(["r02_fold_rs.ncu-rep", "r02_elem_rs.ncu-rep", "r02_prop_h.ncu-rep", "r02b_fold_tc.ncu-rep", "r02_pairs_tc.ncu-rep", "r02_gemm3.ncu-rep"],
              "r02_ncu_full.csv")
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     allt = json.load(open(tp)) if os.path.exists(tp) else {}
