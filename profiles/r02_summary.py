@@ -46,9 +46,9 @@ def full(reps, out):
                 w.writerow(["Kernel Name"] + METRICS)
                 w.writerow([""] + [units[c] if c is not None else "" for c in cols[1:]])
             for r in rows[2:]:
-                w.writerow([r[c] if c is not None else "" for c in cols])
-                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[cols[2]]]
-                traffic[short(r[cols[0]])] = (float(r[cols[2]]) + float(r[cols[3]])) * scale
+                w.writerow([r[cols[0]]] + [(r[c] + " " + units[c]) if c is not None else "" for c in cols[1:]])
+                sc = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                traffic[short(r[cols[0]])] = float(r[cols[2]]) * sc[units[cols[2]]] + float(r[cols[3]]) * sc[units[cols[3]]]
     return traffic
 
 
@@ -64,8 +64,7 @@ if __name__ == "__main__":
     pick = lambda pre: next((v for k, v in t.items() if k.startswith(pre)), 0)
     allt["large_A"] = {"mcgra_fold_adam": round(pick("k_fold_rs")), "elem_stats": round(pick("k_elem_rs")),
                        "mcgra_pairs": round(pick("k_pairs_tc")),
-                       "_note": "k_elem_rs: dram__bytes_read 17.2 GB (= algorithmic) + 16-17 GB that ncu books as dram writes although the "
-                                "kernel writes O(n) bytes and the sum would exceed the DRAM peak; fold: read 40.3 + write 25.8 GB"}
+                       "_note": "k_elem_rs: read 17.2 GB (= algorithmic), writes 17 MB; k_fold_rs: read 40.3 + write 25.8 GB"}
     allt["pubmed_B"] = {k: round(t.get("k_gemm3<2>", 0)) for k in ("gemm_grad", "gemm_c1", "gemm_c2_T")}
     allt["_source_r02"] = "profiles/r02_ncu_full.csv (ncu --set full --clock-control none; dram bytes read + written per launch)"
     json.dump(allt, open(tp, "w"), indent=1, sort_keys=True)
