@@ -127,17 +127,23 @@ def test_engines_agree(which, eng):
     assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 2e-5
 
 
+FOLD_WSETS = {"mse_ent": {1: 0.01, 6: 10.0, 7: 10.0, 9: 10.0, 10: 1000.0},       # k_fold_rs<MSE, entropy>
+              "none_ent": {6: 10.0, 7: 10.0, 9: 10.0, 10: 1000.0},               # no c1 term
+              "mse_noent": {1: 0.01, 7: 10.0, 9: 10.0, 10: 1000.0}}              # no entropy term
+
+
 @pytest.mark.parametrize("eng", [3])
-@pytest.mark.parametrize("density,grid", [(1e7, 5), (1e7, 0), (1.0, 7)])
-def test_fold_persistent_engine_multi_tile(eng, density, grid):
+@pytest.mark.parametrize("density,grid,wset", [(1e7, 5, "mse_ent"), (1e7, 0, "mse_ent"), (1.0, 7, "mse_ent"),
+                                               (1e7, 5, "none_ent"), (1.0, 5, "none_ent"), (1e7, 7, "mse_noent")])
+def test_fold_persistent_engine_multi_tile(eng, density, grid, wset):
     """fold engine 3 (persistent, warp-specialised, row runs with the A operand resident in tensor memory, bulk-copy
     rings for B and for x / m / v / F) against engine 2 (one tile per CTA) with several tiles and several tile rows per
     CTA: n = 1500 (78 tiles, 12 tile rows, last row ragged) on a grid capped to 5 / 7 CTAs and uncapped; density 1e7 =
-    fast path from the second iteration (clamped store), density 1 = budget binds (engine 3 defers to engine 2)."""
+    clamped-parameter view from the second iteration (clamped store), density 1 = budget binds (lazily projected view,
+    un-clamped store, min / max for the bisection); the weight sets select the kernel's template variants."""
     from helpers import synthetic_case
     from mcgra_b200 import _native as N
-    d = synthetic_case(1500, 40, 5, weights={1: 0.01, 6: 10.0, 7: 10.0, 9: 10.0, 10: 1000.0}, epochs=4, density=density,
-                       mean_deg=8.0)
+    d = synthetic_case(1500, 40, 5, weights=FOLD_WSETS[wset], epochs=4, density=density, mean_deg=8.0)
     try:
         N.lib().mcgra_set_engine(1, 2)
         a = run_native_case(d)
