@@ -1016,16 +1016,37 @@ k_bisect_pass(const float* __restrict__ tiles, int64_t n, int64_t t0, float epsi
   const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
   const float4* src = reinterpret_cast<const float4*>(tiles + (int64_t)blockIdx.x * TILE_ELEMS);
   float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int e = threadIdx.x; e < TILE_ELEMS / 4; e += 256) {
-    const int row = e >> 5, c4 = e & 31;
-    const int64_t gi = i0 + row, gj = j0 + c4 * 4;
-    const float4 x4 = src[e];
-    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+  const bool interior = (J < I) && (i0 + TILE <= n);
+  // 16 float4 per thread, loaded in two batches of 8 before any arithmetic (the pass is otherwise latency / issue bound)
+#pragma unroll 1
+  for (int hb = 0; hb < 2; ++hb) {
+    float4 xq[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if ((gj + k < gi) && (gi < n)) {
+    for (int u = 0; u < 8; ++u) xq[u] = src[(hb * 8 + u) * 256 + threadIdx.x];
+    if (interior) {
 #pragma unroll
-        for (int q = 0; q < 7; ++q) s[q] += fminf(fmaxf(xv[k] - c[q], 0.f), 1.f);
+      for (int u = 0; u < 8; ++u) {
+        const float xv[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int q = 0; q < 7; ++q) s[q] += __saturatef(xv[k] - c[q]);
+      }
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < 8; ++u) {
+        const int e = (hb * 8 + u) * 256 + threadIdx.x;
+        const int row = e >> 5, c4 = e & 31;
+        const int64_t gi = i0 + row, gj = j0 + c4 * 4;
+        const float4 x4 = src[e];
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if ((gj + k < gi) && (gi < n)) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) s[q] += __saturatef(xv[k] - c[q]);
+          }
+        }
       }
     }
   }
@@ -1057,10 +1078,11 @@ __global__ void k_bisect_update(double budget, float epsilon, float* state, doub
 }
 
 // after the bisection: statistics of the projected parameter clamp(x' - mu, 0, 1)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_bisect_finish(const float* __restrict__ tiles, int64_t n, int64_t t0, const float* __restrict__ state,
                 const float* __restrict__ mu, double* __restrict__ acc_next, float* __restrict__ d_next) {
   __shared__ float colacc[TILE];
+  __shared__ float rowpart[TILE][33];                          // per-lane row sums, summed once per tile
   __shared__ double red[32];
   if (state[4] == 0.f) return;                                 // projection inactive: fold's statistics stand
   const float m = *mu;
@@ -1069,36 +1091,48 @@ k_bisect_finish(const float* __restrict__ tiles, int64_t n, int64_t t0, const fl
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
   const float4* src = reinterpret_cast<const float4*>(tiles + (int64_t)blockIdx.x * TILE_ELEMS);
-  colacc[tid] = 0.f;
-  __syncthreads();
+  if (tid < TILE) colacc[tid] = 0.f;
+  const bool interior = (J < I) && (i0 + TILE <= n);
   float col[4] = {0.f, 0.f, 0.f, 0.f};
   float ssq = 0.f;
-  for (int it = 0; it < 32; ++it) {
-    const int row = it * 4 + warp;
-    const float4 x4 = src[row * 32 + lane];
-    const int64_t gi = i0 + row, gj = j0 + lane * 4;
-    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-    float rs = 0.f;
+#pragma unroll 1
+  for (int hb = 0; hb < 2; ++hb) {                             // rows (hb * 8 + u) * 8 + warp, 8 loads in flight per thread
+    float4 xq[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if ((gj + k < gi) && (gi < n)) {
-        const float c = fminf(fmaxf(xv[k] - m, 0.f), 1.f);
-        rs += c;
-        col[k] += c;
-        ssq = fmaf(c, c, ssq);
+    for (int u = 0; u < 8; ++u) xq[u] = src[((hb * 8 + u) * 8 + warp) * 32 + lane];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int row = (hb * 8 + u) * 8 + warp;
+      const int64_t gi = i0 + row, gj = j0 + lane * 4;
+      const float xv[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+      float rs = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (interior || ((gj + k < gi) && (gi < n))) {
+          const float c = __saturatef(xv[k] - m);
+          rs += c;
+          col[k] += c;
+          ssq = fmaf(c, c, ssq);
+        }
       }
+      rowpart[row][lane] = rs;
     }
-    rs = warp_sum(rs);
-    if (lane == 0 && gi < n && rs != 0.f) atomicAdd(d_next + gi, rs);
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) atomicAdd(&colacc[lane * 4 + k], col[k]);
   __syncthreads();
-  if (j0 + tid < n && colacc[tid] != 0.f) atomicAdd(d_next + j0 + tid, colacc[tid]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (col[k] != 0.f) atomicAdd(&colacc[lane * 4 + k], col[k]);
+  if (tid < TILE) {
+    float rs = 0.f;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) rs += rowpart[tid][l];
+    if (i0 + tid < n && rs != 0.f) atomicAdd(d_next + i0 + tid, rs);
+  }
+  __syncthreads();
+  if (tid < TILE && j0 + tid < n && colacc[tid] != 0.f) atomicAdd(d_next + j0 + tid, colacc[tid]);
   block_atomic_add_d((double)ssq, acc_next + MCGRA_ACC_SUMSQ, red);
 }
 
-// when the projection turned out active the fold's d_next / SUMSQ (taken at mu = 0) must be discarded first
 __global__ void k_bisect_reset(int64_t n, const float* state, double* acc_next, float* d_next) {
   if (state[4] == 0.f) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1208,7 +1242,7 @@ int mcgra_bisect_finish(const float* tiles, int64_t n, int tr0, int tr1, const f
     MCGRA_LAUNCH_CHECK();
   }
   if (nt <= 0) return 0;
-  k_bisect_finish<<<(unsigned)nt, 128, 0, (cudaStream_t)stream>>>(tiles, n, tri(tr0), state, mu, acc_next, d_next);
+  k_bisect_finish<<<(unsigned)nt, 256, 0, (cudaStream_t)stream>>>(tiles, n, tri(tr0), state, mu, acc_next, d_next);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }
