@@ -62,12 +62,18 @@ enum {
 };
 
 int mcgra_version(void);
-/* engine selection for A/B validation: which 0 = propagate (0 fp32 FFMA, 1 mma.sync 3xTF32, 2 tcgen05+mma.sync
- * hybrid, 3: hybrid for the plain 32-wide passes only, 4: both products on tcgen05 kind::tf32 with the transposed
- * operand in tensor memory, 5: both products on tcgen05 kind::f16 from one fp16x2 image per tile [default]; values
- * >= 100 set developer timing bits and are not for production use); which 1 = fold (0 FFMA, 1 mma.sync, 2 tcgen05 [default]);
- * which 2 = pairs (0 FFMA, 1 mma.sync, 2 tcgen05 for the entropy-only configuration + mma.sync otherwise [default]); which 3 = dense contraction mcgra_gemm_nt (1 = cta_group::1, 128 x 128
- * tiles; 2 = cta_group::2 CTA pairs, 256 x 256 tiles [default]).  Returns 0, or -1 for an unknown selector.          */
+/* engine selection for A/B validation (values >= 100 are developer knobs -- grid caps for the tests, ablation / policy
+ * bits -- and not for production use):
+ *   which 0 = propagate:    0 exact fp32 FFMA (reference of the agreement tests), 5 both products on tcgen05 kind::f16 from
+ *                           one fp16x2 image per tile [default]
+ *   which 1 = fold:         0 exact fp32 FFMA, 2 tcgen05 one tile per CTA (every parameter view / measure), 3 persistent
+ *                           row runs with the A operand resident in tensor memory for the clamped and the lazily projected
+ *                           view, engine 2 otherwise [default]
+ *   which 2 = pairs:        0 FFMA, 1 mma.sync 3xTF32, 2 tcgen05 for the entropy-only configuration + 1 otherwise [default]
+ *   which 3 = mcgra_gemm_nt: 1 cta_group::1 (128 x 128 tiles), 2 cta_group::2 CTA pairs (256 x 256 tiles) [default]
+ *   which 4 = element-wise pass: 0 one tile per CTA, 1 persistent bulk-staged kernel for MSE on the clamped / lazily
+ *                           projected view, 0 otherwise [default]
+ * Returns 0, or -1 for an unknown selector.                                                                            */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */
 
