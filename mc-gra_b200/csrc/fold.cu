@@ -309,10 +309,8 @@ __device__ __forceinline__ void fold_row(SM& sm, const mcgra_fold_args& fa, cons
   if (lane == 0 && gi < n && rowp != 0.f) atomicAdd(fa.d_next + gi, rowp);
 }
 
-// Fast-path row for the persistent engine (interior tile, buffer holds the clamped parameter, clamped store): same
-// arithmetic as fold_row<true, ...> with the per-row constants hoisted, sqrt / clamp as single instructions, no min / max
-// tracking (only the budget projection reads them, and it cannot bind on this path) and the row sum left per lane in
-// shared memory (rowpart[a][lane]; summed once per tile instead of a shuffle chain + atomic per row).
+// Constants of the persistent engine's inlined row arithmetic (same formulas as fold_row<true, ...> with the per-launch
+// factors hoisted, sqrt / clamp as single instructions).
 struct FastConst {
   float k1x4, k6x2, norm_scale, omb1, omb2, inv_sqrt_bc2, adam_eps, neg_step;
 };
@@ -321,8 +319,6 @@ __device__ __forceinline__ float sqrt_approx(float v) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
-__device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void st4_stream(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 
 // Streaming epilogue of a one-tile-per-CTA engine: 8 warps, UNR rows in flight per warp.
 template <bool FAST, int MEAS, bool ENT, typename SM>
