@@ -311,8 +311,12 @@ k_row_sumexp(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
 //
 // Plane image: element (i, j) at (j/8)*H_SJ + (i/8)*128 + (i%8)*16 + (j%8)*2, two planes per tile, two tile buffers.
 // Warps 0-7 convert their prefetched registers into the planes, arrive on ready[b], prefetch the tile after next and
-// flush the mirrored result of the previous tile; warp 8 streams the pre-formatted B[J] blocks and issues the 32 MMAs
-// of a tile.  TMEM columns: D1 [0, 3KC) | D2[0] [96, 96+3KC) | D2[1] [192, 192+3KC).
+// flush the mirrored result of the previous tile; warp 8 (one lane) issues the 32 MMAs of a tile and nothing else -- a
+// clock64 trace showed its serial instruction stream to be the bound of the kernel (2.6 k clk of MMA issue + 1.9 k clk of
+// cp.async B-block loading per tile for an HBM time of 2.7 k clk) -- and warp 9 (one lane) streams the pre-formatted B[J]
+// blocks with one cp.async.bulk each into a ring of three.  With the issuer freed, the converters' own chain (convert +
+// flush of the previous tile, 3-3.4 k clk) became the bound, so the flush moved to warps 8-11; registers are re-partitioned
+// with setmaxnreg (converters keep two prefetched tiles in registers, everything else needs few).  TMEM columns: D1 [0, 3KC) | D2[0] [96, 96+3KC) | D2[1] [192, 192+3KC).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int H_RUN = 32;
 int g_prop_dbg = 0;                                // timing experiments only: mcgra_set_engine(0, 100 + bits)
@@ -324,7 +328,8 @@ struct PropHSmem {
   unsigned char tile[2][2][H_PLANE];               // [buffer][plane h0 / h1]
   unsigned char bkJ[3][16 * (2 * KC) * 16];        // 16 K-groups x (2KC rows [g0 | g1] x 16 B); ring of 3
   unsigned char bkI[16 * (2 * KC) * 16];
-  uint64_t ready[2], tile_done[2];
+  uint64_t ready[2], tile_done[2], flushed[2];
+  uint64_t bfull[3], bfree[3], bIfull;           // B-block ring (bulk copies by the loader warp)
   float inv_s[32];
   uint32_t tmem_base;
 };
@@ -426,8 +431,9 @@ __device__ __forceinline__ void h_flush(float* __restrict__ Y, int64_t n, int64_
   }
 }
 
+constexpr int H_THREADS = 512;      // 4 warpgroups: converters (2), flushers, MMA issuer + B loader (+ 2 idle warps)
 template <int KC>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(H_THREADS, 1)
 k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
               const unsigned char* __restrict__ Bk, const float* __restrict__ scale, float* __restrict__ Y, int dbg) {
   const int I = tr0 + (int)blockIdx.y;
@@ -447,7 +453,7 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
   constexpr uint32_t LBO_B = (2 * KC) * 16;
   constexpr uint32_t BLK = 16 * LBO_B;
   constexpr uint32_t COL_D1 = 0, COL_D2 = 96;
-  const bool tcwarp = warp == 8;
+  const bool tcwarp = warp == 12;
   const bool rows_ok = (i0 + TILE <= n) && (pv.raw == 2);
   const int64_t tix0 = tri((int64_t)I) - tri((int64_t)tr0);
 
@@ -455,6 +461,9 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
   if (tid == 0) {
     tc::mbar_init(&sm.ready[0], 256); tc::mbar_init(&sm.ready[1], 256);
     tc::mbar_init(&sm.tile_done[0], 1); tc::mbar_init(&sm.tile_done[1], 1);
+    tc::mbar_init(&sm.flushed[0], 128); tc::mbar_init(&sm.flushed[1], 128);
+    for (int r = 0; r < 3; ++r) { tc::mbar_init(&sm.bfull[r], 1); tc::mbar_init(&sm.bfree[r], 1); }
+    tc::mbar_init(&sm.bIfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid >= 32 && tid < 32 + KC) sm.inv_s[tid - 32] = scale[KC + tid - 32];
@@ -463,37 +472,34 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
   tc::fence_after();
   const uint32_t tm = sm.tmem_base;
 
-  if (tcwarp) {
-    // =================================== B-block producer + MMA issuer ===================================
-    auto load_block = [&](int node_tile, unsigned char* dst) {
-      const float4* src = reinterpret_cast<const float4*>(Bk + (int64_t)node_tile * BLK);
-#pragma unroll 4
-      for (int e = lane; e < (int)(BLK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(dst) + e, src + e);
-    };
-    load_block(I, sm.bkI);
-    load_block(tile_of(0), sm.bkJ[0]);
-    tc::cp_async_commit();
-    const uint32_t id_cat = make_idesc_f16(128, 2 * KC, 0), id_one = make_idesc_f16(128, KC, 0);
-    const uint32_t id_cat_t = make_idesc_f16(128, 2 * KC, 1), id_one_t = make_idesc_f16(128, KC, 1);
-    const uint64_t bI0 = tc::make_desc(tc::smem_u32(sm.bkI), LBO_B, 128u);
-    for (int k = 0; k < nt; ++k) {
-      const int b = k & 1;
-      if (k + 1 < nt) {                        // B[J+1] into ring slot (k+1)%3, last read by tile k-2 (long complete:
-        // the converters could not have filled tile buffer b for tile k otherwise -- checked below through ready[b])
-        if (k >= 2) tc::mbar_wait(&sm.tile_done[b], (uint32_t)(((k - 2) >> 1) & 1));
-        load_block(tile_of(k + 1), sm.bkJ[(k + 1) % 3]);
-        tc::cp_async_commit();
-        tc::cp_async_wait_group<1>();          // B[J] (committed one tile ago) has landed
-      } else {
-        tc::cp_async_wait_all();
+  if (warp >= 12) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
+  if (warp == 13) {
+    // =================================== B-block loader ===================================
+    if (lane == 0) {
+      tc::mbar_expect_tx(&sm.bIfull, BLK);
+      tc::bulk_g2s(sm.bkI, Bk + (int64_t)I * BLK, BLK, &sm.bIfull);
+      for (int k = 0; k < nt; ++k) {
+        const int r = k % 3;
+        if (k >= 3) tc::mbar_wait_backoff(&sm.bfree[r], (uint32_t)((k / 3 - 1) & 1));     // MMAs of tile k-3 have read slot r
+        tc::mbar_expect_tx(&sm.bfull[r], BLK);
+        tc::bulk_g2s(sm.bkJ[r], Bk + (int64_t)tile_of(k) * BLK, BLK, &sm.bfull[r]);
       }
-      tc::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
+    }
+  } else if (tcwarp) {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
+      const uint32_t id_cat = make_idesc_f16(128, 2 * KC, 0), id_one = make_idesc_f16(128, KC, 0);
+      const uint32_t id_cat_t = make_idesc_f16(128, 2 * KC, 1), id_one_t = make_idesc_f16(128, KC, 1);
+      const uint64_t bI0 = tc::make_desc(tc::smem_u32(sm.bkI), LBO_B, 128u);
+      tc::mbar_wait(&sm.bIfull, 0u);
+      for (int k = 0; k < nt; ++k) {
+        const int b = k & 1, r = k % 3;
+        tc::mbar_wait(&sm.bfull[r], (uint32_t)((k / 3) & 1));
         tc::mbar_wait(&sm.ready[b], (uint32_t)((k >> 1) & 1));
+        if (k >= 2 && !(dbg & 1)) tc::mbar_wait(&sm.flushed[b], (uint32_t)(((k - 2) >> 1) & 1));   // D2[b] of tile k-2 has been read
         tc::fence_after();
         const uint32_t p0 = tc::smem_u32(sm.tile[b][0]), p1 = tc::smem_u32(sm.tile[b][1]);
-        const uint64_t bJ0 = tc::make_desc(tc::smem_u32(sm.bkJ[k % 3]), LBO_B, 128u);
+        const uint64_t bJ0 = tc::make_desc(tc::smem_u32(sm.bkJ[r]), LBO_B, 128u);
         const uint32_t d2 = tm + COL_D2 + (uint32_t)b * 96u;
 #pragma unroll 2
         for (int ks = 0; ks < ((dbg & 2) ? 0 : TILE / 16); ++ks) {
@@ -507,17 +513,35 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
           mma_f16(d2 + 2 * KC, tc::make_desc(p1 + (uint32_t)ks * 256u, 128u, H_SJ), bI0 + db, id_one_t, acc2);
         }
         tc::mma_commit(&sm.tile_done[b]);
+        tc::mma_commit(&sm.bfree[r]);
       }
-      __syncwarp();
     }
-  } else {
-    // =================================== converter warps ===================================
-    const int q = warp & 3, cg = warp >> 2;           // TMEM lane quarter; 16-column group this warp flushes
+  } else if (warp >= 8 && warp < 12) {
+    // =================================== flusher warps ===================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
+    const int q = warp & 3;                              // TMEM lane quarter (= warp % 4)
     const int ltid = q * 32 + lane;
     const uint32_t tlane = tm + ((uint32_t)(q * 32) << 16);
-    const bool flusher = cg < KC / 16 && !(dbg & 1);
-    const float* inv_s = sm.inv_s + (flusher ? cg * 16 : 0);
-
+    const bool on = !(dbg & 1);
+    for (int k = 0; k < nt; ++k) {
+      const int b = k & 1;
+      tc::mbar_wait(&sm.tile_done[b], (uint32_t)((k >> 1) & 1));
+      tc::fence_after();
+      if (on) {
+#pragma unroll
+        for (int cg = 0; cg < KC / 16; ++cg)
+          h_flush<KC>(Y, n, (int64_t)tile_of(k) * TILE + ltid, tlane + COL_D2 + (uint32_t)b * 96u, cg * 16, sm.inv_s + cg * 16);
+      }
+      tc::fence_before();
+      mbar_arrive(&sm.flushed[b]);
+    }
+    if (on) {                                            // the run's direct result (complete with the last tile_done)
+#pragma unroll
+      for (int cg = 0; cg < KC / 16; ++cg) h_flush<KC>(Y, n, i0 + ltid, tlane + COL_D1, cg * 16, sm.inv_s + cg * 16);
+    }
+  } else if (warp < 8) {
+    // =================================== converter warps ===================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(200));
     auto fetch = [&](int J, float4 (&dst)[16]) {
       const float4* src = reinterpret_cast<const float4*>(tiles + (tix0 + J) * TILE_ELEMS);
 #pragma unroll
@@ -558,12 +582,6 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
       tc::fence_async_smem();
       mbar_arrive(&sm.ready[b]);
       if (k + 2 < nt) fetch(tile_of(k + 2), cur);   // two tiles ahead, into the registers just consumed
-      if (k >= 1) {                            // flush the mirrored result of the previous tile
-        tc::mbar_wait(&sm.tile_done[b ^ 1], (uint32_t)(((k - 1) >> 1) & 1));
-        tc::fence_after();
-        if (flusher) h_flush<KC>(Y, n, (int64_t)tile_of(k - 1) * TILE + ltid, tlane + COL_D2 + (uint32_t)(b ^ 1) * 96u, cg * 16, inv_s);
-        tc::fence_before();
-      }
     };
     float4 ra[16], rb[16];
     fetch(tile_of(0), ra);
@@ -571,14 +589,6 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
     for (int k = 0; k < nt; k += 2) {
       step(k, ra, rb);
       if (k + 1 < nt) step(k + 1, rb, ra);
-    }
-    // ---- epilogue: the last tile's D2 and the run's D1 ----
-    const int bl = (nt - 1) & 1;
-    tc::mbar_wait(&sm.tile_done[bl], (uint32_t)(((nt - 1) >> 1) & 1));
-    tc::fence_after();
-    if (flusher) {
-      h_flush<KC>(Y, n, (int64_t)tile_of(nt - 1) * TILE + ltid, tlane + COL_D2 + (uint32_t)bl * 96u, cg * 16, inv_s);
-      h_flush<KC>(Y, n, i0 + ltid, tlane + COL_D1, cg * 16, inv_s);
     }
   }
   tc::fence_before();
@@ -607,7 +617,7 @@ int launch_prop_h(const float* tiles, int64_t n, int tr0, int tr1, const float* 
   if (e != cudaSuccess) return (int)e;
   if (tr1 - tr0 > 65535) return -3;
   dim3 grid((unsigned)((tr1 + H_RUN - 1) / H_RUN), (unsigned)(tr1 - tr0));
-  k_propagate_h<KC><<<grid, 288, smem, st>>>(tiles, n, tr0, mu, raw, Bk, scale, Y, g_prop_dbg);
+  k_propagate_h<KC><<<grid, H_THREADS, smem, st>>>(tiles, n, tr0, mu, raw, Bk, scale, Y, g_prop_dbg);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }
