@@ -12,8 +12,10 @@
 //   C planes     cs = s_c C:   h0 = fp16(cs), h1 = fp16((cs - h0) 2^11)                 (s_c: power of two, |cs| < 2^14)
 //   zhat blocks  g = s_f z:    g0, g1 likewise per feature column f;   D[:, 0:32] += h0 [g0 | g1],  D[:, 32:48] += h1 g0,
 //                dz = (d0 + (d1 + d2) 2^-11) / (s_f s_c)
-// Pipeline (288 threads, 1 CTA / SM, runs of up to 32 tiles of one tile row): warp 8 streams the pre-formatted operand
-// blocks (ring of 4, cp.async two tiles ahead), issues the S product of tile k+1 and then the 32 skinny MMAs of tile k;
+// Pipeline (320 threads, 1 CTA / SM, runs of up to 32 tiles of one tile row): warp 9 (one lane) streams the pre-formatted
+// operand blocks (ring of 4, two cp.async.bulk per tile); warp 8 (one lane) only issues MMAs -- its serial instruction
+// stream is what bounds this family of kernels (propagate.cu) -- the S product of tile k+1 and then the 32 skinny MMAs of
+// tile k;
 // warps 0-7 read S[k] from TMEM (lane = row), write the two fp16 planes of C (the same image is the K-major A operand of
 // the direct product and the MN-major A operand of the mirrored one) and flush the mirrored result of tile k-1.
 // TMEM columns: D1 [0,48) | D2[0] [48,96) | D2[1] [96,144) | S[0] [256,384) | S[1] [384,512).
@@ -43,6 +45,7 @@ struct PairTcSmem {
   unsigned char zbI[ZB_BLK];
   unsigned char zaI[ZA_BLK];
   uint64_t ready[2], tile_done[2], s_ready[2], s_free[2];
+  uint64_t bfull[RING], bfree[RING], bIfull;         // operand-block ring (loader warp)
   float inv_s[16];
   double red[32];
   uint32_t tmem_base;
@@ -143,7 +146,7 @@ __device__ __forceinline__ void ptc_flush(float* __restrict__ dz, int64_t n, int
   }
 }
 
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(320, 1)
 k_pairs_tc(int64_t n, int tr0, const unsigned char* __restrict__ Zb, const unsigned char* __restrict__ Za,
            const float* __restrict__ scale, float k7, float sc, float* __restrict__ dzhat, double* __restrict__ acc) {
   const int I = tr0 + (int)blockIdx.y;
@@ -166,6 +169,8 @@ k_pairs_tc(int64_t n, int tr0, const unsigned char* __restrict__ Zb, const unsig
       tc::mbar_init(&sm.s_ready[b], 1);
       tc::mbar_init(&sm.s_free[b], 256);
     }
+    for (int r = 0; r < RING; ++r) { tc::mbar_init(&sm.bfull[r], 1); tc::mbar_init(&sm.bfree[r], 1); }
+    tc::mbar_init(&sm.bIfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid >= 32 && tid < 32 + HID) sm.inv_s[tid - 32] = scale[HID + tid - 32];
@@ -174,58 +179,48 @@ k_pairs_tc(int64_t n, int tr0, const unsigned char* __restrict__ Zb, const unsig
   tc::fence_after();
   const uint32_t tm = sm.tmem_base;
 
-  if (warp == 8) {
-    // =================================== operand producer + MMA issuer ===================================
-    auto load_blocks = [&](int node_tile, unsigned char* zb, unsigned char* za) {
-      const float4* s1 = reinterpret_cast<const float4*>(Zb + (int64_t)node_tile * ZB_BLK);
-      const float4* s2 = reinterpret_cast<const float4*>(Za + (int64_t)node_tile * ZA_BLK);
-#pragma unroll 4
-      for (int e = lane; e < (int)(ZB_BLK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(zb) + e, s1 + e);
-#pragma unroll 4
-      for (int e = lane; e < (int)(ZA_BLK / 16); e += 32) tc::cp_async16(reinterpret_cast<float4*>(za) + e, s2 + e);
-    };
-    const uint32_t id_s = idesc_f16(128, 128, 0);
-    const uint32_t id_cat = idesc_f16(128, 2 * HID, 0), id_one = idesc_f16(128, HID, 0);
-    const uint32_t id_cat_t = idesc_f16(128, 2 * HID, 1), id_one_t = idesc_f16(128, HID, 1);
-    const uint32_t zaI = tc::smem_u32(sm.zaI);
-    const uint64_t aIh = tc::make_desc(zaI, ZA_LBO, 128u), aIl = tc::make_desc(zaI + ZA_PLANE, ZA_LBO, 128u);
-    const uint64_t bI0 = tc::make_desc(tc::smem_u32(sm.zbI), ZB_LBO, 128u);
-    auto issue_s = [&](int k) {                     // S[k & 1] = zhat_I zhat_J(k)^T, three K = 16 MMAs
-      const int b = k & 1;
-      if (k >= 2) tc::mbar_wait(&sm.s_free[b], (uint32_t)(((k - 2) >> 1) & 1));
-      tc::fence_after();
-      const uint32_t zaJ = tc::smem_u32(sm.zaJ[k % RING]);
-      const uint64_t bJh = tc::make_desc(zaJ, ZA_LBO, 128u), bJl = tc::make_desc(zaJ + ZA_PLANE, ZA_LBO, 128u);
-      const uint32_t d = tm + COL_S + (uint32_t)b * 128u;
-      mma_f16(d, aIh, bJh, id_s, 0u);
-      mma_f16(d, aIh, bJl, id_s, 1u);
-      mma_f16(d, aIl, bJh, id_s, 1u);
-      tc::mma_commit(&sm.s_ready[b]);
-    };
-    // prologue: blocks of I, tile 0 (group 0) and tile 1 (group 1)
-    load_blocks(I, sm.zbI, sm.zaI);
-    load_blocks(tile_of(0), sm.zbJ[0], sm.zaJ[0]);
-    tc::cp_async_commit();
-    if (nt > 1) load_blocks(tile_of(1), sm.zbJ[1], sm.zaJ[1]);
-    tc::cp_async_commit();
-    tc::cp_async_wait_group<1>();                   // I and tile 0 have landed
-    tc::fence_async_smem();
-    __syncwarp();
-    if (lane == 0) issue_s(0);
-    __syncwarp();
-    for (int k = 0; k < nt; ++k) {
-      const int b = k & 1;
-      // blocks of tile k+2 into ring slot (k+2) % 4, last read by the skinny MMAs of tile k-2
-      if (k + 2 < nt) {
-        if (k >= 2) tc::mbar_wait(&sm.tile_done[b], (uint32_t)(((k - 2) >> 1) & 1));
-        load_blocks(tile_of(k + 2), sm.zbJ[(k + 2) % RING], sm.zaJ[(k + 2) % RING]);
+  if (warp == 9) {
+    // =================================== operand-block loader ===================================
+    if (lane == 0) {
+      tc::mbar_expect_tx(&sm.bIfull, ZB_BLK + ZA_BLK);
+      tc::bulk_g2s(sm.zbI, Zb + (int64_t)I * ZB_BLK, ZB_BLK, &sm.bIfull);
+      tc::bulk_g2s(sm.zaI, Za + (int64_t)I * ZA_BLK, ZA_BLK, &sm.bIfull);
+      for (int k = 0; k < nt; ++k) {
+        const int r = k % RING;
+        if (k >= RING) tc::mbar_wait_backoff(&sm.bfree[r], (uint32_t)((k / RING - 1) & 1));   // MMAs of tile k - RING are done
+        const int J = tile_of(k);
+        tc::mbar_expect_tx(&sm.bfull[r], ZB_BLK + ZA_BLK);
+        tc::bulk_g2s(sm.zbJ[r], Zb + (int64_t)J * ZB_BLK, ZB_BLK, &sm.bfull[r]);
+        tc::bulk_g2s(sm.zaJ[r], Za + (int64_t)J * ZA_BLK, ZA_BLK, &sm.bfull[r]);
       }
-      tc::cp_async_commit();
-      tc::cp_async_wait_group<1>();                 // the group committed one iteration ago (tile k+1) has landed
-      tc::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (k + 1 < nt) issue_s(k + 1);             // next tile's gram first: the converters never wait for it
+    }
+  } else if (warp == 8) {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
+      const uint32_t id_s = idesc_f16(128, 128, 0);
+      const uint32_t id_cat = idesc_f16(128, 2 * HID, 0), id_one = idesc_f16(128, HID, 0);
+      const uint32_t id_cat_t = idesc_f16(128, 2 * HID, 1), id_one_t = idesc_f16(128, HID, 1);
+      const uint32_t zaI = tc::smem_u32(sm.zaI);
+      const uint64_t aIh = tc::make_desc(zaI, ZA_LBO, 128u), aIl = tc::make_desc(zaI + ZA_PLANE, ZA_LBO, 128u);
+      const uint64_t bI0 = tc::make_desc(tc::smem_u32(sm.zbI), ZB_LBO, 128u);
+      auto issue_s = [&](int k) {                     // S[k & 1] = zhat_I zhat_J(k)^T, three K = 16 MMAs
+        const int b = k & 1;
+        tc::mbar_wait(&sm.bfull[k % RING], (uint32_t)((k / RING) & 1));      // blocks of tile k have landed
+        if (k >= 2) tc::mbar_wait(&sm.s_free[b], (uint32_t)(((k - 2) >> 1) & 1));
+        tc::fence_after();
+        const uint32_t zaJ = tc::smem_u32(sm.zaJ[k % RING]);
+        const uint64_t bJh = tc::make_desc(zaJ, ZA_LBO, 128u), bJl = tc::make_desc(zaJ + ZA_PLANE, ZA_LBO, 128u);
+        const uint32_t d = tm + COL_S + (uint32_t)b * 128u;
+        mma_f16(d, aIh, bJh, id_s, 0u);
+        mma_f16(d, aIh, bJl, id_s, 1u);
+        mma_f16(d, aIl, bJh, id_s, 1u);
+        tc::mma_commit(&sm.s_ready[b]);
+      };
+      tc::mbar_wait(&sm.bIfull, 0u);
+      issue_s(0);
+      for (int k = 0; k < nt; ++k) {
+        const int b = k & 1;
+        if (k + 1 < nt) issue_s(k + 1);               // next tile's gram first: the converters never wait for it
         tc::mbar_wait(&sm.ready[b], (uint32_t)((k >> 1) & 1));
         tc::fence_after();
         const uint32_t p0 = tc::smem_u32(sm.tile[b][0]), p1 = tc::smem_u32(sm.tile[b][1]);
@@ -243,10 +238,10 @@ k_pairs_tc(int64_t n, int tr0, const unsigned char* __restrict__ Zb, const unsig
           mma_f16(d2 + 2 * HID, tc::make_desc(p1 + (uint32_t)ks * 256u, 128u, P_SJ), bI0 + db, id_one_t, acc2);
         }
         tc::mma_commit(&sm.tile_done[b]);
+        tc::mma_commit(&sm.bfree[k % RING]);
       }
-      __syncwarp();
     }
-  } else {
+  } else if (warp < 8) {
     // =================================== converter warps ===================================
     const int q = warp & 3, ch = warp >> 2;         // TMEM lane quarter; column half [64 ch, +64)
     const int row = q * 32 + lane;
@@ -379,7 +374,7 @@ int mcgra_pairs_tc_(int64_t n, int tr0, int tr1, const float* zhat, float k7, fl
   if (e != cudaSuccess) return (int)e;
   if (tr1 - tr0 > 65535) return -3;
   dim3 grid((unsigned)((tr1 + P_RUN - 1) / P_RUN), (unsigned)(tr1 - tr0));
-  k_pairs_tc<<<grid, 288, smem, st>>>(n, tr0, Zb, Za, scale, k7, sc, dzhat, acc);
+  k_pairs_tc<<<grid, 320, smem, st>>>(n, tr0, Zb, Za, scale, k7, sc, dzhat, acc);
   MCGRA_LAUNCH_CHECK();
   return 0;
 }
