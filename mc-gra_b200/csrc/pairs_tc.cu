@@ -27,7 +27,7 @@
 
 namespace {
 
-constexpr int P_RUN = 32;
+constexpr int P_RUN = 64;
 constexpr uint32_t P_SJ = 16 * 128 + 16;            // stride between 8-column groups of a plane (padded)
 constexpr uint32_t P_PLANE = 16 * P_SJ;
 constexpr uint32_t ZB_LBO = 32 * 16;                 // [g0 | g1]: 32 rows x 16 B per 8-node K group

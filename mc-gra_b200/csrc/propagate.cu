@@ -316,9 +316,9 @@ k_row_sumexp(const float* __restrict__ tiles, int64_t n, int64_t t0, const float
 // cp.async B-block loading per tile for an HBM time of 2.7 k clk) -- and warp 9 (one lane) streams the pre-formatted B[J]
 // blocks with one cp.async.bulk each into a ring of three.  With the issuer freed, the converters' own chain (convert +
 // flush of the previous tile, 3-3.4 k clk) became the bound, so the flush moved to warps 8-11; registers are re-partitioned
-// with setmaxnreg (converters keep two prefetched tiles in registers, everything else needs few).  TMEM columns: D1 [0, 3KC) | D2[0] [96, 96+3KC) | D2[1] [192, 192+3KC).
+// with setmaxnreg (converters keep two prefetched tiles in registers, everything else needs few).  TMEM columns: D1 (even tiles) [0, 3KC) | D1 (odd tiles) [96, 96+3KC) | D2[0] [192, 192+3KC) | D2[1] [288, 288+3KC).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int H_RUN = 32;
+constexpr int H_RUN = 64;
 int g_prop_dbg = 0;                                // timing experiments only: mcgra_set_engine(0, 100 + bits)
 constexpr uint32_t H_SJ = 16 * 128 + 16;           // stride between 8-column groups of a plane (padded: conflict-free stores)
 constexpr uint32_t H_PLANE = 16 * H_SJ;
@@ -432,6 +432,34 @@ __device__ __forceinline__ void h_flush(float* __restrict__ Y, int64_t n, int64_
 }
 
 constexpr int H_THREADS = 512;      // 4 warpgroups: converters (2), flushers, MMA issuer + B loader (+ 2 idle warps)
+// the same for the sum of two accumulators (the run's direct result is split over the two MMA-issuing lanes)
+template <int KC>
+__device__ __forceinline__ void h_flush2(float* __restrict__ Y, int64_t n, int64_t row, uint32_t ta, uint32_t tb, int c0, const float* inv_s) {
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    uint32_t a0[8], a1[8], a2[8], b0[8], b1[8], b2[8];
+    const int c = c0 + half * 8;
+    tc::tmem_ld8_nowait(ta + c, a0);
+    tc::tmem_ld8_nowait(ta + KC + c, a1);
+    tc::tmem_ld8_nowait(ta + 2 * KC + c, a2);
+    tc::tmem_ld8_nowait(tb + c, b0);
+    tc::tmem_ld8_nowait(tb + KC + c, b1);
+    tc::tmem_ld8_nowait(tb + 2 * KC + c, b2);
+    tc::tmem_ld_wait();
+    if (row < n) {
+      float4* dst = reinterpret_cast<float4*>(Y + row * KC + c);
+      const float* is = inv_s + half * 8;
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = ((__uint_as_float(a0[u]) + __uint_as_float(b0[u])) +
+                ((__uint_as_float(a1[u]) + __uint_as_float(b1[u])) + (__uint_as_float(a2[u]) + __uint_as_float(b2[u]))) * (1.f / 2048.f)) * is[u];
+      atomicAdd(dst, make_float4(v[0], v[1], v[2], v[3]));
+      atomicAdd(dst + 1, make_float4(v[4], v[5], v[6], v[7]));
+    }
+  }
+}
+
 template <int KC>
 __global__ void __launch_bounds__(H_THREADS, 1)
 k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* mu, int raw,
@@ -452,8 +480,8 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
   const int64_t i0 = (int64_t)I * TILE;
   constexpr uint32_t LBO_B = (2 * KC) * 16;
   constexpr uint32_t BLK = 16 * LBO_B;
-  constexpr uint32_t COL_D1 = 0, COL_D2 = 96;
-  const bool tcwarp = warp == 12;
+  constexpr uint32_t COL_D1 = 0, COL_D2 = 192;    // D1 of the even / odd tiles at 0 / 96, D2[b] at 192 + 96 b
+  const bool tcwarp = warp == 12 || warp == 14;   // two issuing lanes: even / odd tiles of the run
   const bool rows_ok = (i0 + TILE <= n) && (pv.raw == 2);
   const int64_t tix0 = tri((int64_t)I) - tri((int64_t)tr0);
 
@@ -486,28 +514,32 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
       }
     }
   } else if (tcwarp) {
-    // =================================== MMA issuer ===================================
+    // =================================== MMA issuers ===================================
+    // Two lanes (warps 12 and 14) take the even / odd tiles of the run: the barrier round trips of one overlap the MMA issue
+    // of the other (a single lane spent ~0.75 k clk per tile in them next to ~3 k clk of issue).  Each accumulates the direct
+    // result of its tiles in its own D1 (summed by the final flush); D2[b] belongs to parity b anyway.
     if (lane == 0) {
+      const int par = (warp - 12) >> 1;
       const uint32_t id_cat = make_idesc_f16(128, 2 * KC, 0), id_one = make_idesc_f16(128, KC, 0);
       const uint32_t id_cat_t = make_idesc_f16(128, 2 * KC, 1), id_one_t = make_idesc_f16(128, KC, 1);
       const uint64_t bI0 = tc::make_desc(tc::smem_u32(sm.bkI), LBO_B, 128u);
+      const uint32_t d1 = tm + COL_D1 + (uint32_t)par * 96u, d2 = tm + COL_D2 + (uint32_t)par * 96u;
       tc::mbar_wait(&sm.bIfull, 0u);
-      for (int k = 0; k < nt; ++k) {
-        const int b = k & 1, r = k % 3;
+      for (int k = par; k < nt; k += 2) {
+        const int b = par, r = k % 3;
         tc::mbar_wait(&sm.bfull[r], (uint32_t)((k / 3) & 1));
         tc::mbar_wait(&sm.ready[b], (uint32_t)((k >> 1) & 1));
         if (k >= 2 && !(dbg & 1)) tc::mbar_wait(&sm.flushed[b], (uint32_t)(((k - 2) >> 1) & 1));   // D2[b] of tile k-2 has been read
         tc::fence_after();
         const uint32_t p0 = tc::smem_u32(sm.tile[b][0]), p1 = tc::smem_u32(sm.tile[b][1]);
         const uint64_t bJ0 = tc::make_desc(tc::smem_u32(sm.bkJ[r]), LBO_B, 128u);
-        const uint32_t d2 = tm + COL_D2 + (uint32_t)b * 96u;
 #pragma unroll 2
         for (int ks = 0; ks < ((dbg & 2) ? 0 : TILE / 16); ++ks) {
           const uint64_t db = (uint64_t)((uint32_t)ks * ((2u * LBO_B) >> 4));
-          const uint32_t acc1 = (k > 0 || ks > 0) ? 1u : 0u, acc2 = ks > 0 ? 1u : 0u;
+          const uint32_t acc1 = (k > par || ks > 0) ? 1u : 0u, acc2 = ks > 0 ? 1u : 0u;
           // direct: A K-major (M = row: SBO 128 between 8-row groups; K = column: LBO H_SJ between 8-column groups)
-          mma_f16(tm + COL_D1, tc::make_desc(p0 + (uint32_t)ks * 2u * H_SJ, H_SJ, 128u), bJ0 + db, id_cat, acc1);
-          mma_f16(tm + COL_D1 + 2 * KC, tc::make_desc(p1 + (uint32_t)ks * 2u * H_SJ, H_SJ, 128u), bJ0 + db, id_one, acc1);
+          mma_f16(d1, tc::make_desc(p0 + (uint32_t)ks * 2u * H_SJ, H_SJ, 128u), bJ0 + db, id_cat, acc1);
+          mma_f16(d1 + 2 * KC, tc::make_desc(p1 + (uint32_t)ks * 2u * H_SJ, H_SJ, 128u), bJ0 + db, id_one, acc1);
           // mirrored: the same image as an MN-major A operand (M = column: SBO H_SJ; K = row: LBO 128)
           mma_f16(d2, tc::make_desc(p0 + (uint32_t)ks * 256u, 128u, H_SJ), bI0 + db, id_cat_t, acc2);
           mma_f16(d2 + 2 * KC, tc::make_desc(p1 + (uint32_t)ks * 256u, 128u, H_SJ), bI0 + db, id_one_t, acc2);
@@ -518,7 +550,7 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
     }
   } else if (warp >= 8 && warp < 12) {
     // =================================== flusher warps ===================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(72));
     const int q = warp & 3;                              // TMEM lane quarter (= warp % 4)
     const int ltid = q * 32 + lane;
     const uint32_t tlane = tm + ((uint32_t)(q * 32) << 16);
@@ -537,11 +569,14 @@ k_propagate_h(const float* __restrict__ tiles, int64_t n, int tr0, const float* 
     }
     if (on) {                                            // the run's direct result (complete with the last tile_done)
 #pragma unroll
-      for (int cg = 0; cg < KC / 16; ++cg) h_flush<KC>(Y, n, i0 + ltid, tlane + COL_D1, cg * 16, sm.inv_s + cg * 16);
+      for (int cg = 0; cg < KC / 16; ++cg) {
+        if (nt >= 2) h_flush2<KC>(Y, n, i0 + ltid, tlane + COL_D1, tlane + COL_D1 + 96u, cg * 16, sm.inv_s + cg * 16);
+        else h_flush<KC>(Y, n, i0 + ltid, tlane + COL_D1, cg * 16, sm.inv_s + cg * 16);
+      }
     }
   } else if (warp < 8) {
     // =================================== converter warps ===================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(200));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(192));     // 2 x 128 x 192 + 128 x 72 + 128 x 48 <= 64 K registers
     auto fetch = [&](int J, float4 (&dst)[16]) {
       const float4* src = reinterpret_cast<const float4*>(tiles + (tix0 + J) * TILE_ELEMS);
 #pragma unroll

@@ -153,10 +153,12 @@ def test_fold_persistent_engine_multi_tile(eng, density, grid, wset):
     finally:
         N.lib().mcgra_set_engine(1, 100)
         N.lib().mcgra_set_engine(1, DEFAULT_ENGINE[1])
-    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)
-    # (not bit-equal: the degree row sums and the norm term are accumulated with float / double atomics in tile order)
-    assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-6
-    np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-5, atol=5e-6)
+    # (not bit-equal: the degree row sums and the norm term are accumulated with float / double atomics in tile order; when
+    #  the budget binds, a bisection decision at the 1e-5 bracket can flip on such a difference and shift mu by < 1e-5)
+    tol = 5e-6 if density > 1.0 else 3e-5
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6 if density > 1.0 else 1e-5)
+    assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < tol
+    np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-5, atol=tol)
 
 
 @pytest.mark.parametrize("grid", [5, 0])
