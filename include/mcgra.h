@@ -73,6 +73,10 @@ int mcgra_version(void);
  *   which 3 = mcgra_gemm_nt: 1 cta_group::1 (128 x 128 tiles), 2 cta_group::2 CTA pairs (256 x 256 tiles) [default]
  *   which 4 = element-wise pass: 0 one tile per CTA, 1 persistent bulk-staged kernel for MSE on the clamped / lazily
  *                           projected view, 0 otherwise [default]
+ *   which 5 = mcgra_ensemble: 0 one CTA per 64 x 64 block, 1 one CTA per block PAIR (I, J) / (J, I) when the full matrix is
+ *                           written (symmetric terms evaluated once), 0 for row bands [default]
+ *   which 6 = mcgra_auc_ap: 0 1024-sample search table, 1 the sorted positives (or the largest sample that fits) in
+ *                           the 227 KB of shared memory [default]
  * Returns 0, or -1 for an unknown selector.                                                                            */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */

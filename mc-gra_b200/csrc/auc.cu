@@ -190,6 +190,324 @@ k_rank_negatives(const float* __restrict__ scores, const uint8_t* __restrict__ l
   }
 }
 
+// Ranking against the DISTINCT positive keys, search table in dynamic shared memory.
+//
+// What bounds k_rank_negatives (measured, tools/auc_ab.py, 4.3e9 negatives): not the histogram updates (5 ms) but the
+// searches (87 of 119 ms) -- after its 1024-sample table every lane walks the sorted array in its own 128-byte line, and a
+// negative that ties with a positive is searched twice (lower and upper bound).  The scores of the reference's ensemble
+// (sums of sigmoids of clamped grams + integer label terms) are heavily tied: 2 055 distinct values among 294 878 positives at
+// the bench size.  So the sorted positives are first reduced to their distinct keys U[0 .. nU) with C[u] = number of positives
+// below U[u] (C[nU] = npos; k_unique_pos), and a negative needs ONE search over U: lb = C[u], ub = C[u + 1] if U[u] ties with
+// it, else lb.  U and C both live in shared memory while 2 nU + 1 <= 57 344 words; beyond that U is sampled (57 344 samples,
+// the remaining log2(nU / 57 344) levels in global memory) and C is read from global memory.  The search has a uniform trip
+// count (branch-free halving), and a thread ranks 4 consecutive pairs per round (16-byte score / 4-byte label loads, the next
+// round's loaded before the current one is ranked).
+extern __shared__ uint32_t dyn_tab[];
+
+// distinct keys of the sorted positives; single block (npos is a few 1e5: < 1 ms)
+__global__ void __launch_bounds__(1024)
+k_unique_pos(const uint32_t* __restrict__ pos, unsigned long long* __restrict__ counter, int64_t npos_max,
+             uint32_t* __restrict__ U, uint32_t* __restrict__ Cidx) {
+  __shared__ int carry;
+  __shared__ int wsum[32];
+  const int64_t np64 = (int64_t)counter[0];
+  const int npos = (int)(np64 < npos_max ? np64 : npos_max);
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < npos; base += 1024) {
+    const int t = base + threadIdx.x;
+    const int flag = (t < npos && (t == 0 || pos[t] != pos[t - 1])) ? 1 : 0;
+    int inc = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      const int sv = wsum[lane];
+      int si = sv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, si, o);
+        if (lane >= o) si += v;
+      }
+      wsum[lane] = si - sv;
+    }
+    __syncthreads();
+    const int excl = carry + wsum[w] + inc - flag;
+    if (flag) { U[excl] = pos[t]; Cidx[excl] = (uint32_t)t; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + flag;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { Cidx[carry] = (uint32_t)npos; counter[3] = (unsigned long long)carry; }
+}
+
+// number of table entries below k (uniform trip count: depends on ntab only)
+__device__ __forceinline__ int tab_lower(const uint32_t* tab, int ntab, uint32_t k) {
+  if (ntab <= 0) return 0;
+  int base = 0, len = ntab;
+  while (len > 1) {
+    const int half = len >> 1;
+    base += (tab[base + half - 1] < k) ? half : 0;
+    len -= half;
+  }
+  return base + ((tab[base] < k) ? 1 : 0);
+}
+
+// Sampled mode with <= 3 distinct keys per sample: segment t -> one aligned 32-byte block
+//   [U[t step .. t step + step) | C[t step .. t step + step]]   (keys beyond nU = +inf, indices clamped to C[nU] = npos)
+// so that a negative needs one sector of global memory instead of a walk over U plus two reads of C (each divergent
+// global access costs ~15 ms per 4.3e9 negatives: 32 L1 wavefronts per warp).
+__global__ void k_build_blocks(const uint32_t* __restrict__ U, const uint32_t* __restrict__ Cidx,
+                               const unsigned long long* __restrict__ counter, int tab_cap, uint32_t* __restrict__ blocks) {
+  const int nU = (int)counter[3];
+  if (2 * (int64_t)nU + 1 <= (int64_t)tab_cap) return;
+  const int step = (nU + tab_cap - 1) / tab_cap;
+  if (step > 3) return;
+  const int ntab = (nU + step - 1) / step;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntab; t += gridDim.x * blockDim.x) {
+    uint32_t* w = blocks + 8 * (int64_t)t;
+    for (int i = 0; i < 8; ++i) {
+      uint32_t v = 0xffffffffu;
+      if (i < step) {
+        const int idx = t * step + i;
+        if (idx < nU) v = U[idx];
+      } else if (i <= 2 * step) {
+        const int idx = t * step + (i - step);
+        v = Cidx[idx < nU ? idx : nU];
+      }
+      w[i] = v;
+    }
+  }
+}
+
+constexpr int RK_E = 4;       // pairs per thread and round
+__global__ void __launch_bounds__(1024, 1)
+k_rank_negatives_tab(const float* __restrict__ scores, const uint8_t* __restrict__ labels, int64_t N,
+                     const uint32_t* __restrict__ U, const uint32_t* __restrict__ Cidx, const uint4* __restrict__ blocks,
+                     const unsigned long long* __restrict__ counter, unsigned long long* __restrict__ hist /*[npos+1]*/,
+                     unsigned long long* __restrict__ sums /*[2]*/, int tab_cap, int dbg) {
+  uint32_t* tab = dyn_tab;
+  const int npos = (int)counter[0];
+  const int nU = (int)counter[3];
+  const bool both = 2 * (int64_t)nU + 1 <= (int64_t)tab_cap;      // keys and start indices in shared memory
+  const bool hsm = 3 * (int64_t)nU + 2 <= (int64_t)tab_cap;       // ... and a CTA-private histogram over the nU + 1 possible ub
+  const int step = both ? 1 : (nU + tab_cap - 1) / tab_cap;
+  const int ntab = both ? nU : (nU + step - 1) / step;             // tab[t] = U[t * step]
+  uint32_t* Cs = tab + ntab;
+  uint32_t* Hs = Cs + nU + 1;
+  const bool ident = nU == npos;
+  const bool blocked = !both && step <= 3;                          // sampled table + one 32-byte block per segment (k_build_blocks)
+  for (int t = threadIdx.x; t < ntab; t += blockDim.x) tab[t] = U[(int64_t)t * step];
+  if (both)
+    for (int t = threadIdx.x; t <= nU; t += blockDim.x) Cs[t] = Cidx[t];
+  if (hsm)
+    for (int t = threadIdx.x; t <= nU; t += blockDim.x) Hs[t] = 0u;
+  __syncthreads();
+  const bool vec = ((reinterpret_cast<uintptr_t>(scores) & 15) == 0) && ((reinterpret_cast<uintptr_t>(labels) & 3) == 0);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * RK_E;
+  const int64_t nround = (N + stride - 1) / stride;
+  const int lane = threadIdx.x & 31;
+  unsigned long long twice = 0, nneg = 0;
+
+  auto load = [&](int64_t g, float (&sc)[RK_E], bool (&neg)[RK_E]) {
+    if (vec && g + RK_E <= N) {
+      const float4 s4 = *reinterpret_cast<const float4*>(scores + g);
+      const uchar4 l4 = *reinterpret_cast<const uchar4*>(labels + g);
+      sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+      neg[0] = !l4.x; neg[1] = !l4.y; neg[2] = !l4.z; neg[3] = !l4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < RK_E; ++e) {
+        const bool in = g + e < N;
+        neg[e] = in && !labels[in ? g + e : 0];
+        sc[e] = in ? scores[g + e] : 0.f;
+      }
+    }
+  };
+
+  int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * RK_E;
+  float sc[RK_E], scn[RK_E];
+  bool neg[RK_E], negn[RK_E];
+#pragma unroll
+  for (int e = 0; e < RK_E; ++e) { sc[e] = scn[e] = 0.f; neg[e] = negn[e] = false; }
+  if (g < N) load(g, sc, neg);
+  for (int64_t rd = 0; rd < nround; ++rd) {
+    const int64_t gn = g + stride;
+#pragma unroll
+    for (int e = 0; e < RK_E; ++e) negn[e] = false;
+    if (rd + 1 < nround && gn < N) load(gn, scn, negn);
+    {                                                   // rounds further ahead: into L2 (no registers)
+      const int64_t gp = g + 4 * stride;
+      if (gp + RK_E <= N) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(scores + gp));
+        if ((lane & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + gp));
+      }
+    }
+    uint32_t k[RK_E];
+    int u[RK_E];
+    int lb[RK_E], ub[RK_E], vb[RK_E];     // vb: ub in the space of distinct keys (ub = C[vb])
+#pragma unroll
+    for (int e = 0; e < RK_E; ++e) { k[e] = fkey(sc[e]); u[e] = 0; lb[e] = ub[e] = vb[e] = 0; }
+    if (blocked) {
+      // segment t = [t * step, (t + 1) * step) of the distinct keys, tab[t] = its first key.  t = last sample <= k; then
+      // the keys below k, a tie and the start indices C[u], C[u + 1] all come from the segment's 32-byte block.
+      int base[RK_E];
+#pragma unroll
+      for (int e = 0; e < RK_E; ++e) base[e] = 0;
+      int len = ntab;
+      while (len > 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int e = 0; e < RK_E; ++e) base[e] += (tab[base[e] + half - 1] <= k[e]) ? half : 0;
+        len -= half;
+      }
+#pragma unroll
+      for (int pr = 0; pr < RK_E; pr += 2) {           // two blocks in flight (register budget of 1024 threads)
+        uint32_t w[2][8];
+        int t[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int e = pr + q;
+          t[q] = base[e] + ((tab[base[e]] <= k[e]) ? 1 : 0) - 1;
+          const uint4* bp = blocks + 2 * (int64_t)(t[q] < 0 ? 0 : t[q]);
+          // one 256-bit load (LDG.E.256): a divergent access costs its L1 wavefronts per instruction, not per byte
+          asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(w[q][0]), "=r"(w[q][1]), "=r"(w[q][2]), "=r"(w[q][3]), "=r"(w[q][4]), "=r"(w[q][5]),
+                         "=r"(w[q][6]), "=r"(w[q][7])
+                       : "l"(bp));
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int e = pr + q;
+          const uint32_t w0 = w[q][0], w1 = w[q][1], w2 = w[q][2], w3 = w[q][3];
+          const uint32_t w4 = w[q][4], w5 = w[q][5], w6 = w[q][6], w7 = w[q][7];
+          const uint32_t kk = k[e];
+          const bool s1 = step > 1, s2 = step > 2;
+          const int m = (w0 < kk ? 1 : 0) + ((s1 && w1 < kk) ? 1 : 0) + ((s2 && w2 < kk) ? 1 : 0);
+          const bool tied = (w0 == kk) || (s1 && w1 == kk) || (s2 && w2 == kk);
+          const int ci = step + m;                       // C[u] sits at word step + m of the block, C[u + 1] behind it
+          const uint32_t c0 = ci == 1 ? w1 : ci == 2 ? w2 : ci == 3 ? w3 : ci == 4 ? w4 : ci == 5 ? w5 : w6;
+          const uint32_t c1 = ci == 1 ? w2 : ci == 2 ? w3 : ci == 3 ? w4 : ci == 4 ? w5 : ci == 5 ? w6 : w7;
+          lb[e] = t[q] < 0 ? 0 : (int)c0;
+          ub[e] = t[q] < 0 ? 0 : (tied ? (int)c1 : (int)c0);
+        }
+      }
+    } else {
+    if (ntab > 0) {
+      // RK_E interleaved searches with one trip count
+      int base[RK_E];
+#pragma unroll
+      for (int e = 0; e < RK_E; ++e) base[e] = 0;
+      int len = ntab;
+      while (len > 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int e = 0; e < RK_E; ++e) base[e] += (tab[base[e] + half - 1] < k[e]) ? half : 0;
+        len -= half;
+      }
+#pragma unroll
+      for (int e = 0; e < RK_E; ++e) u[e] = base[e] + ((tab[base[e]] < k[e]) ? 1 : 0);
+      if (step > 1) {
+        // u = first SAMPLE not below k: the distinct key sought lies in ((u - 1) * step, u * step]  (u == ntab: up to nU).
+        // The RK_E segment searches run interleaved with one trip count (segments are <= step long; entries beyond a
+        // segment's end count as +inf), so that their global loads overlap instead of forming one dependent chain.
+        int l[RK_E], h[RK_E];
+#pragma unroll
+        for (int e = 0; e < RK_E; ++e) {
+          l[e] = u[e] == 0 ? 0 : (u[e] - 1) * step + 1;
+          h[e] = u[e] == ntab ? nU : u[e] * step;
+        }
+        int len2 = step;
+        while (len2 > 1) {
+          const int half = len2 >> 1;
+#pragma unroll
+          for (int e = 0; e < RK_E; ++e) {
+            const int idx = l[e] + half - 1;
+            const uint32_t v = idx < h[e] ? U[idx] : 0xffffffffu;
+            l[e] += (v < k[e]) ? half : 0;
+          }
+          len2 -= half;
+        }
+#pragma unroll
+        for (int e = 0; e < RK_E; ++e) {
+          const uint32_t v = l[e] < h[e] ? U[l[e]] : 0xffffffffu;
+          u[e] = l[e] + ((v < k[e]) ? 1 : 0);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < RK_E; ++e) u[e] = 0;
+    }
+#pragma unroll
+    for (int e = 0; e < RK_E; ++e) {
+      if (both) {
+        const bool tied = u[e] < nU && tab[u[e]] == k[e];
+        lb[e] = (int)Cs[u[e]];
+        vb[e] = u[e] + (tied ? 1 : 0);
+        ub[e] = tied ? (int)Cs[vb[e]] : lb[e];
+      } else {
+        const bool tied = u[e] < nU && U[u[e]] == k[e];
+        vb[e] = u[e] + (tied ? 1 : 0);
+        if (ident) { lb[e] = u[e]; ub[e] = vb[e]; }       // all positives distinct: C[u] = u
+        else { lb[e] = (int)Cidx[u[e]]; ub[e] = tied ? (int)Cidx[vb[e]] : lb[e]; }
+      }
+    }
+    }      // !blocked
+    unsigned int tw32 = 0;
+#pragma unroll
+    for (int e = 0; e < RK_E; ++e) {
+      if (neg[e]) {
+        tw32 += 2u * (unsigned)(npos - ub[e]) + (unsigned)(ub[e] - lb[e]);      // 12 npos < 2^32: npos < 2^28 checked by the host
+        nneg += 1;
+      }
+      if (!(dbg & 1)) {
+        const int sent = -1 - lane;         // unique sentinel so inactive lanes do not aggregate
+        if (hsm) {
+          // few distinct values = hot bins: global updates of the same ~nU addresses serialise in L2 (90 of 120 ms measured)
+          const unsigned peers = __match_any_sync(0xffffffffu, neg[e] ? vb[e] : sent);
+          if (neg[e] && lane == (__ffs(peers) - 1)) atomicAdd(Hs + vb[e], (unsigned)__popc(peers));
+        } else {
+          const unsigned peers = __match_any_sync(0xffffffffu, neg[e] ? ub[e] : sent);
+          if (neg[e] && lane == (__ffs(peers) - 1)) atomicAdd(hist + ub[e], (unsigned long long)__popc(peers));
+        }
+      }
+    }
+    twice += (unsigned long long)tw32;
+    g = gn;
+#pragma unroll
+    for (int e = 0; e < RK_E; ++e) { sc[e] = scn[e]; neg[e] = negn[e]; }
+  }
+  __shared__ unsigned long long r0[32], r1[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    twice += __shfl_xor_sync(0xffffffffu, twice, o);
+    nneg += __shfl_xor_sync(0xffffffffu, nneg, o);
+  }
+  if (lane == 0) { r0[threadIdx.x >> 5] = twice; r1[threadIdx.x >> 5] = nneg; }
+  __syncthreads();
+  if (hsm && !(dbg & 1)) {
+    for (int t = threadIdx.x; t <= nU; t += blockDim.x) {
+      const uint32_t c = Hs[t];
+      if (c) atomicAdd(hist + Cs[t], (unsigned long long)c);
+    }
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, b = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += r0[w]; b += r1[w]; }
+    if (a) atomicAdd(sums, a);
+    if (b) atomicAdd(sums + 1, b);
+  }
+}
+
+int g_auc_dbg = 0;         // timing experiments only (mcgra_set_engine(6, 100 + bits)): 1 no histogram updates (AP invalid)
+int g_auc_engine = 1;      // mcgra_set_engine(6, v): 0 k_rank_negatives (1024-sample table), 1 k_rank_negatives_tab (default)
+constexpr int TAB_CAP_MAX = 57344;      // 224 KB of dynamic shared memory
+
 // suffix sums of hist -> fp(>= pos[t]) = sum_{j > t} hist[j]; AP over distinct positive values.  Single block.
 __global__ void __launch_bounds__(1024)
 k_ap_finish(const uint32_t* __restrict__ pos, const unsigned long long* __restrict__ counter,
@@ -265,6 +583,7 @@ __global__ void k_make_keys_desc(const float* __restrict__ scores, int64_t N, ui
 }
 
 inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+constexpr int64_t TAB_CAP_MAX_WS = 57344;      // = TAB_CAP_MAX: one 32-byte block per table sample
 
 // LSD radix sort of `keys` (and payload) in place using `tmp` buffers; 4 passes of 8 bits
 template <typename PAY>
@@ -289,12 +608,18 @@ int radix_sort(uint32_t* keys, PAY* pay, uint32_t* keys_tmp, PAY* pay_tmp, int64
 
 extern "C" {
 
+int mcgra_set_auc_engine_(int value) {
+  if (value >= 100) g_auc_dbg = value - 100; else g_auc_engine = value;
+  return 0;
+}
+
 // workspace layout (bytes): [counter+sums 256][poskeys cap*4][poskeys_tmp cap*4][hist_sort][offs_sort][hist cap+1 u64]
+// [start indices of the distinct keys cap+1 u32][segment blocks 57 344 x 32 B]   (counter block: [0] npos, [1..2] sums, [3] number of distinct keys)
 int64_t mcgra_auc_workspace_bytes(int64_t N, int64_t npos_max) {
   (void)N;
   const int64_t nb = (npos_max + CHUNK - 1) / CHUNK + 1;
   return 256 + 2 * align256(npos_max * 4) + align256(nb * 256 * 4) + align256(nb * 256 * 8) +
-         align256((npos_max + 2) * 8);
+         align256((npos_max + 2) * 8) + align256((npos_max + 2) * 4) + TAB_CAP_MAX_WS * 32;
 }
 
 // The three stages of mcgra_auc_ap, callable separately so that the n^2 pairs can be split over ranks by row bands:
@@ -335,7 +660,29 @@ int mcgra_auc_stage(int stage, const float* scores, const uint8_t* labels, int64
   } else if (stage == 1) {
     int rc = radix_sort<uint32_t>(pos, nullptr, pos_tmp, nullptr, npos_max, hs, offs, st);
     if (rc) return rc;
-    if (N > 0) k_rank_negatives<<<148 * 8, 256, 0, st>>>(scores, labels, N, pos, counter, hist, sums);
+    if (N > 0 && g_auc_engine == 1 && npos_max < (1LL << 28)) {      // (per-round 32-bit partial sums: 12 npos < 2^32)
+      // distinct keys into the (now free) sort buffer, start indices behind the histogram
+      uint32_t* Cidx = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(hist) + align256((npos_max + 2) * 8));
+      k_unique_pos<<<1, 1024, 0, st>>>(pos, counter, npos_max, pos_tmp, Cidx);
+      // table capacity (32-bit words): keys + start indices + private histogram of all distinct values when they fit, else
+      // what fits of them (the kernel decides from the number of distinct keys), at least the largest sample
+      const int64_t want = 3 * npos_max + 2;
+      const int cap = (int)(want < TAB_CAP_MAX ? (want > 1024 ? want : 1024) : TAB_CAP_MAX);
+      const size_t smem = (size_t)cap * 4;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_rank_negatives_tab, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             TAB_CAP_MAX * 4);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+      }
+      uint32_t* blocks = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(Cidx) + align256((npos_max + 2) * 4));
+      if (want > cap) k_build_blocks<<<64, 256, 0, st>>>(pos_tmp, Cidx, counter, cap, blocks);
+      k_rank_negatives_tab<<<148, 1024, smem, st>>>(scores, labels, N, pos_tmp, Cidx, reinterpret_cast<const uint4*>(blocks),
+                                                    counter, hist, sums, cap, g_auc_dbg);
+    } else if (N > 0) {
+      k_rank_negatives<<<148 * 8, 256, 0, st>>>(scores, labels, N, pos, counter, hist, sums);
+    }
   } else {
     k_ap_finish<<<1, 1024, 0, st>>>(pos, counter, hist, sums, out);
   }

@@ -424,36 +424,74 @@ k_pairs_mma(const float* __restrict__ tiles, int64_t n, int64_t t0, const float*
   if (k2 != 0.f) block_atomic_add_d((double)v2 * (double)k2, acc + MCGRA_ACC_C2, sm.red);
 }
 
+int g_ensemble_engine = 1;  // mcgra_set_engine(5, v): 0 one CTA per 64 x 64 block, 1 one CTA per block PAIR for the full matrix (default)
 int g_pairs_engine = 2;     // 0 fp32 FFMA (exact), 1 mma.sync 3xTF32, 2 tcgen05 for the entropy-only configuration (else 1)
 
 // x_final tiles = relu(z_i . z_j), j < i < n  (dot_product_decode of the last embedding, :300-301)
+// Register-tiled: thread (tx, ty) owns rows 8 ty .. + 7 and columns 8 tx .. + 7 of the tile; factors staged transposed
+// ([k][row], pitch 132) so that one k step is four 16-byte shared loads for 64 FMAs (the scalar form was LDS-bound:
+// 9.4 ms for the 8.6 GB of tiles at n = 65 536).  The fmaf chain over k runs in the same order as before.
+constexpr int DLD = TILE + 4;
 __global__ void __launch_bounds__(256)
 k_decode_to_tiles(const float* __restrict__ z, int64_t n, int64_t t0, float* __restrict__ tiles) {
-  __shared__ float zI[TILE][HID + 1], zJ[TILE][HID + 1];
+  __shared__ __align__(16) float zIT[HID * DLD], zJT[HID * DLD];
   int I, J;
   tile_coords(t0 + blockIdx.x, I, J);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t i0 = (int64_t)I * TILE, j0 = (int64_t)J * TILE;
-  for (int e = tid; e < TILE * HID; e += 256) {
-    const int a = e >> 4, k = e & 15;
-    zI[a][k] = (i0 + a < n) ? z[(i0 + a) * HID + k] : 0.f;
-    zJ[a][k] = (j0 + a < n) ? z[(j0 + a) * HID + k] : 0.f;
+  for (int it = tid; it < 2 * TILE * (HID / 4); it += 256) {
+    const int m = it >= TILE * (HID / 4) ? 1 : 0, idx = it - m * TILE * (HID / 4);
+    const int a = idx >> 2, q4 = idx & 3;
+    const int64_t row = (m ? j0 : i0) + a;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) {
+      const float* zr = z + row * HID + 4 * q4;
+      if ((reinterpret_cast<uintptr_t>(z) & 15) == 0) v = __ldg(reinterpret_cast<const float4*>(zr));
+      else v = make_float4(zr[0], zr[1], zr[2], zr[3]);
+    }
+    float* dst = (m ? zJT : zIT) + (4 * q4) * DLD + a;
+    dst[0] = v.x; dst[DLD] = v.y; dst[2 * DLD] = v.z; dst[3 * DLD] = v.w;
   }
   __syncthreads();
-  float* dst = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
-  for (int e = tid; e < TILE_ELEMS; e += 256) {
-    const int a = e >> 7, b = e & 127;
-    const int64_t gi = i0 + a, gj = j0 + b;
-    float v = 0.f;
-    if (gj < gi && gi < n) {
-      float s = 0.f;
+  float s[8][8];
 #pragma unroll
-      for (int k = 0; k < HID; ++k) s = fmaf(zI[a][k], zJ[b][k], s);
-      v = fmaxf(s, 0.f);
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[p][q] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < HID; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4*>(zIT + k * DLD + ty * 8);
+    const float4 a1 = *reinterpret_cast<const float4*>(zIT + k * DLD + ty * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(zJT + k * DLD + tx * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(zJT + k * DLD + tx * 8 + 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[p][q] = fmaf(av[p], bv[q], s[p][q]);
+  }
+  float* dst = tiles + (int64_t)blockIdx.x * TILE_ELEMS;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int a = ty * 8 + p;
+    const int64_t gi = i0 + a;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int64_t gj = j0 + tx * 8 + q;
+      v[q] = (gj < gi && gi < n) ? fmaxf(s[p][q], 0.f) : 0.f;
     }
-    dst[e] = v;
+    float4* d4 = reinterpret_cast<float4*>(dst + a * TILE + tx * 8);
+    d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d4[1] = make_float4(v[4], v[5], v[6], v[7]);
   }
 }
+
+// sigmoid of dot_product_decode2 (:425) for v >= 0 (after the relu): MUFU ex2 + rcp, ~2e-7 relative (the IEEE expf + division
+// form cost ~30 instructions per entry and term, more than the 16-step fmaf chain it follows).  ONE definition for the three
+// kernels below, so that the fused ensemble stays bit-equal to the sequence of single-term kernels.
+__device__ __forceinline__ float ens_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
 // out[i, j] += f(Z_i . Z_j)   for i in [row0,row1), all j; 32x32 output block per CTA, d <= 32
 __global__ void __launch_bounds__(256)
@@ -477,7 +515,7 @@ k_gram_accumulate(const float* __restrict__ Z, int d, int64_t n, int variant, co
     if (variant == 2) s = s / fmaxf(rownorm[gi], 1e-12f);
     float v = (variant == 3) ? s : fmaxf(s - (gi == gj ? 1.f : 0.f), 0.f);
     if (variant == 4) v = (gi == gj) ? 0.f : fmaxf(s, 0.f);
-    if (variant == 0) v = 1.f / (1.f + expf(-v));
+    if (variant == 0) v = ens_sigmoid(v);
     out[gi * ld + gj] += v;
   }
 }
@@ -555,7 +593,7 @@ k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, f
           if (T.variant == 2) sv = sv / rn;
           float v = (T.variant == 3) ? sv : fmaxf(sv - (gi == gj ? 1.f : 0.f), 0.f);
           if (T.variant == 4) v = (gi == gj) ? 0.f : fmaxf(sv, 0.f);
-          if (T.variant == 0) v = 1.f / (1.f + expf(-v));
+          if (T.variant == 0) v = ens_sigmoid(v);
           acc[p][q] += v;
         }
       }
@@ -601,6 +639,196 @@ k_ensemble(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, f
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (gj + q < n) out[gi * ld + gj + q] = acc[p][q];
+    }
+  }
+}
+
+// Symmetric form of k_ensemble for the full matrix (row0 = 0, row1 = n): one CTA per PAIR of 64 x 64 blocks (I >= J).
+// The stored block, the gram sums s_ij (the fmaf chain over k is the same for (i, j) and (j, i): the products commute)
+// and their variant transforms (sigmoid: expf + division, the expensive part) are evaluated once and feed two
+// accumulation chains -- the block (I, J) and its mirror (J, I) -- which differ only in the un-symmetric terms (dense
+// operands, row norms of variant 2).  Element values are bit-for-bit those of k_ensemble: same chain order, same
+// transforms, same left-to-right sum of the terms.  Factors are staged by 16-byte loads into a [k][row] layout with a
+// 68-float pitch (2-way instead of 16-way bank conflicts on the transposing stores).
+constexpr int ELD = EB + 4;
+__device__ __forceinline__ float ens_transform(float sv, bool diag, int variant) {
+  float v = (variant == 3) ? sv : fmaxf(sv - (diag ? 1.f : 0.f), 0.f);
+  if (variant == 4) v = diag ? 0.f : fmaxf(sv, 0.f);
+  if (variant == 0) v = ens_sigmoid(v);
+  return v;
+}
+
+__global__ void __launch_bounds__(256, 3)
+k_ensemble_sym(const float* __restrict__ tiles, int64_t n, mcgra_ensemble_args ea, float* __restrict__ out, int64_t ld) {
+  __shared__ __align__(16) float buf[2 * 32 * ELD];       // M stage: [64][65]; gram stage: ziT[32][68] | zjT[32][68]
+  int I, J;
+  tile_coords((int64_t)blockIdx.x, I, J);                  // pair index -> (I, J), I >= J (same triangle enumeration)
+  const int64_t bi = (int64_t)I * EB, bj = (int64_t)J * EB;
+  const bool offdiag = I != J;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4], act[4][4];                               // act: the mirrored block, act[p][q] = out[gj + q][gi + p]
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[p][q] = act[p][q] = 0.f;
+  if (tiles != nullptr) {
+    const float* tl = tiles + (tri(bi / TILE) + bj / TILE) * (int64_t)TILE_ELEMS + (bi % TILE) * TILE + (bj % TILE);
+    for (int e = tid; e < EB * EB; e += 256) {
+      const int rr = e >> 6, cc = e & 63;
+      buf[rr * (EB + 1) + cc] = fminf(fmaxf(tl[rr * TILE + cc], 0.f), 1.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4 + q;
+        const int a = (int)(gi > gj ? gi - bi : gj - bi), c = (int)(gi > gj ? gj - bj : gi - bj);
+        acc[p][q] = act[p][q] = (gi < n && gj < n && gi != gj) ? buf[a * (EB + 1) + c] : 0.f;
+      }
+    __syncthreads();
+  }
+  float* ziT = buf;
+  float* zjT = buf + 32 * ELD;
+  const bool vec_ok = (n & 3) == 0;
+  for (int tm = 0; tm < ea.nterms; ++tm) {
+    const mcgra_ensemble_term& T = ea.t[tm];
+    if (T.kind == MCGRA_TERM_GRAM) {
+      const int d = T.d;
+      if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(T.Z) & 15) == 0) {
+        const int dq = d >> 2, items = EB * dq;
+        for (int it = tid; it < 2 * items; it += 256) {
+          const int m = it >= items ? 1 : 0, idx = it - m * items;
+          const int a = idx / dq, q4 = idx - a * dq;
+          const int64_t row = (m ? bj : bi) + a;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < n) v = __ldg(reinterpret_cast<const float4*>(T.Z + row * d) + q4);
+          float* dst = (m ? zjT : ziT) + (4 * q4) * ELD + a;
+          dst[0] = v.x; dst[ELD] = v.y; dst[2 * ELD] = v.z; dst[3 * ELD] = v.w;
+        }
+      } else {
+        for (int e = tid; e < EB * d; e += 256) {
+          const int a = e / d, k = e % d;
+          ziT[k * ELD + a] = (bi + a < n) ? T.Z[(bi + a) * d + k] : 0.f;
+          zjT[k * ELD + a] = (bj + a < n) ? T.Z[(bj + a) * d + k] : 0.f;
+        }
+      }
+      __syncthreads();
+      float s[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[p][q] = 0.f;
+      for (int k = 0; k < d; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(ziT + k * ELD + ty * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(zjT + k * ELD + tx * 4);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s[p][q] = fmaf(av[p], bv[q], s[p][q]);
+      }
+      if (T.variant == 2) {                      // row-normalised gram: the two orientations divide by different norms
+        float rni[4], rnj[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4 + p;
+          rni[p] = gi < n ? fmaxf(T.rownorm[gi], 1e-12f) : 1.f;
+          rnj[p] = gj < n ? fmaxf(T.rownorm[gj], 1e-12f) : 1.f;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool dg = (bi + ty * 4 + p) == (bj + tx * 4 + q);
+            acc[p][q] += ens_transform(s[p][q] / rni[p], dg, 2);
+            act[p][q] += ens_transform(s[p][q] / rnj[q], dg, 2);
+          }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool dg = (bi + ty * 4 + p) == (bj + tx * 4 + q);
+            const float v = ens_transform(s[p][q], dg, T.variant);
+            acc[p][q] += v;
+            act[p][q] += v;
+          }
+      }
+      __syncthreads();
+    } else if (T.kind == MCGRA_TERM_DENSE) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {                         // block (I, J): row gi, columns gj .. gj + 3
+        const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4;
+        if (gi >= n) continue;
+        if (vec_ok) {
+          if (gj < n) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(T.dense + gi * n + gj));
+            acc[p][0] += v.x; acc[p][1] += v.y; acc[p][2] += v.z; acc[p][3] += v.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (gj + q < n) acc[p][q] += T.dense[gi * n + gj + q];
+        }
+      }
+      if (offdiag) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                       // block (J, I): row gj, columns gi .. gi + 3
+          const int64_t gj = bj + tx * 4 + q, gi = bi + ty * 4;
+          if (gj >= n) continue;
+          if (vec_ok) {
+            if (gi < n) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(T.dense + gj * n + gi));
+              act[0][q] += v.x; act[1][q] += v.y; act[2][q] += v.z; act[3][q] += v.w;
+            }
+          } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+              if (gi + p < n) act[p][q] += T.dense[gj * n + gi + p];
+          }
+        }
+      }
+    } else {
+      int64_t lj[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) lj[q] = (bj + tx * 4 + q < n) ? T.labels[bj + tx * 4 + q] : -1;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int64_t gi = bi + ty * 4 + p;
+        if (gi >= n) continue;
+        const int64_t li = T.labels[gi];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (bj + tx * 4 + q < n && li == lj[q]) { acc[p][q] += 1.f; act[p][q] += 1.f; }
+      }
+    }
+  }
+  const bool st_vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int64_t gi = bi + ty * 4 + p, gj = bj + tx * 4;
+    if (gi >= n) continue;
+    if (st_vec && gj + 3 < n) {
+      *reinterpret_cast<float4*>(out + gi * ld + gj) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (gj + q < n) out[gi * ld + gj + q] = acc[p][q];
+    }
+  }
+  if (offdiag) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t gj = bj + tx * 4 + q, gi = bi + ty * 4;
+      if (gj >= n) continue;
+      if (st_vec && gi + 3 < n) {
+        *reinterpret_cast<float4*>(out + gj * ld + gi) = make_float4(act[0][q], act[1][q], act[2][q], act[3][q]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (gi + p < n) out[gj * ld + gi + p] = act[p][q];
+      }
     }
   }
 }
@@ -651,6 +879,7 @@ int launch_pairs_mma(const float* tiles, int64_t n, int tr0, int64_t nt, const f
 extern "C" {
 
 int mcgra_set_pairs_engine_(int value) { g_pairs_engine = value; return 0; }
+int mcgra_set_ensemble_engine_(int value) { g_ensemble_engine = value; return 0; }
 
 int mcgra_pairs_tc_(int64_t n, int tr0, int tr1, const float* zhat, float k7, float* dzhat, double* acc, void* ws,
                     cudaStream_t st);
@@ -710,6 +939,13 @@ int mcgra_ensemble(const float* tiles, int64_t n, const mcgra_ensemble_args* arg
   for (int t = 0; t < args->nterms; ++t)
     if (args->t[t].kind == MCGRA_TERM_GRAM && (args->t[t].d < 1 || args->t[t].d > 32)) return -1;
   if (row1 <= row0) return 0;
+  if (g_ensemble_engine == 1 && row0 == 0 && row1 >= n) {       // full matrix: block pairs (I >= J), both orientations per CTA
+    const int64_t nb = (n + EB - 1) / EB, pairs = nb * (nb + 1) / 2;
+    if (pairs > 2147483647LL) return -3;
+    k_ensemble_sym<<<(unsigned)pairs, 256, 0, (cudaStream_t)stream>>>(tiles, n, *args, out, ld);
+    MCGRA_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((unsigned)((n + EB - 1) / EB), (unsigned)((row1 - row0 + EB - 1) / EB));
   if (grid.y > 65535) return -3;
   k_ensemble<<<grid, 256, 0, (cudaStream_t)stream>>>(tiles, n, *args, out, ld, row0, row1);

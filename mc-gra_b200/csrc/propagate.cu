@@ -990,7 +990,11 @@ extern "C" {
 int mcgra_set_fold_engine_(int value);
 int mcgra_set_pairs_engine_(int value);
 int mcgra_set_gemm_engine_(int value);
+int mcgra_set_ensemble_engine_(int value);
+int mcgra_set_auc_engine_(int value);
 int mcgra_set_engine(int which, int value) {
+  if (which == 5) return mcgra_set_ensemble_engine_(value);
+  if (which == 6) return mcgra_set_auc_engine_(value);
   if (which == 3) return mcgra_set_gemm_engine_(value);
   if (which == 4) {
     if (value >= 100) g_elem_grid = value - 100;

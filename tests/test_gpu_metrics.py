@@ -21,15 +21,26 @@ def test_auc_ap_matches_sklearn_fixture_with_ties():
     assert abs(ap - float(fn["ap_value"])) < 1e-12
 
 
-@pytest.mark.parametrize("n,ties", [(1000, False), (300000, True), (2000003, False)])
-def test_auc_ap_random(n, ties):
+@pytest.mark.parametrize("engine", [1, 0])
+@pytest.mark.parametrize("n,ties", [(1000, False), (300000, True), (1300003, False), (2000003, False), (2500001, True),
+                                    (5000011, False), (7000003, False)])
+def test_auc_ap_random(n, ties, engine):
+    """engine 1: distinct positive keys in dynamic shared memory -- keys + start indices + private histogram (tied cases,
+    n = 1000), sampled keys + one 32-byte block per segment of 1 / 2 / 3 distinct keys (~39 000 / ~60 000 / ~150 000
+    positives: n = 1.3e6, 2e6, 5e6), sampled keys + search in global memory (~210 000: n = 7e6); engine 0: the
+    1024-sample kernel over the sorted positives."""
     from mcgra_b200 import metrics
+    from mcgra_b200 import _native as N
+    N.lib().mcgra_set_engine(6, engine)
     rng = np.random.RandomState(n % 1000)
     y = (rng.random_sample(n) < 0.03).astype(np.uint8)
     s = (rng.standard_normal(n) + 0.8 * y).astype(np.float32)
     if ties:
         s = np.round(s * 20) / 20
-    auc, ap = metrics.roc_auc_ap(torch.from_numpy(s).cuda(), torch.from_numpy(y).cuda())
+    try:
+        auc, ap = metrics.roc_auc_ap(torch.from_numpy(s).cuda(), torch.from_numpy(y).cuda())
+    finally:
+        N.lib().mcgra_set_engine(6, 1)
     assert abs(auc - O.roc_auc(y, s)) < 1e-10
     assert abs(ap - O.average_precision(y, s)) < 1e-10
 
@@ -72,8 +83,9 @@ def test_metric_pool_api():
     assert abs(sub - O.roc_auc(real, pred)) < 1e-9
 
 
-@pytest.mark.parametrize("n", [97, 300, 515])
-def test_fused_ensemble_is_bitwise_the_sequence_of_terms(n):
+@pytest.mark.parametrize("engine", [1, 0])
+@pytest.mark.parametrize("n", [97, 300, 515, 1024])
+def test_fused_ensemble_is_bitwise_the_sequence_of_terms(n, engine):
     """mcgra_ensemble (one pass over the n x n result) == mcgra_tiles_to_dense followed by mcgra_gram_accumulate /
     mcgra_dense_add / mcgra_label_accumulate in the same order, bit for bit (topology_attack.py:300-322)."""
     import ctypes
@@ -111,6 +123,10 @@ def test_fused_ensemble_is_bitwise_the_sequence_of_terms(n):
             e.labels = ptr(t)
     ea.nterms = len(spec)
     fused = torch.full((n, n), float("nan"), device="cuda")
-    call("mcgra_ensemble", ptr(tiles), n, ctypes.byref(ea), ptr(fused), n, 0, n, st)
-    torch.cuda.synchronize()
+    N.lib().mcgra_set_engine(5, engine)      # 1: one CTA per block pair (symmetric terms once), 0: one CTA per block
+    try:
+        call("mcgra_ensemble", ptr(tiles), n, ctypes.byref(ea), ptr(fused), n, 0, n, st)
+        torch.cuda.synchronize()
+    finally:
+        N.lib().mcgra_set_engine(5, 1)
     assert torch.equal(fused, seq)
