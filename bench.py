@@ -551,6 +551,9 @@ def run_native(a):
                            + ", amortised over K",
                "auc": auc, "ap": ap}
 
+    parity_mgpu = None
+    if world > 1 and not a.no_parity:
+        parity_mgpu = mgpu_parity(device, world)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -575,12 +578,46 @@ def run_native(a):
            "iter_bytes_algorithmic": 52.0 * P, "hbm_frac_whole_iter": 52.0 * P / world / (ms / K * 1e-3) / 1e9 / hbm,
            "loss_first_last": [float(losses[0]), float(losses[-1])], "parity_large": parity_large,
            "tf32_tflops_measured": extra.get("tf32_tflops")}
+    if parity_mgpu is not None:
+        out["parity_mgpu"] = parity_mgpu
     if a.profile == "B":
         out["dense_flops_per_iter_useful"] = (8.0 if w_active(PROFILE_W, 0) else 6.0) * float(n) ** 3
     if world == 1 and not a.no_cpu:
         out["cpu_baseline"] = cpu_baseline(a, threads=os.cpu_count())
         out["same_config_baseline"] = same_config_baseline(a, device)
     print(json.dumps(out))
+
+
+def mgpu_parity(device, world):
+    """Untimed, N > 1: the sharded attack of THIS process group (tile-row shards, row-band finalisation, sharded AUC / AP)
+    against single-GPU golden fixtures generated from the unmodified reference (tests/golden/attack_*.npz,
+    tests/golden/make_golden.py): per-iteration loss, final n x n result, and the sharded AUC / AP against the
+    single-process kernel on the gathered matrix.  The full list of cases is tests/mgpu_check.py."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from mcgra_b200 import metrics
+    out = {"world": world, "cases": {}}
+    ok = True
+    got = d = None
+    for case in ("mse_all_n150", "mse_budget_n150", "hsic_B_n150"):
+        d = np.load(os.path.join(ROOT, "tests", "golden", f"attack_{case}.npz"))
+        got = helpers.run_native_case(d, device=str(device))
+        e_loss = float(np.max(np.abs(got["loss"] - d["loss"]) / np.abs(d["loss"])))
+        e_adj = float(np.max(np.abs(got["modified_adj"] - d["modified_adj"])))
+        out["cases"][case] = {"rel_loss": e_loss, "max_dadj": e_adj}
+        ok = ok and e_loss < 1e-4 and e_adj < 2e-3
+    mdl = got["model"]
+    n = int(d["labels"].shape[0])
+    ee = np.argwhere(np.triu(d["adj"], 1) > 0)
+    auc_s, ap_s = metrics.auc_ap_from_edges_sharded(mdl.modified_adj, mdl.modified_adj_rows[0], n, ee)
+    auc_f, ap_f = metrics.auc_ap_from_edges(torch.from_numpy(got["modified_adj"]).to(device), ee)
+    out["auc_ap_sharded"] = [auc_s, ap_s]
+    out["auc_ap_gathered"] = [auc_f, ap_f]
+    ok = ok and abs(auc_s - auc_f) < 1e-12 and abs(ap_s - ap_f) < 1e-12
+    out["ok"] = bool(ok)
+    out["tolerances"] = "rel_loss < 1e-4, max_dadj < 2e-3, sharded AUC / AP equal to the gathered value"
+    return out
 
 
 def cpu_problem(n, f, c, seed=15):
