@@ -153,12 +153,20 @@ def test_fold_persistent_engine_multi_tile(eng, density, grid, wset):
     finally:
         N.lib().mcgra_set_engine(1, 100)
         N.lib().mcgra_set_engine(1, DEFAULT_ENGINE[1])
-    # (not bit-equal: the degree row sums and the norm term are accumulated with float / double atomics in tile order; when
-    #  the budget binds, a bisection decision at the 1e-5 bracket can flip on such a difference and shift mu by < 1e-5)
-    tol = 5e-6 if density > 1.0 else 3e-5
-    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6 if density > 1.0 else 1e-5)
-    assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < tol
-    np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-5, atol=tol)
+    # (not bit-equal: the degree row sums and the norm term are accumulated with float / double atomics in tile order.  When
+    #  the budget binds, a bisection decision at the 1e-5 bracket can flip on such a difference -- run to run, with either
+    #  engine: the atomics' order is not fixed -- and shift mu, i.e. EVERY free entry, by up to 1e-5 per iteration: up to
+    #  4e-5 in x after the 4 iterations, ~1e-4 relative in the row sums that normalise the next forward pass.  The
+    #  budget-binding cases therefore get the tolerances of the oracle comparison (test_multi_tile_matches_oracle); a wrong
+    #  kernel is off by O(lr) = 1e-2.)
+    if density > 1.0:
+        np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)
+        assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-6
+        np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-5, atol=5e-6)
+    else:
+        np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-4)
+        assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 1e-4
+        np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-3, atol=1e-3)
 
 
 @pytest.mark.parametrize("grid", [5, 0])
