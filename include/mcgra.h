@@ -75,8 +75,9 @@ int mcgra_version(void);
  *                           projected view, 0 otherwise [default]
  *   which 5 = mcgra_ensemble: 0 one CTA per 64 x 64 block, 1 one CTA per block PAIR (I, J) / (J, I) when the full matrix is
  *                           written (symmetric terms evaluated once), 0 for row bands [default]
- *   which 6 = mcgra_auc_ap: 0 1024-sample search table, 1 the sorted positives (or the largest sample that fits) in
- *                           the 227 KB of shared memory [default]
+ *   which 6 = mcgra_auc_ap: 0 1024-sample search table over the sorted positives, 1 the DISTINCT positive keys with their
+ *                           start indices (and a CTA-private histogram while they fit) in up to 224 KB of shared memory,
+ *                           sampled keys + one 32-byte block per segment beyond that [default]
  * Returns 0, or -1 for an unknown selector.                                                                            */
 int mcgra_set_engine(int which, int value);
 int64_t mcgra_tiles_in_rows(int tr0, int tr1);           /* number of tiles in tile rows [tr0,tr1) */
@@ -248,7 +249,9 @@ int mcgra_decode_to_tiles(const float* zhat, int64_t n, int tr0, int tr1, float*
  * (dot_product_decode2, :421-467): variant 0 sigmoid(relu(g - I)), 1 relu(g - I),
  * 2 relu(g/rownorm_i - I) (rownorm = ||row i of ZZ^T||, given), 3 plain g (gcn_parameterized.py:406-416),
  * 4 relu(g) with a zero diagonal (the symmetric expansion of dot_product_decode: get_modified_adj, :365-379, 414-419,
- * used when the row band of an ensemble is computed on a rank that does not hold the mirrored tiles).              */
+ * used when the row band of an ensemble is computed on a rank that does not hold the mirrored tiles).
+ * The sigmoid of variant 0 is evaluated as 1 / (1 + 2^(-v log2 e)) on the MUFU ex2 / rcp units (~2e-7 relative; v >= 0),
+ * with the same definition in mcgra_ensemble.                                                                       */
 int mcgra_gram_accumulate(const float* Z, int d, int64_t n, int variant, const float* rownorm,
                           float* out, int64_t ld, int64_t row0, int64_t row1, void* stream);
 /* out[i,j] += (labels[i]==labels[j])                                                                */
@@ -461,8 +464,8 @@ int mcgra_softmax_rows(const float* em, const float* Wl, const float* bl, int64_
 int mcgra_softmax_chain(const float* gp, const float* p, const float* Wl, int64_t n, int c, float* demd, void* stream);
 
 /* ---- AUC / AP (main.metric_pool, main.py:66-75; gcn_parameterized.py:55-65) ----
- * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU,
- * every negative is ranked against them; exact integer counts => sklearn's trapezoid AUC with ties, and
+ * scores [N] fp32, labels [N] uint8 (non-zero = positive).  The positives' keys are radix-sorted on the GPU and
+ * reduced to their distinct values; every negative is ranked against them; exact integer counts => sklearn's trapezoid AUC with ties, and
  * sklearn's average precision.  npos_max bounds the number of positives (workspace size).
  * out: device double[4] = {auc, ap, npos, nneg}.                                                     */
 int64_t mcgra_auc_workspace_bytes(int64_t N, int64_t npos_max);
