@@ -56,9 +56,9 @@ def main():
     above = int((S > hi).sum().item())
     print(json.dumps({"npos": npos, "pos_min": lo, "pos_max": hi, "entries_below_all_pos": below, "entries_above_all_pos": above,
                       "distinct_pos_scores": int(torch.unique(ps).numel())}), flush=True)
-    for name, eng, dbg in (("tab (default)", 1, 0), ("tab, no histogram", 1, 1), ("tab, no search", 1, 2),
-                           ("tab, neither", 1, 3), ("tab, private hist w/o warp aggregation", 1, 4),
-                           ("1024-sample kernel", 0, 0)):
+    # (the logs under profiles/r02_auc_ablation.txt also list "no search" / "private hist w/o warp aggregation" variants:
+    #  developer knobs of the intermediate kernels, removed again)
+    for name, eng, dbg in (("tab (default)", 1, 0), ("tab, no histogram", 1, 1), ("1024-sample kernel", 0, 0)):
         N.lib().mcgra_set_engine(6, eng)
         N.lib().mcgra_set_engine(6, 100 + dbg)
         t, r = timed(lambda: metrics.roc_auc_ap(S, lab, npos_max=npos))
