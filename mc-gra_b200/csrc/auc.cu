@@ -112,14 +112,6 @@ __global__ void k_compact_pos(const float* __restrict__ scores, const uint8_t* _
   }
 }
 
-__device__ __forceinline__ int64_t lower_bound(const uint32_t* a, int64_t n, uint32_t k) {
-  int64_t lo = 0, hi = n;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (a[mid] < k) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 __device__ __forceinline__ int64_t upper_bound(const uint32_t* a, int64_t n, uint32_t k) {
   int64_t lo = 0, hi = n;
   while (lo < hi) {
@@ -244,18 +236,6 @@ k_unique_pos(const uint32_t* __restrict__ pos, unsigned long long* __restrict__ 
     __syncthreads();
   }
   if (threadIdx.x == 0) { Cidx[carry] = (uint32_t)npos; counter[3] = (unsigned long long)carry; }
-}
-
-// number of table entries below k (uniform trip count: depends on ntab only)
-__device__ __forceinline__ int tab_lower(const uint32_t* tab, int ntab, uint32_t k) {
-  if (ntab <= 0) return 0;
-  int base = 0, len = ntab;
-  while (len > 1) {
-    const int half = len >> 1;
-    base += (tab[base + half - 1] < k) ? half : 0;
-    len -= half;
-  }
-  return base + ((tab[base] < k) ? 1 : 0);
 }
 
 // Sampled mode with <= 3 distinct keys per sample: segment t -> one aligned 32-byte block
