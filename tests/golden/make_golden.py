@@ -144,6 +144,8 @@ def run_attack_case(name, n, f, c, measure, weights, lr_exp, epochs, dataset="co
                 (labels[:, None] == labels[None, :]).astype(np.float32))      # main.py:440-450
         os.chdir(td)
         torch.Tensor.backward = rec_backward
+        if eps != 0:      # adding_noise (:474-478) draws torch.randn_like(n x n) once per iteration from the global stream
+            torch.manual_seed(seed + 1000)
         try:
             model.attack(args, None, 10 ** lr_exp, 0, weight_sup, wp, feature_adj, 0, 0, 0,
                          None, None, np.arange(min(8, n)), adj_t, X, np.zeros((n, n), np.float32), labels,
@@ -167,6 +169,8 @@ def run_attack_case(name, n, f, c, measure, weights, lr_exp, epochs, dataset="co
         auc=np.float64(auc(fpr, tpr)), ap=np.float64(average_precision_score(real, pred)),
         **{k: v for k, v in W.items()},
     )
+    if eps != 0:
+        out["noise_seed"] = np.int64(seed + 1000)
     np.savez_compressed(os.path.join(HERE, f"attack_{name}.npz"), **out)
     print(f"[golden] attack_{name}: n={n} measure={measure} loss[0..2]={losses[:3]} auc={out['auc']:.5f} "
           f"ap={out['ap']:.5f} budget={num_edges} sum_x={xs[-1].sum():.3f}")
@@ -358,6 +362,9 @@ def main():
              lr_exp=-2, epochs=5, dataset="brazil", x0_scale=0.3),
         dict(name="mse_sub_n90", n=90, f=20, c=3, measure="MSELoss", weights=PROFILE_A, lr_exp=-2, epochs=5, nlabel=0.6,
              dataset="usair", use=(False, False, True)),
+        # --eps != 0 (adding_noise, :165 / :474-478): un-symmetrised n x n Gaussian noise on the expanded estimate, every term
+        # downstream sees the noisy clamped matrix.  Oracle-only fixture (the native attack() raises for eps != 0).
+        dict(name="mse_eps_n37", n=37, f=24, c=4, measure="MSELoss", weights=ALLW, lr_exp=-2, epochs=5, eps=0.05, x0_scale=0.4),
         # --measure KDE (README Cora K={X,Y}: --w1=1000 --w6=0.01 --lr=-3 --useY, plus the other terms): utils.MutualInformation
         # hard-codes device='cuda:0' for its bins (utils.py:990-991); the shim below drops that keyword on this CPU-only image
         dict(name="kde_n90", n=90, f=20, c=3, measure="KDE", weights={1: 1000, 2: 500, 6: 0.01, 7: 1.0, 9: 50.0, 10: 20.0},

@@ -94,3 +94,35 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "iterations/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_attack_with_noise_or_other_depth_fails_loudly():
+    """--eps != 0 and --nlayers != 2 are not built natively: the public call must raise, never fall back to a
+    torch / CPU path.  Both guards sit in front of any device work, so this runs without a GPU."""
+    import numpy as np
+    import pytest
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from mcgra_b200.models.gcn import GCN, embedding_GCN
+    from mcgra_b200.topology_attack import PGDAttack
+    d = np.load(os.path.join(ROOT, "tests", "golden", "attack_mse_eps_n37.npz"))
+    n = int(d["labels"].shape[0])
+    victim, emb = helpers.make_models(d, torch.device("cpu"))
+    args = helpers.make_args(d)
+    assert args.eps != 0
+    model = PGDAttack(model=victim, embedding=emb, H_A=torch.from_numpy(d["H_A2"]), Y_A=torch.from_numpy(d["Y_A"]),
+                      nnodes=n, loss_type="CE", device="cpu")
+    call = lambda: model.attack(args, None, 1e-2, 0, 1.0, tuple(d["weights"]), torch.from_numpy(d["feature_adj"]), 0, 0, 0,
+                                None, None, None, torch.from_numpy(d["adj"].astype(np.float32)), d["X"],
+                                np.zeros((n, n), np.float32), d["labels"], d["idx_attack"], 10 ** 9, 0, epochs=1)
+    with pytest.raises(NotImplementedError, match="eps"):
+        call()
+    args.eps = 0.0
+    f, c = d["X"].shape[1], int(d["Wl"].shape[0])
+    deep = GCN(nfeat=f, nclass=c, nhid=16, nlayer=3, dropout=0.5, weight_decay=5e-4, device="cpu")
+    model3 = PGDAttack(model=deep, embedding=embedding_GCN(nfeat=f, nhid=16, nlayer=3, device="cpu"),
+                       H_A=torch.from_numpy(d["H_A2"]), Y_A=torch.from_numpy(d["Y_A"]), nnodes=n, loss_type="CE", device="cpu")
+    model = model3
+    with pytest.raises(NotImplementedError, match="layer"):
+        call()

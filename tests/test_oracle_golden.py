@@ -104,6 +104,8 @@ def test_auc_ap_sklearn_semantics(fn):
 def test_attack_loop_matches_reference(case):
     d = np.load(os.path.join(GOLDEN, f"attack_{case}.npz"))
     prob, cfg = O.problem_from_npz(d)
+    if "noise_seed" in d.files:      # eps != 0: adding_noise draws torch.randn_like(n x n) once per iteration (:474-478)
+        torch.manual_seed(int(d["noise_seed"]))
     res = O.attack(prob, cfg, int(d["epochs"]), x0=T(d["x0"]))
     ref_loss = d["loss"]
     got = np.array(res["loss"])
