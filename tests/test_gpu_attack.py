@@ -156,17 +156,17 @@ def test_fold_persistent_engine_multi_tile(eng, density, grid, wset):
     # (not bit-equal: the degree row sums and the norm term are accumulated with float / double atomics in tile order.  When
     #  the budget binds, a bisection decision at the 1e-5 bracket can flip on such a difference -- run to run, with either
     #  engine: the atomics' order is not fixed -- and shift mu, i.e. EVERY free entry, by up to 1e-5 per iteration: up to
-    #  4e-5 in x after the 4 iterations, ~1e-4 relative in the row sums that normalise the next forward pass.  The
-    #  budget-binding cases therefore get the tolerances of the oracle comparison (test_multi_tile_matches_oracle); a wrong
-    #  kernel is off by O(lr) = 1e-2.)
+    #  4e-5 in x after the 4 iterations, ~1e-4 relative in the row sums that normalise the next forward pass and about as
+    #  much in the loss.  The budget-binding cases are therefore a regression guard at 10x that (a wrong kernel is off by
+    #  O(lr) = 1e-2 in x after one Adam step); parity proper is held against the oracle / goldens by the tests above.)
     if density > 1.0:
         np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)
         assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 5e-6
         np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-5, atol=5e-6)
     else:
-        np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-4)
-        assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 1e-4
-        np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-3)
+        assert np.max(np.abs(np.stack(a["x_iters"]) - np.stack(b["x_iters"]))) < 4e-4
+        np.testing.assert_allclose(a["modified_adj"], b["modified_adj"], rtol=2e-3, atol=2e-3)
 
 
 @pytest.mark.parametrize("grid", [5, 0])
