@@ -653,7 +653,8 @@ def cpu_baseline(a, threads, iters=2):
     dt = time.perf_counter() - t0
     v = iters / dt
     scale = (wl["n"] / n) ** 3
-    return {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port",
+    return {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port", "sample_n": n,
+            "value_scaled_to_workload": v / scale,       # n^3 extrapolation of the sample rate to the bench size
             "sample": f"oracle port of the reference loop at n={n} (f={wl['f']}, c={wl['c']}), {iters} iterations incl. "
                       f"the reference's in-loop bookkeeping; the reference algorithm is O(n^3)/iteration and needs "
                       f">0.9 TB at n={wl['n']} (not runnable) -- n^3 extrapolation to n={wl['n']}: {v / scale:.3e} it/s"}
@@ -686,7 +687,8 @@ def run_reference(a):
                       "same_config_as_native_arm": n == wl["n"],
                       "note": "the reference's dense algorithm is O(n^3) time / >0.9 TB at n=65536; the native arm reports a "
                               "same-size comparison in `same_config_baseline` (n=2708, all three arms in one run)"},
-           "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample, "sample_n": n,
+                            "value_scaled_to_workload": v / (wl["n"] / n) ** 3},
            "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
